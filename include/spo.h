@@ -1,0 +1,218 @@
+/*
+ * libspo -- C-ABI of the B200-native SafePO hot path (rollout forward -> dual GAE ->
+ * policy / critic update).  Plain pointers and sizes only; every pointer marked
+ * "device" is a CUDA device pointer owned by the caller (PyTorch tensors in the shipped
+ * host code); the library never allocates, frees or retains memory past a call.
+ *
+ * Each entry point names the reference code it replaces (paths relative to the
+ * PKU-Alignment/Safe-Policy-Optimization checkout).
+ *
+ * Conventions
+ *   - return value: 0 (SPO_OK) or a negative spo_status; message via spo_last_error()
+ *     (thread-local).  Nothing aborts or throws across the boundary.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All
+ *     work is asynchronous on that stream; asynchronous CUDA errors surface at the next
+ *     call or at spo_sync_check().
+ *   - there is no CPU fallback: unsupported dimensions return SPO_ERR_UNSUPPORTED.
+ *
+ * Packed parameter layout (fp32, one buffer of spo_param_count() floats):
+ *     actor         : log_std[A] W1[H*D] b1[H] W2[H*H] b2[H] W3[A*H] b3[A]
+ *     reward critic : W1[H*D] b1[H] W2[H*H] b2[H] W3[H] b3[1]
+ *     cost critic   : (same)
+ *   matrices are row-major [out][in] exactly as torch.nn.Linear stores them, so the actor
+ *   slice is the flat vector of get_flat_params_from(policy.actor)
+ *   (safepo/single_agent/cpo.py:70-78; log_std first) and nn.Parameter views into the
+ *   buffer reproduce actor.state_dict() (safepo/common/model.py:73-76).
+ *   Adam moments use the same layout; step counters are 3 int32 (actor, reward, cost).
+ *
+ * Rollout storage is env-major: element (env n, step t) of a per-step scalar lives at
+ * n*T + t, rows of obs/act at (n*T + t)*D / *A -- the order buffer.get() produces
+ * (safepo/common/buffer.py:149-153).
+ */
+#ifndef SPO_H_
+#define SPO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPO_VERSION 100
+
+typedef enum spo_status {
+  SPO_OK = 0,
+  SPO_ERR_INVALID_ARG = -1,
+  SPO_ERR_UNSUPPORTED = -2,
+  SPO_ERR_CUDA = -3,
+  SPO_ERR_NCCL = -4
+} spo_status;
+
+/* Network dimensions.  hidden must be 64 (two tanh layers of 64, the reference's
+ * default_cfg for every MuJoCo task: ppo_lag.py:46, cpo.py:48, focops.py:48). */
+typedef struct spo_dims {
+  int obs_dim; /* D, 1..128 */
+  int act_dim; /* A, 1..8   */
+  int hidden;  /* H, 64     */
+} spo_dims;
+
+/* Env-major rollout arrays of one epoch, all device pointers (buffer.py:53-73). */
+typedef struct spo_rollout {
+  float *obs, *act;                  /* [N,T,D], [N,T,A] */
+  float *reward, *cost;              /* [N,T] */
+  float *value_r, *value_c, *logp;   /* [N,T] */
+  uint8_t* seg_end;                  /* [N,T] 1 where a path closes (ppo_lag.py:200) */
+  float *boot_r, *boot_c;            /* [N,T] bootstrap value of the path closing at t */
+  int num_envs, steps;               /* N, T */
+} spo_rollout;
+
+int spo_version(void);
+const char* spo_last_error(void);
+int spo_sync_check(void* stream);
+
+/* offsets (in floats) into the packed buffer; out arrays may be NULL.
+ * net: 0 actor, 1 reward critic, 2 cost critic. */
+int spo_param_count(const spo_dims* d, int* actor, int* critic, int* total);
+int spo_param_offsets(const spo_dims* d, int net, int* log_std, int* w1, int* b1, int* w2, int* b2, int* w3, int* b3);
+
+/* ---- F1/F2: ActorVCritic.step (safepo/common/model.py:149-170) fused with
+ * VectorizedOnPolicyBuffer.store (safepo/common/buffer.py:84-95) ------------------------
+ * obs [n,D] device.  eps [n,A] device or NULL (NULL: in-kernel Philox4x32-10 keyed by
+ * (seed, offset), perf mode).  deterministic!=0: act = mean.  Outputs act [n,A], logp
+ * [n], v_r [n], v_c [n] (device, any may be NULL).  If `store` is not NULL the kernel
+ * also writes obs/act/logp/value_r/value_c of every env into slot t of the rollout
+ * arrays (n must equal store->num_envs). */
+int spo_policy_step(const spo_dims* d, const float* params, const float* obs, const float* eps,
+                    uint64_t seed, uint64_t offset, int deterministic, int n,
+                    float* act, float* logp, float* v_r, float* v_c,
+                    const spo_rollout* store, int t, void* stream);
+
+/* Reward/cost critic values only (the bootstrap forwards of ppo_lag.py:204-213). */
+int spo_critic_values(const spo_dims* d, const float* params, const float* obs, int n,
+                      float* v_r, float* v_c, void* stream);
+
+/* Slot-t bookkeeping of the rollout loop (ppo_lag.py:187-234):
+ * writes reward/cost [n] into column t and derives seg_end/boot from the env flags:
+ *   seg_end = epoch_end | terminated | truncated
+ *   boot    = terminated ? 0 : truncated ? V(final_obs) : V(next_obs)
+ * terminated/truncated: uint8 [n] device.  next_v_*: V(next_obs) [n] (used only when
+ * epoch_end).  final_v_*: V(final_observation) [n] or NULL when no env truncated. */
+int spo_store_transition(const spo_rollout* r, int t, const float* reward, const float* cost,
+                         const uint8_t* terminated, const uint8_t* truncated, int epoch_end,
+                         const float* next_v_r, const float* next_v_c,
+                         const float* final_v_r, const float* final_v_c, void* stream);
+
+/* ---- G1: finish_path -> calculate_adv_and_value_targets -> discount_cumsum
+ * (safepo/common/buffer.py:97-140,167-201) for every path of every env in one launch.
+ * delta in fp32 ((r + gamma*v') - v, unfused), carry in fp64, outputs rounded to fp32.
+ * disc_r = gamma*lam, disc_c = gamma*lam_c as doubles (buffer.py:199).
+ * mode 0: warp-shuffle reverse affine scan (re-associates the fp64 carry);
+ * mode 1: sequential recurrence per env, bit-exact with the reference. */
+int spo_gae_dual(const float* reward, const float* cost, const float* value_r, const float* value_c,
+                 const uint8_t* seg_end, const float* boot_r, const float* boot_c,
+                 float gamma, double disc_r, double disc_c,
+                 float* adv_r, float* adv_c, float* tgt_r, float* tgt_c,
+                 int num_envs, int steps, int mode, void* stream);
+
+/* ---- G3 + L1: buffer.get() statistics (buffer.py:154-160) and the Lagrange mix
+ * (ppo_lag.py:280-281).  stats (device, 4 doubles) = {sum adv_r, sum adv_r^2, sum adv_c,
+ * count}; spo_adv_stats overwrites them (all-reduce them across ranks before apply for
+ * global statistics).  apply:
+ *   a = (adv_r - mean) / (std_unbiased + 1e-8)   (if standardize_r)
+ *   c = adv_c - mean_c                           (if standardize_c)
+ *   mixed = (a - lam*c) / lam_plus_1
+ * a/c overwrite adv_r/adv_c in place; mixed may be NULL. */
+int spo_adv_stats(const float* adv_r, const float* adv_c, int64_t count, double* stats, void* stream);
+int spo_adv_apply(float* adv_r, float* adv_c, int64_t count, const double* stats,
+                  int standardize_r, int standardize_c, float lam, float lam_plus_1,
+                  float* mixed, void* stream);
+
+/* ---- U1/U3/C5: the minibatch update loop (ppo_lag.py:297-336, focops.py:309-357,
+ * cpo.py:543-571) as ONE persistent launch per pass: for each of n_steps minibatches
+ * gather `batch` rows by perm, forward+backward of the three nets, critic L2 term,
+ * joint grad-norm clip, three Adam steps.  No host round trip inside. */
+typedef enum spo_loss_kind {
+  SPO_LOSS_PPO_CLIP = 0,   /* ppo_lag.py:315-319 */
+  SPO_LOSS_FOCOPS = 1,     /* focops.py:323-337 ([B,1]x[B] broadcast semantics) */
+  SPO_LOSS_CRITIC_ONLY = 2 /* cpo.py:543-571, trpo_lag.py:466-494 */
+} spo_loss_kind;
+
+typedef struct spo_batch {
+  const float *obs, *act, *logp;      /* [S,D], [S,A], [S] */
+  const float *target_r, *target_c;   /* [S] */
+  const float* adv;                   /* [S] mixed advantage (NULL for critic-only) */
+  const float *old_mean, *old_std;    /* [S,A] each, FOCOPS only (focops.py:298-299) */
+  int64_t count;                      /* S */
+} spo_batch;
+
+typedef struct spo_hparams {
+  float lr_actor, lr_reward, lr_cost;
+  float beta1, beta2, adam_eps;       /* 0.9, 0.999, 1e-8 */
+  float max_grad_norm;                /* 40.0, ppo_lag.py:325 */
+  float critic_l2;                    /* 0.001, ppo_lag.py:310-314 (0 disables) */
+  float clip_lo, clip_hi;             /* 0.8, 1.2 (ppo_lag.py:318) */
+  float focops_lam, focops_kl;        /* 1.5 (focops.py:45), target_kl */
+  float value_coef;                   /* 1.0 (2.0 with use_value_coefficient) */
+} spo_hparams;
+
+/* Device control block shared by the update and KL kernels (zero it per epoch). */
+typedef struct spo_update_ctrl {
+  double loss_sum[3];   /* sums over minibatches of loss_r, loss_c, loss_pi */
+  double kl_sum;        /* scratch of the KL pass */
+  long long steps;      /* minibatch steps taken */
+  int stop;             /* set when kl > target_kl (ppo_lag.py:347-348) */
+  int passes;           /* Train/StopIter */
+  float final_kl;       /* Train/KL */
+  unsigned int ticket;  /* internal */
+  float extra_sumsq;    /* squared norm of stale .grad that joins the joint clip (cpo.py:562) */
+  int pad_;
+} spo_update_ctrl;
+
+/* perm: int64 device, n_steps*batch indices (the last step may be short: total =
+ * perm_len).  adam_m/adam_v: packed like params.  adam_t: 3 int32 device step counters.
+ * If ctrl->stop is already set the launch returns without touching anything. */
+int spo_pg_update(const spo_dims* d, float* params, float* adam_m, float* adam_v, int* adam_t,
+                  const spo_batch* data, const int64_t* perm, int64_t perm_len, int batch,
+                  spo_loss_kind kind, const spo_hparams* hp, spo_update_ctrl* ctrl, void* stream);
+
+/* ---- U2: full-batch actor passes -------------------------------------------------------
+ * spo_actor_forward: mean [S,A] of policy.actor(obs) (old_distribution, ppo_lag.py:277).
+ * spo_actor_kl: KL(N(old_mean, exp(old_log_std)) || N(mean(obs), exp(log_std))) with
+ *   reduce 0: .sum(-1).mean() (ppo_lag.py:338-344)   reduce 1: .mean() over S*A (cpo.py:489-491)
+ *   result -> ctrl->final_kl, ctrl->passes += 1, ctrl->stop |= (kl > target_kl).
+ *   Skipped (no-op) when ctrl->stop is already set. */
+int spo_actor_forward(const spo_dims* d, const float* params, const float* obs, int64_t count,
+                      float* mean_out, void* stream);
+int spo_actor_kl(const spo_dims* d, const float* params, const float* obs, const float* old_mean,
+                 const float* old_log_std, int64_t count, int reduce, float target_kl,
+                 spo_update_ctrl* ctrl, void* stream);
+
+/* ---- C1-C4: trust-region pieces (cpo.py:70-157,353-519; trpo_lag.py:363-442) -----------
+ * All vectors are actor-flat [P_a] device fp32 (log_std first).
+ * spo_surrogate_grad: loss = mean(ratio*adv) (cpo.py:356-359) and d loss / d theta.
+ *   out_loss: device float.  grad may be NULL (loss only).
+ * spo_fvp: (H + damping I) v with H the Hessian of mean_{S*A} KL(old||new) at new=old
+ *   (cpo.py:132-157), evaluated in closed form (one JVP + one VJP through the mean MLP).
+ * spo_linesearch_eval: with theta = params actor slice (already set to the trial
+ *   point) writes out[0]=mean(ratio*adv_a), out[1]=mean(ratio*adv_b) (adv_b may be NULL),
+ *   out[2]=mean_{S*A} KL(old||new)  (cpo.py:475-491). */
+int spo_surrogate_grad(const spo_dims* d, const float* params, const float* obs, const float* act,
+                       const float* logp_old, const float* adv, int64_t count,
+                       float* out_loss, float* grad, void* stream);
+int spo_fvp(const spo_dims* d, const float* params, const float* obs, int64_t count,
+            const float* v, float damping, float* out, void* stream);
+int spo_linesearch_eval(const spo_dims* d, const float* params, const float* obs, const float* act,
+                        const float* logp_old, const float* adv_a, const float* adv_b,
+                        const float* old_mean, const float* old_log_std, int64_t count,
+                        float* out3, void* stream);
+/* Conjugate gradient (cpo.py:81-106) fully on device: 1 + iters FVPs, all dots/axpys and
+ * the residual_tol break evaluated on device (no host sync).  work: 4*P_a floats + 8. */
+int spo_conjugate_gradient(const spo_dims* d, const float* params, const float* obs, int64_t count,
+                           const float* b, int iters, float damping, float residual_tol, float eps,
+                           float* x, float* work, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPO_H_ */

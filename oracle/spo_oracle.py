@@ -635,3 +635,30 @@ def trpo_policy_update(pol, data, advantage, target_kl=0.01, cg_iters=15, search
     set_flat_params(pol, theta_old + step_frac * step_dir)
     return {"g": g, "x": x, "xHx": xHx, "alpha": alpha, "step_dir": step_dir, "step_frac": step_frac,
             "acceptance": acceptance, "kl": final_kl, "loss_actor": loss_pi.item()}
+
+
+# --------------------------------------------------------------------------------------
+# vectorised-over-envs restatement of gae_dual for full-size checks (same sequential
+# arithmetic per env: separate fp32 mul/add/sub for delta, separate fp64 mul/add for the
+# carry -- numpy ufuncs never fuse), validated against gae_dual in tests.
+# --------------------------------------------------------------------------------------
+
+def gae_dual_np(rew, cost, v_r, v_c, seg_end, boot_r, boot_c, gamma=0.99, lam=0.95, lam_c=0.95):
+    rew, cost, v_r, v_c, boot_r, boot_c = (np.asarray(x, dtype=np.float32) for x in (rew, cost, v_r, v_c, boot_r, boot_c))
+    seg = np.asarray(seg_end).astype(bool).copy()
+    N, T = rew.shape
+    seg[:, -1] = True
+    g32 = np.float32(gamma)
+    outs = [np.zeros((N, T), dtype=np.float32) for _ in range(4)]
+    for (r, v, boot, l, oa, ot) in ((rew, v_r, boot_r, lam, outs[0], outs[2]), (cost, v_c, boot_c, lam_c, outs[1], outs[3])):
+        disc = gamma * l
+        acc = np.zeros(N, dtype=np.float64)
+        for t in range(T - 1, -1, -1):
+            end = seg[:, t]
+            vnext = np.where(end, boot[:, t], v[:, t + 1] if t + 1 < T else boot[:, t]).astype(np.float32)
+            delta = ((r[:, t] + g32 * vnext).astype(np.float32) - v[:, t]).astype(np.float32)
+            d64 = delta.astype(np.float64)
+            acc = np.where(end, d64, d64 + disc * acc)
+            oa[:, t] = acc.astype(np.float32)
+            ot[:, t] = (acc + v[:, t].astype(np.float64)).astype(np.float32)
+    return [torch.from_numpy(o) for o in outs]

@@ -1,0 +1,698 @@
+// The minibatch update loop as one persistent launch per pass.
+//
+// Reference: safepo/single_agent/ppo_lag.py:297-336 (PPO-Lag), focops.py:309-357
+// (FOCOPS), cpo.py:543-571 / trpo_lag.py:466-494 (critic regression).  Per minibatch:
+// forward of the three nets, losses, backward, critic L2 term, ONE joint grad-norm clip
+// over all three nets (ppo_lag.py:325), three Adam steps.
+//
+// Mapping: a thread-block cluster of 3 CTAs (4 when the driver refuses a cluster of 3:
+// the 4th CTA only joins the barriers), one net per CTA -- actor / reward critic / cost
+// critic.  Each CTA keeps its net's weights (both orientations), the Adam moments and
+// all activations of the 64-row tile in shared memory / registers for the whole pass;
+// the only traffic per step is the gather of the minibatch rows (cp.async, prefetched one
+// tile ahead) and one float per CTA exchanged through distributed shared memory for the
+// joint gradient norm.  Weights and moments touch HBM once per launch.
+//
+// The chain of steps is strictly sequential (each step needs the weights of the previous
+// one), so this kernel is latency-bound by construction: what is optimised is
+// microseconds per step, not bandwidth.
+#include <cooperative_groups.h>
+#include "spo_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int AUXW = 28;       // per-row side data: act[8] | logp adv tgt _ | old_mean[8] | old_std[8]
+constexpr int AUX_LOGP = 8, AUX_ADV = 9, AUX_TGT = 10, AUX_OMEAN = 12, AUX_OSTD = 20;
+constexpr float kLogSqrt2Pi = 0.91893853320467274178f;
+
+struct UpdArgs {
+  float *params, *adam_m, *adam_v;
+  int* adam_t;
+  spo_batch data;
+  const int64_t* perm;
+  int64_t perm_len;
+  int batch, kind, D, A;
+  spo_hparams hp;
+  spo_update_ctrl* ctrl;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// One Adam step on a scalar, mirroring torch's _multi_tensor_adam op order:
+//   m = lerp(m, g, 1-b1) (fused mul-add);  v = v*b2 + ((1-b2)*g)*g;
+//   denom = sqrt(v)/sqrt(bc2) + eps;  p = p + (step_size*m)/denom,  step_size = -lr/bc1.
+struct AdamK {
+  float w1, b2, w2, bc2s, eps, ss;  // w1 = 1-b1, w2 = 1-b2
+};
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, const AdamK& k) {
+  m = fmaf(k.w1, __fsub_rn(g, m), m);
+  v = __fadd_rn(__fmul_rn(v, k.b2), __fmul_rn(__fmul_rn(k.w2, g), g));
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), k.bc2s), k.eps);
+  return __fadd_rn(p, __fdiv_rn(__fmul_rn(k.ss, m), denom));
+}
+
+// small parameters of a net in the order b1[64] b2[64] w3[O*64] b3[O] log_std[A(actor)]
+struct SmallMap {
+  int O, A_ls;  // A_ls = A for the actor, 0 for critics
+  __device__ int count() const { return 2 * SPO_HID + O * SPO_HID + O + A_ls; }
+  // global offset (within packed buffer) of small param i
+  __device__ int goff(const SpoNetOff& o, int i) const {
+    if (i < SPO_HID) return o.b1 + i;
+    i -= SPO_HID;
+    if (i < SPO_HID) return o.b2 + i;
+    i -= SPO_HID;
+    if (i < O * SPO_HID) return o.w3 + i;
+    i -= O * SPO_HID;
+    if (i < O) return o.b3 + i;
+    return o.log_std + (i - O);
+  }
+};
+
+template <int NT1>
+__global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  spo_update_ctrl* ctrl = a.ctrl;
+  if (*reinterpret_cast<volatile int*>(&ctrl->stop)) return;  // whole cluster takes this branch together
+
+  const int D = a.D, A = a.A, Dp = spo_pad4(D), ldx = spo_ld(D);
+  const bool idle = rank >= 3;
+  const int net = idle ? 2 : static_cast<int>(rank);
+  const bool is_actor = (net == 0) && !idle;
+  const bool active = !idle && !(is_actor && a.kind == SPO_LOSS_CRITIC_ONLY);
+  const SpoNetOff off = spo_net_off(D, A, net);
+  const int O = off.out;
+  const SmallMap sm{O, is_actor ? A : 0};
+  const int SP = sm.count();
+
+  // ---- shared memory carve-up ----
+  SpoNetSmem w;
+  float* p = spo_carve_net(smem, D, O, true, w);
+  float* log_std = p; p += 8;
+  float* msmall = p;  p += 672;
+  float* vsmall = p;  p += 672;
+  float* gsmall = p;  p += 672;
+  float* xbuf[2];
+  xbuf[0] = p; p += SPO_ROWS * ldx;
+  xbuf[1] = p; p += SPO_ROWS * ldx;
+  float* auxbuf[2];
+  auxbuf[0] = p; p += SPO_ROWS * AUXW;
+  auxbuf[1] = p; p += SPO_ROWS * AUXW;
+  float* h1 = p;  p += SPO_ROWS * SPO_LDH;
+  float* h2 = p;  p += SPO_ROWS * SPO_LDH;   // becomes dz1 during backward
+  float* dz2 = p; p += SPO_ROWS * SPO_LDH;
+  float* y = p;   p += SPO_ROWS * SPO_MAX_ACT;
+  float* dy = p;  p += SPO_ROWS * SPO_MAX_ACT;
+  float* dls = p; p += SPO_ROWS * SPO_MAX_ACT;   // per-row d loss / d log_std
+  float* red = p; p += 64;                       // block-reduction scratch
+  float* xchg = p; p += 4;                       // [parity] CTA grad sumsq, read by peers through DSMEM
+  float* m1s = nullptr; float* v1s = nullptr;    // W1 moments in smem when they do not fit registers
+  if (NT1 > 1) { m1s = p; p += Dp * SPO_LDH; v1s = p; p += Dp * SPO_LDH; }
+  float* dz1 = h2;
+
+  const int tps = (a.batch + SPO_ROWS - 1) / SPO_ROWS;                    // tiles per step
+  const int64_t n_steps = (a.perm_len + a.batch - 1) / a.batch;
+  const int64_t n_tiles = n_steps * tps;
+
+  // ---- one-time loads ----
+  if (!idle) {
+    spo_load_net(a.params, off, D, w, tid, SPO_THREADS);
+    for (int i = tid; i < SP; i += SPO_THREADS) {
+      msmall[i] = a.adam_m[sm.goff(off, i)];
+      vsmall[i] = a.adam_v[sm.goff(off, i)];
+    }
+    if (is_actor && tid < A) log_std[tid] = a.params[off.log_std + tid];
+    for (int i = tid; i < 2 * SPO_ROWS * ldx; i += SPO_THREADS) xbuf[0][i] = 0.f;       // xbuf[0],[1] contiguous
+    for (int i = tid; i < 2 * SPO_ROWS * AUXW; i += SPO_THREADS) auxbuf[0][i] = 0.f;
+  }
+  // thread tiles: W2[j0..+3][k0..+3]; W1 tile i covers j0 = 4*(id&15), k0 = 4*(id>>4), id = tid + 256*i
+  const int j0 = (tid & 15) * 4, k0 = (tid >> 4) * 4;
+  float mW2[4][4], vW2[4][4], mW1[NT1 == 1 ? 4 : 1][4], vW1[NT1 == 1 ? 4 : 1][4];
+  if (active) {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int g = off.w2 + (j0 + mi) * SPO_HID + k0 + ni;
+        mW2[mi][ni] = a.adam_m[g];
+        vW2[mi][ni] = a.adam_v[g];
+      }
+    if (NT1 == 1) {
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const bool ok = (k0 + ni) < D;
+          const int g = off.w1 + (j0 + mi) * D + k0 + ni;
+          mW1[mi][ni] = ok ? a.adam_m[g] : 0.f;
+          vW1[mi][ni] = ok ? a.adam_v[g] : 0.f;
+        }
+    } else {
+      for (int i = tid; i < Dp * SPO_HID; i += SPO_THREADS) {
+        const int k = i >> 6, j = i & 63;
+        const bool ok = k < D;
+        m1s[k * SPO_LDH + j] = ok ? a.adam_m[off.w1 + j * D + k] : 0.f;
+        v1s[k * SPO_LDH + j] = ok ? a.adam_v[off.w1 + j * D + k] : 0.f;
+      }
+    }
+  }
+  const int t0 = idle ? 0 : a.adam_t[net];
+  double b1pow = pow(static_cast<double>(a.hp.beta1), static_cast<double>(t0));
+  double b2pow = pow(static_cast<double>(a.hp.beta2), static_cast<double>(t0));
+  const float lr = (net == 0) ? a.hp.lr_actor : (net == 1 ? a.hp.lr_reward : a.hp.lr_cost);
+  const float extra_sumsq = (is_actor && a.kind == SPO_LOSS_CRITIC_ONLY) ? ctrl->extra_sumsq : 0.f;
+  const float vcoef = (net == 1) ? a.hp.value_coef : 1.f;
+  const float reg = is_actor ? 0.f : __fmul_rn(vcoef, __fmul_rn(a.hp.critic_l2, 2.f));
+
+  // gather + async copy of one tile (64 rows) into buffer b
+  auto prefetch = [&](int64_t q, int b) {
+    if (!active || q >= n_tiles) return;
+    const int64_t step = q / tps;
+    const int sub = static_cast<int>(q - step * tps);
+    const int64_t first = step * a.batch + sub * SPO_ROWS;
+    int64_t rs = a.perm_len - step * a.batch;
+    if (rs > a.batch) rs = a.batch;
+    int rows = static_cast<int>(rs) - sub * SPO_ROWS;
+    rows = rows < 0 ? 0 : (rows > SPO_ROWS ? SPO_ROWS : rows);
+    float* x = xbuf[b];
+    float* aux = auxbuf[b];
+    if ((D & 3) == 0) {
+      const int c4 = D >> 2;
+      for (int i = tid; i < rows * c4; i += SPO_THREADS) {
+        const int r = i / c4, c = i - r * c4;
+        const int64_t g = a.perm[first + r];
+        cp_async16(x + r * ldx + 4 * c, a.data.obs + g * D + 4 * c);
+      }
+    } else {
+      for (int i = tid; i < rows * D; i += SPO_THREADS) {
+        const int r = i / D, c = i - r * D;
+        const int64_t g = a.perm[first + r];
+        cp_async4(x + r * ldx + c, a.data.obs + g * D + c);
+      }
+    }
+    if (is_actor) {
+      const int per = A + 2 + (a.kind == SPO_LOSS_FOCOPS ? 2 * A : 0);
+      for (int i = tid; i < rows * per; i += SPO_THREADS) {
+        const int r = i / per, c = i - r * per;
+        const int64_t g = a.perm[first + r];
+        float* dst = aux + r * AUXW;
+        if (c < A) cp_async4(dst + c, a.data.act + g * A + c);
+        else if (c == A) cp_async4(dst + AUX_LOGP, a.data.logp + g);
+        else if (c == A + 1) cp_async4(dst + AUX_ADV, a.data.adv + g);
+        else if (c < 2 * A + 2) cp_async4(dst + AUX_OMEAN + (c - A - 2), a.data.old_mean + g * A + (c - A - 2));
+        else cp_async4(dst + AUX_OSTD + (c - 2 * A - 2), a.data.old_std + g * A + (c - 2 * A - 2));
+      }
+    } else {
+      const float* tg = (net == 1) ? a.data.target_r : a.data.target_c;
+      for (int r = tid; r < rows; r += SPO_THREADS) cp_async4(aux + r * AUXW + AUX_TGT, tg + a.perm[first + r]);
+    }
+    // rows beyond the valid range must read as zeros (only the final, short step has any)
+    if (rows < SPO_ROWS) {
+      for (int i = tid; i < (SPO_ROWS - rows) * ldx; i += SPO_THREADS) x[rows * ldx + i] = 0.f;
+      for (int i = tid; i < (SPO_ROWS - rows) * AUXW; i += SPO_THREADS) aux[rows * AUXW + i] = 0.f;
+    }
+  };
+
+  __syncthreads();
+  prefetch(0, 0);
+  cp_async_commit();
+
+  // gradient accumulators (persist across the tiles of one step)
+  float gW2[4][4], gW1[NT1][4][4];
+  spo_zero(gW2);
+#pragma unroll
+  for (int i = 0; i < NT1; ++i) spo_zero(gW1[i]);
+  for (int i = tid; i < SP; i += SPO_THREADS) gsmall[i] = 0.f;
+  double acc_loss = 0.0;        // thread 0: sum over steps of this net's logged loss
+  float step_loss = 0.f;        // thread 0: loss numerator of the current step (sum over its tiles)
+  float step_aux0 = 0.f, step_aux1 = 0.f;  // FOCOPS: sum(ratio*adv), sum(mask)
+  int64_t step_idx = 0;
+
+  for (int64_t q = 0; q < n_tiles; ++q) {
+    const int cur = static_cast<int>(q & 1);
+    const int64_t step = q / tps;
+    const int sub = static_cast<int>(q - step * tps);
+    int64_t rs64 = a.perm_len - step * a.batch;
+    if (rs64 > a.batch) rs64 = a.batch;
+    const int rows_step = static_cast<int>(rs64);
+    int rows = rows_step - sub * SPO_ROWS;
+    rows = rows < 0 ? 0 : (rows > SPO_ROWS ? SPO_ROWS : rows);
+    const bool last_tile = (sub == tps - 1);
+    const float inv_b = __fdiv_rn(1.f, static_cast<float>(rows_step));
+
+    cp_async_wait_all();
+    __syncthreads();                       // tile q landed; buffers of tile q-1 are free
+    prefetch(q + 1, cur ^ 1);
+    cp_async_commit();
+
+    const float* x = xbuf[cur];
+    const float* aux = auxbuf[cur];
+
+    if (active) {
+      // ---------------- forward ----------------
+      spo_hidden_fwd(x, ldx, Dp, w.w1t, w.b1, h1, tid);
+      __syncthreads();
+      spo_hidden_fwd(h1, SPO_LDH, SPO_HID, w.w2t, w.b2, h2, tid);
+      __syncthreads();
+      spo_out_fwd(h2, w.w3, w.b3, O, y, SPO_MAX_ACT, tid, SPO_THREADS);
+      __syncthreads();
+
+      // ---------------- loss and d loss / d output, one thread per row ----------------
+      float part0 = 0.f, part1 = 0.f, part2 = 0.f;
+      if (tid < SPO_ROWS) {
+        const int r = tid;
+        const bool valid = r < rows;
+        const float* ax = aux + r * AUXW;
+        if (!is_actor) {
+          const float dv = __fsub_rn(y[r * SPO_MAX_ACT], ax[AUX_TGT]);
+          part0 = valid ? __fmul_rn(dv, dv) : 0.f;
+          dy[r * SPO_MAX_ACT] = valid ? __fmul_rn(__fmul_rn(__fmul_rn(2.f, dv), inv_b), vcoef) : 0.f;
+        } else {
+          float lp = 0.f, kl = 0.f;
+          float dmu_lp[SPO_MAX_ACT], dls_lp[SPO_MAX_ACT], dmu_kl[SPO_MAX_ACT], dls_kl[SPO_MAX_ACT];
+#pragma unroll
+          for (int j = 0; j < SPO_MAX_ACT; ++j) {
+            dmu_lp[j] = dls_lp[j] = dmu_kl[j] = dls_kl[j] = 0.f;
+            if (j < A) {
+              const float mean = y[r * SPO_MAX_ACT + j];
+              const float std = expf(log_std[j]);
+              const float var = __fmul_rn(std, std);
+              const float diff = __fsub_rn(ax[j], mean);
+              const float d2 = __fmul_rn(diff, diff);
+              const float term = __fsub_rn(__fsub_rn(__fdiv_rn(-d2, __fmul_rn(2.f, var)), logf(std)), kLogSqrt2Pi);
+              lp = (j == 0) ? term : __fadd_rn(lp, term);
+              dmu_lp[j] = __fdiv_rn(diff, var);
+              dls_lp[j] = __fsub_rn(__fdiv_rn(d2, var), 1.f);
+              if (a.kind == SPO_LOSS_FOCOPS) {
+                // KL(new || old), torch _kl_normal_normal(p=new, q=old)
+                const float os = ax[AUX_OSTD + j], om = ax[AUX_OMEAN + j];
+                const float sr = __fdiv_rn(std, os);
+                const float vr = __fmul_rn(sr, sr);
+                const float dm = __fdiv_rn(__fsub_rn(mean, om), os);
+                const float t1 = __fmul_rn(dm, dm);
+                const float klj = __fmul_rn(0.5f, __fsub_rn(__fsub_rn(__fadd_rn(vr, t1), 1.f), logf(vr)));
+                kl = (j == 0) ? klj : __fadd_rn(kl, klj);
+                dmu_kl[j] = __fdiv_rn(dm, os);
+                dls_kl[j] = __fsub_rn(vr, 1.f);
+              }
+            }
+          }
+          const float ratio = expf(__fsub_rn(lp, ax[AUX_LOGP]));
+          const float adv = ax[AUX_ADV];
+          if (a.kind == SPO_LOSS_PPO_CLIP) {
+            const float s1 = __fmul_rn(ratio, adv);
+            const float s2 = __fmul_rn(fminf(fmaxf(ratio, a.hp.clip_lo), a.hp.clip_hi), adv);
+            part0 = valid ? -fminf(s1, s2) : 0.f;
+            // d(-mean(min))/d logp = -(1/B) * adv * ratio where the unclipped branch is active
+            const float gl = (valid && s1 <= s2) ? -__fmul_rn(__fmul_rn(adv, ratio), inv_b) : 0.f;
+#pragma unroll
+            for (int j = 0; j < SPO_MAX_ACT; ++j) {
+              dy[r * SPO_MAX_ACT + j] = __fmul_rn(gl, dmu_lp[j]);
+              dls[r * SPO_MAX_ACT + j] = __fmul_rn(gl, dls_lp[j]);
+            }
+          } else {
+            // FOCOPS needs mean(mask) over the minibatch before gradients can be formed:
+            // stash per-row pieces, finish after the block reduction below.
+            const float mask = (valid && kl <= a.hp.focops_kl) ? 1.f : 0.f;
+            part0 = valid ? __fmul_rn(kl, mask) : 0.f;
+            part1 = valid ? __fmul_rn(ratio, adv) : 0.f;
+            part2 = mask;
+#pragma unroll
+            for (int j = 0; j < SPO_MAX_ACT; ++j) {
+              // first term: (1/B) * mask * d kl ; second term scaled later by mean(mask)
+              dy[r * SPO_MAX_ACT + j] = __fmul_rn(__fmul_rn(mask, inv_b), dmu_kl[j]);
+              dls[r * SPO_MAX_ACT + j] = __fmul_rn(__fmul_rn(mask, inv_b), dls_kl[j]);
+              y[r * SPO_MAX_ACT + j] = valid ? __fmul_rn(__fmul_rn(__fmul_rn(adv, ratio), inv_b), dmu_lp[j]) : 0.f;
+            }
+            // keep d logp / d log_std pieces in the (now free) aux row of the *current* buffer
+            float* axw = const_cast<float*>(ax);
+#pragma unroll
+            for (int j = 0; j < SPO_MAX_ACT; ++j)
+              if (j < A) axw[AUX_OMEAN + j] = valid ? __fmul_rn(__fmul_rn(__fmul_rn(adv, ratio), inv_b), dls_lp[j]) : 0.f;
+          }
+        }
+        part0 = spo_warp_sum(part0); part1 = spo_warp_sum(part1); part2 = spo_warp_sum(part2);
+        if (lane == 0) { red[wid * 4 + 0] = part0; red[wid * 4 + 1] = part1; red[wid * 4 + 2] = part2; }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        step_loss += red[0] + red[4];
+        step_aux0 += red[1] + red[5];
+        step_aux1 += red[2] + red[6];
+      }
+      if (is_actor && a.kind == SPO_LOSS_FOCOPS) {
+        // This formulation needs the whole minibatch in one tile (batch <= 64): mean(mask)
+        // and the per-row pieces are combined here.  (focops.py uses batch 64.)
+        const float mbar = __fmul_rn(__fadd_rn(red[2], red[6]), inv_b);
+        const float c2 = -__fmul_rn(__fdiv_rn(1.f, a.hp.focops_lam), mbar);
+        if (tid < SPO_ROWS) {
+          const int r = tid;
+          float* axw = const_cast<float*>(aux) + r * AUXW;
+#pragma unroll
+          for (int j = 0; j < SPO_MAX_ACT; ++j)
+            if (j < A) {
+              dy[r * SPO_MAX_ACT + j] = __fadd_rn(dy[r * SPO_MAX_ACT + j], __fmul_rn(c2, y[r * SPO_MAX_ACT + j]));
+              dls[r * SPO_MAX_ACT + j] = __fadd_rn(dls[r * SPO_MAX_ACT + j], __fmul_rn(c2, axw[AUX_OMEAN + j]));
+            }
+        }
+        __syncthreads();
+      }
+
+      // ---------------- backward ----------------
+      // (a) small grads of the output layer: dW3[o][k], db3[o], dlog_std[j]
+      for (int i = tid; i < O * SPO_HID + O + sm.A_ls; i += SPO_THREADS) {
+        float s = 0.f;
+        if (i < O * SPO_HID) {
+          const int o = i >> 6, k = i & 63;
+#pragma unroll 8
+          for (int r = 0; r < SPO_ROWS; ++r) s = fmaf(dy[r * SPO_MAX_ACT + o], h2[r * SPO_LDH + k], s);
+        } else if (i < O * SPO_HID + O) {
+          const int o = i - O * SPO_HID;
+          for (int r = 0; r < SPO_ROWS; ++r) s += dy[r * SPO_MAX_ACT + o];
+        } else {
+          const int j = i - O * SPO_HID - O;
+          for (int r = 0; r < SPO_ROWS; ++r) s += dls[r * SPO_MAX_ACT + j];
+        }
+        gsmall[2 * SPO_HID + i] += s;
+      }
+      // (b) dz2[r][k] = (sum_o dy[r][o] * w3[o][k]) * (1 - h2[r][k]^2)
+      {
+        const int r0 = (tid >> 4) * 4, kk = (tid & 15) * 4;
+#pragma unroll
+        for (int ri = 0; ri < 4; ++ri) {
+          const int r = r0 + ri;
+          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int o = 0; o < O; ++o) {
+            const float d = dy[r * SPO_MAX_ACT + o];
+            const float4 wv = *reinterpret_cast<const float4*>(w.w3 + o * SPO_HID + kk);
+            s.x = fmaf(d, wv.x, s.x); s.y = fmaf(d, wv.y, s.y); s.z = fmaf(d, wv.z, s.z); s.w = fmaf(d, wv.w, s.w);
+          }
+          const float4 h = *reinterpret_cast<const float4*>(h2 + r * SPO_LDH + kk);
+          s.x *= (1.f - h.x * h.x); s.y *= (1.f - h.y * h.y); s.z *= (1.f - h.z * h.z); s.w *= (1.f - h.w * h.w);
+          *reinterpret_cast<float4*>(dz2 + r * SPO_LDH + kk) = s;
+        }
+      }
+      __syncthreads();
+      // (c) dW2[j][k] += sum_r dz2[r][j] * h1[r][k];  db2[j] += sum_r dz2[r][j]
+      spo_tile_mma<false>(gW2, dz2, SPO_LDH, h1, SPO_LDH, j0, k0, SPO_ROWS);
+      if (tid < SPO_HID) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < SPO_ROWS; ++r) s += dz2[r * SPO_LDH + tid];
+        gsmall[SPO_HID + tid] += s;
+      }
+      // (d) dz1[r][k] = (sum_j dz2[r][j] * W2[j][k]) * (1 - h1[r][k]^2)   -> overwrites h2
+      {
+        float acc[4][4];
+        spo_zero(acc);
+        const int m0 = (tid & 15) * 4, n0 = (tid >> 4) * 4;   // m: input unit k, n: row r
+        spo_tile_mma<true>(acc, w.w2, SPO_LDH, dz2, SPO_LDH, m0, n0, SPO_HID);
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const float4 h = *reinterpret_cast<const float4*>(h1 + (n0 + ni) * SPO_LDH + m0);
+          float4 o4;
+          o4.x = acc[0][ni] * (1.f - h.x * h.x);
+          o4.y = acc[1][ni] * (1.f - h.y * h.y);
+          o4.z = acc[2][ni] * (1.f - h.z * h.z);
+          o4.w = acc[3][ni] * (1.f - h.w * h.w);
+          *reinterpret_cast<float4*>(dz1 + (n0 + ni) * SPO_LDH + m0) = o4;
+        }
+      }
+      __syncthreads();
+      // (e) dW1[j][k] += sum_r dz1[r][j] * x[r][k];  db1[j] += sum_r dz1[r][j]
+#pragma unroll
+      for (int i = 0; i < NT1; ++i) {
+        const int id = tid + i * SPO_THREADS;
+        const int tj = (id & 15) * 4, tk = (id >> 4) * 4;
+        if (tk < Dp) spo_tile_mma<false>(gW1[i], dz1, SPO_LDH, x, ldx, tj, tk, SPO_ROWS);
+      }
+      if (tid < SPO_HID) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < SPO_ROWS; ++r) s += dz1[r * SPO_LDH + tid];
+        gsmall[tid] += s;
+      }
+    }  // active
+
+    if (!last_tile) continue;   // next tile of the same step accumulates into the same gradients
+
+    // ---------------- joint gradient norm (cluster-wide), clip, Adam ----------------
+    float ss = 0.f, th2 = 0.f;
+    if (active) {
+      __syncthreads();  // gsmall complete
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const float th = w.w2[(j0 + mi) * SPO_LDH + k0 + ni];
+          const float g = fmaf(reg, th, gW2[mi][ni]);
+          gW2[mi][ni] = g;
+          ss = fmaf(g, g, ss);
+          th2 = fmaf(th, th, th2);
+        }
+#pragma unroll
+      for (int i = 0; i < NT1; ++i) {
+        const int id = tid + i * SPO_THREADS;
+        const int tj = (id & 15) * 4, tk = (id >> 4) * 4;
+        if (tk < Dp) {
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+              const float th = w.w1t[(tk + ni) * SPO_LDH + tj + mi];
+              const float g = fmaf(reg, th, gW1[i][mi][ni]);
+              gW1[i][mi][ni] = g;
+              ss = fmaf(g, g, ss);
+              th2 = fmaf(th, th, th2);
+            }
+        }
+      }
+      for (int i = tid; i < SP; i += SPO_THREADS) {
+        float th;
+        if (i < SPO_HID) th = w.b1[i];
+        else if (i < 2 * SPO_HID) th = w.b2[i - SPO_HID];
+        else if (i < 2 * SPO_HID + O * SPO_HID) th = w.w3[i - 2 * SPO_HID];
+        else if (i < 2 * SPO_HID + O * SPO_HID + O) th = w.b3[i - 2 * SPO_HID - O * SPO_HID];
+        else th = log_std[i - 2 * SPO_HID - O * SPO_HID - O];
+        const float g = fmaf(reg, th, gsmall[i]);
+        gsmall[i] = g;
+        ss = fmaf(g, g, ss);
+        th2 = fmaf(th, th, th2);
+      }
+      ss = spo_warp_sum(ss);
+      th2 = spo_warp_sum(th2);
+      if (lane == 0) { red[16 + wid] = ss; red[32 + wid] = th2; }
+      __syncthreads();
+    }
+    const int par = static_cast<int>(step_idx & 1);
+    if (tid == 0) {
+      float s = extra_sumsq, t2 = 0.f;
+      if (active) {
+        for (int i = 0; i < SPO_THREADS / 32; ++i) { s += red[16 + i]; t2 += red[32 + i]; }
+      }
+      xchg[par] = idle ? 0.f : s;
+      // logged loss of this step (ppo_lag.py:330-336): critics include the L2 term
+      if (active) {
+        float L;
+        if (!is_actor) L = fmaf(a.hp.critic_l2, t2, __fmul_rn(step_loss, inv_b));
+        else if (a.kind == SPO_LOSS_PPO_CLIP) L = __fmul_rn(step_loss, inv_b);
+        else L = __fsub_rn(__fmul_rn(step_loss, inv_b),
+                           __fmul_rn(__fmul_rn(__fdiv_rn(1.f, a.hp.focops_lam), __fmul_rn(step_aux0, inv_b)), __fmul_rn(step_aux1, inv_b)));
+        acc_loss += static_cast<double>(L);
+      }
+      step_loss = 0.f; step_aux0 = 0.f; step_aux1 = 0.f;
+    }
+    cluster.sync();
+    float total = 0.f;
+    {
+      const unsigned nblk = cluster.num_blocks();
+      for (unsigned b = 0; b < nblk; ++b) total += *cluster.map_shared_rank(xchg + par, b);
+    }
+    const float clip = fminf(__fdiv_rn(a.hp.max_grad_norm, __fadd_rn(sqrtf(total), 1e-6f)), 1.f);
+
+    if (active) {
+      b1pow *= static_cast<double>(a.hp.beta1);
+      b2pow *= static_cast<double>(a.hp.beta2);
+      AdamK k;
+      k.w1 = static_cast<float>(1.0 - static_cast<double>(a.hp.beta1));
+      k.b2 = a.hp.beta2;
+      k.w2 = static_cast<float>(1.0 - static_cast<double>(a.hp.beta2));
+      k.bc2s = static_cast<float>(sqrt(1.0 - b2pow));
+      k.eps = a.hp.adam_eps;
+      k.ss = static_cast<float>(-(static_cast<double>(lr) / (1.0 - b1pow)));
+      // W2 (natural + transposed images)
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int ia = (j0 + mi) * SPO_LDH + k0 + ni;
+          const float nw = adam_update(w.w2[ia], __fmul_rn(gW2[mi][ni], clip), mW2[mi][ni], vW2[mi][ni], k);
+          w.w2[ia] = nw;
+          w.w2t[(k0 + ni) * SPO_LDH + j0 + mi] = nw;
+          gW2[mi][ni] = 0.f;
+        }
+      // W1 (transposed image only)
+#pragma unroll
+      for (int i = 0; i < NT1; ++i) {
+        const int id = tid + i * SPO_THREADS;
+        const int tj = (id & 15) * 4, tk = (id >> 4) * 4;
+        if (tk < Dp) {
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+              const int ia = (tk + ni) * SPO_LDH + tj + mi;
+              const float g = __fmul_rn(gW1[i][mi][ni], clip);
+              if (NT1 == 1) {
+                w.w1t[ia] = adam_update(w.w1t[ia], g, mW1[mi][ni], vW1[mi][ni], k);
+              } else {
+                float m = m1s[ia], v = v1s[ia];
+                w.w1t[ia] = adam_update(w.w1t[ia], g, m, v, k);
+                m1s[ia] = m; v1s[ia] = v;
+              }
+              gW1[i][mi][ni] = 0.f;
+            }
+        }
+      }
+      for (int i = tid; i < SP; i += SPO_THREADS) {
+        float* th;
+        if (i < SPO_HID) th = w.b1 + i;
+        else if (i < 2 * SPO_HID) th = w.b2 + (i - SPO_HID);
+        else if (i < 2 * SPO_HID + O * SPO_HID) th = w.w3 + (i - 2 * SPO_HID);
+        else if (i < 2 * SPO_HID + O * SPO_HID + O) th = w.b3 + (i - 2 * SPO_HID - O * SPO_HID);
+        else th = log_std + (i - 2 * SPO_HID - O * SPO_HID - O);
+        float m = msmall[i], v = vsmall[i];
+        *th = adam_update(*th, __fmul_rn(gsmall[i], clip), m, v, k);
+        msmall[i] = m; vsmall[i] = v;
+        gsmall[i] = 0.f;
+      }
+    }
+    ++step_idx;
+    // the __syncthreads at the top of the next iteration orders these weight writes
+    // before the next forward
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- write back: weights, moments, step counters, logged losses ----
+  if (active) {
+    for (int i = tid; i < SPO_HID * D; i += SPO_THREADS) {
+      const int j = i / D, kx = i - j * D;
+      a.params[off.w1 + i] = w.w1t[kx * SPO_LDH + j];
+      if (NT1 > 1) {
+        a.adam_m[off.w1 + i] = m1s[kx * SPO_LDH + j];
+        a.adam_v[off.w1 + i] = v1s[kx * SPO_LDH + j];
+      }
+    }
+    for (int i = tid; i < SPO_HID * SPO_HID; i += SPO_THREADS)
+      a.params[off.w2 + i] = w.w2[(i >> 6) * SPO_LDH + (i & 63)];
+    for (int i = tid; i < SP; i += SPO_THREADS) {
+      float th;
+      if (i < SPO_HID) th = w.b1[i];
+      else if (i < 2 * SPO_HID) th = w.b2[i - SPO_HID];
+      else if (i < 2 * SPO_HID + O * SPO_HID) th = w.w3[i - 2 * SPO_HID];
+      else if (i < 2 * SPO_HID + O * SPO_HID + O) th = w.b3[i - 2 * SPO_HID - O * SPO_HID];
+      else th = log_std[i - 2 * SPO_HID - O * SPO_HID - O];
+      const int g = sm.goff(off, i);
+      a.params[g] = th;
+      a.adam_m[g] = msmall[i];
+      a.adam_v[g] = vsmall[i];
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int g = off.w2 + (j0 + mi) * SPO_HID + k0 + ni;
+        a.adam_m[g] = mW2[mi][ni];
+        a.adam_v[g] = vW2[mi][ni];
+        if (NT1 == 1 && (k0 + ni) < D) {
+          const int g1 = off.w1 + (j0 + mi) * D + k0 + ni;
+          a.adam_m[g1] = mW1[mi][ni];
+          a.adam_v[g1] = vW1[mi][ni];
+        }
+      }
+    if (tid == 0) {
+      a.adam_t[net] = t0 + static_cast<int>(n_steps);
+      const int slot = (net == 0) ? 2 : (net == 1 ? 0 : 1);
+      atomicAdd(&ctrl->loss_sum[slot], acc_loss);
+    }
+  }
+  if (rank == 1 && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->steps), static_cast<unsigned long long>(n_steps));
+  cluster.sync();  // no CTA may exit while a peer can still read its shared memory
+}
+
+size_t update_smem_bytes(int D, int A, int nt1) {
+  const int Dp = spo_pad4(D);
+  size_t f = spo_net_smem_floats(D, A > 1 ? A : 1, true) + 8 + 3 * 672 + 2 * SPO_ROWS * spo_ld(D) + 2 * SPO_ROWS * AUXW +
+             3 * SPO_ROWS * SPO_LDH + 3 * SPO_ROWS * SPO_MAX_ACT + 64 + 4 + (nt1 > 1 ? 2 * Dp * SPO_LDH : 0);
+  return f * sizeof(float);
+}
+
+template <int NT1>
+int launch_update(const UpdArgs& a, cudaStream_t stream) {
+  const size_t smem = update_smem_bytes(a.D, a.A, NT1);
+  SPO_REQUIRE(smem <= 227 * 1024, SPO_ERR_UNSUPPORTED, "spo_pg_update: obs_dim=%d needs %zu B of shared memory (> 227 KB)", a.D, smem);
+  static int cluster_size = 0;   // 3 preferred; 4 when the driver rejects a cluster of 3
+  SPO_CUDA_TRY(cudaFuncSetAttribute(spo_update_kernel<NT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const int cs = cluster_size ? cluster_size : (attempt == 0 ? 3 : 4);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cs);
+    cfg.blockDim = dim3(SPO_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, spo_update_kernel<NT1>, a);
+    if (e == cudaSuccess) { cluster_size = cs; return SPO_OK; }
+    if (cluster_size || attempt == 1) {
+      spo_set_error("spo_pg_update: launch failed (cluster=%d): %s", cs, cudaGetErrorString(e));
+      return SPO_ERR_CUDA;
+    }
+    (void)cudaGetLastError();  // clear and retry with a cluster of 4
+  }
+  return SPO_ERR_CUDA;
+}
+
+}  // namespace
+
+extern "C" int spo_pg_update(const spo_dims* d, float* params, float* adam_m, float* adam_v, int* adam_t,
+                             const spo_batch* data, const int64_t* perm, int64_t perm_len, int batch,
+                             spo_loss_kind kind, const spo_hparams* hp, spo_update_ctrl* ctrl, void* stream) {
+  int rc = spo_check_dims(d);
+  if (rc) return rc;
+  SPO_REQUIRE(params && adam_m && adam_v && adam_t && data && perm && hp && ctrl, SPO_ERR_INVALID_ARG, "spo_pg_update: null argument");
+  SPO_REQUIRE(batch > 0 && perm_len > 0 && perm_len <= data->count, SPO_ERR_INVALID_ARG,
+              "spo_pg_update: batch=%d perm_len=%lld count=%lld", batch, (long long)perm_len, (long long)data->count);
+  SPO_REQUIRE(kind >= SPO_LOSS_PPO_CLIP && kind <= SPO_LOSS_CRITIC_ONLY, SPO_ERR_INVALID_ARG, "spo_pg_update: kind=%d", (int)kind);
+  SPO_REQUIRE(data->obs && data->target_r && data->target_c, SPO_ERR_INVALID_ARG, "spo_pg_update: batch obs/targets null");
+  if (kind != SPO_LOSS_CRITIC_ONLY)
+    SPO_REQUIRE(data->act && data->logp && data->adv, SPO_ERR_INVALID_ARG, "spo_pg_update: actor loss needs act/logp/adv");
+  if (kind == SPO_LOSS_FOCOPS) {
+    SPO_REQUIRE(data->old_mean && data->old_std, SPO_ERR_INVALID_ARG, "spo_pg_update: FOCOPS needs old_mean/old_std");
+    SPO_REQUIRE(batch <= SPO_ROWS, SPO_ERR_UNSUPPORTED, "spo_pg_update: FOCOPS supports batch <= %d (got %d)", SPO_ROWS, batch);
+  }
+  UpdArgs a{};
+  a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.adam_t = adam_t;
+  a.data = *data; a.perm = perm; a.perm_len = perm_len; a.batch = batch; a.kind = kind;
+  a.D = d->obs_dim; a.A = d->act_dim; a.hp = *hp; a.ctrl = ctrl;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (spo_pad4(d->obs_dim) <= 64) return launch_update<1>(a, st);
+  return launch_update<2>(a, st);
+}

@@ -1,0 +1,131 @@
+"""VectorizedOnPolicyBuffer on device memory with the GAE / statistics done by libspo.
+
+Drop-in for safepo/common/buffer.py:24-164 of the reference (constructor arguments,
+``store`` / ``finish_path`` / ``get``, the 12 keys and the env-major order of ``get()``),
+re-designed for the GPU:
+
+* one contiguous ``[num_envs, size, ...]`` tensor per field instead of ``num_envs`` python
+  dicts -- ``get()`` is a zero-copy reshape (flat index = env*size + t, the order the
+  reference's ``torch.cat`` over envs produces, buffer.py:149-153);
+* ``finish_path`` only records where a path ends and its bootstrap values; the dual GAE
+  of *all* paths of *all* envs runs as one kernel inside ``get()`` (``spo_gae_dual``), then
+  ``spo_adv_stats`` / ``spo_adv_apply`` standardise (buffer.py:154-160);
+* the trainers bypass ``store`` entirely: ``ActorVCritic.step(..., store=(buf.struct, t))``
+  writes the transition from inside the forward kernel and ``store_transition`` applies
+  the segment rule of ppo_lag.py:199-234 for every env at once.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from safepo import _lib as L
+
+_SCALARS = ("reward", "cost", "done", "value_r", "value_c", "adv_r", "adv_c", "target_value_r", "target_value_c",
+            "log_prob")
+
+
+class VectorizedOnPolicyBuffer:
+    def __init__(self, obs_space, act_space, size, gamma=0.99, lam=0.95, lam_c=0.95,
+                 standardized_adv_r=True, standardized_adv_c=True, device="cpu", num_envs=1,
+                 gae_mode="scan"):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise L.SpoError("VectorizedOnPolicyBuffer lives in GPU memory: pass device='cuda:<id>' (no CPU path)")
+        self.num_envs, self.size = int(num_envs), int(size)
+        N, T = self.num_envs, self.size
+        self._device = device
+        self._gamma, self._lam, self._lam_c = gamma, lam, lam_c
+        self._standardized_adv_r, self._standardized_adv_c = standardized_adv_r, standardized_adv_c
+        self.gae_mode = {"scan": 0, "exact": 1}[gae_mode]
+        f32 = dict(dtype=torch.float32, device=device)
+        self.data = {"obs": torch.zeros((N, T, *obs_space.shape), **f32),
+                     "act": torch.zeros((N, T, *act_space.shape), **f32)}
+        for k in _SCALARS:
+            self.data[k] = torch.zeros((N, T), **f32)
+        self.seg_end = torch.zeros((N, T), dtype=torch.uint8, device=device)
+        self.boot_r = torch.zeros((N, T), **f32)
+        self.boot_c = torch.zeros((N, T), **f32)
+        self.adv_mixed = torch.zeros(N * T, **f32)
+        self.stats = torch.zeros(4, dtype=torch.float64, device=device)
+        self.ptr_list = [0] * N
+        self.path_start_idx_list = [0] * N
+        d = self.data
+        self.struct = L.Rollout(L.ptr(d["obs"]), L.ptr(d["act"]), L.ptr(d["reward"]), L.ptr(d["cost"]),
+                                L.ptr(d["value_r"]), L.ptr(d["value_c"]), L.ptr(d["log_prob"]), L.ptr(self.seg_end),
+                                L.ptr(self.boot_r), L.ptr(self.boot_c), N, T)
+
+    # ---- reference-compatible API ---------------------------------------------------------
+    @property
+    def buffers(self):
+        """Per-env views, shaped like the reference's list of dicts (buffer.py:53-73)."""
+        return [{k: v[i] for k, v in self.data.items()} for i in range(self.num_envs)]
+
+    def store(self, **data):
+        """Append one transition per env (buffer.py:84-95): data[key][i] goes to env i."""
+        t = self.ptr_list[0]
+        assert t < self.size, "Buffer overflow"
+        for key, value in data.items():
+            self.data[key][:, t] = value.to(self._device)
+        self.ptr_list = [t + 1] * self.num_envs
+
+    def finish_path(self, last_value_r=None, last_value_c=None, idx=0):
+        """Close the path of env ``idx`` at its current pointer (buffer.py:97-140); the GAE
+        itself is deferred to get()."""
+        end = self.ptr_list[idx] - 1
+        if end < self.path_start_idx_list[idx]:
+            return
+        self.seg_end[idx, end] = 1
+        self.boot_r[idx, end] = 0.0 if last_value_r is None else last_value_r.reshape(()).to(self._device)
+        self.boot_c[idx, end] = 0.0 if last_value_c is None else last_value_c.reshape(()).to(self._device)
+        self.path_start_idx_list[idx] = self.ptr_list[idx]
+
+    def store_transition(self, t, reward, cost, terminated, truncated, epoch_end, next_v=None, final_v=None):
+        """Vectorised slot-t bookkeeping of the rollout loop (ppo_lag.py:187-234): reward,
+        cost [N] float32; terminated, truncated [N] uint8; next_v / final_v = (v_r, v_c)."""
+        nr, nc = next_v if next_v is not None else (None, None)
+        fr, fc = final_v if final_v is not None else (None, None)
+        L.check(L.lib().spo_store_transition(C.byref(self.struct), int(t), L.ptr(reward), L.ptr(cost), L.ptr(terminated),
+                                             L.ptr(truncated), int(bool(epoch_end)), L.ptr(nr), L.ptr(nc), L.ptr(fr),
+                                             L.ptr(fc), L.stream()), "spo_store_transition")
+        self.ptr_list = [int(t) + 1] * self.num_envs
+
+    def compute_gae(self):
+        d = self.data
+        L.check(L.lib().spo_gae_dual(L.ptr(d["reward"]), L.ptr(d["cost"]), L.ptr(d["value_r"]), L.ptr(d["value_c"]),
+                                     L.ptr(self.seg_end), L.ptr(self.boot_r), L.ptr(self.boot_c),
+                                     float(self._gamma), float(self._gamma * self._lam), float(self._gamma * self._lam_c),
+                                     L.ptr(d["adv_r"]), L.ptr(d["adv_c"]), L.ptr(d["target_value_r"]),
+                                     L.ptr(d["target_value_c"]), self.num_envs, self.size, self.gae_mode, L.stream()),
+                "spo_gae_dual")
+
+    def finalize(self, lagrangian_multiplier=0.0, all_reduce=None):
+        """Statistics + standardisation (buffer.py:154-160) + Lagrange mix (ppo_lag.py:280-281).
+        ``all_reduce(stats)``: optional hook summing the 4 fp64 statistics across ranks."""
+        d = self.data
+        S = self.num_envs * self.size
+        lib = L.lib()
+        L.check(lib.spo_adv_stats(L.ptr(d["adv_r"]), L.ptr(d["adv_c"]), S, L.ptr(self.stats), L.stream()), "spo_adv_stats")
+        if all_reduce is not None:
+            all_reduce(self.stats)
+        lam = float(lagrangian_multiplier)
+        L.check(lib.spo_adv_apply(L.ptr(d["adv_r"]), L.ptr(d["adv_c"]), S, L.ptr(self.stats),
+                                  int(self._standardized_adv_r), int(self._standardized_adv_c), lam, lam + 1,
+                                  L.ptr(self.adv_mixed), L.stream()), "spo_adv_apply")
+        return self.adv_mixed
+
+    def get(self, lagrangian_multiplier=0.0, all_reduce=None):
+        """All collected data, env-major [S,...] views (buffer.py:142-164); resets pointers.
+        ``data["adv"]`` additionally holds (adv_r - lam*adv_c)/(lam+1)."""
+        self.compute_gae()
+        mixed = self.finalize(lagrangian_multiplier, all_reduce)
+        S = self.num_envs * self.size
+        out = {k: v.reshape(S, *v.shape[2:]) for k, v in self.data.items()}
+        out["adv"] = mixed
+        self.ptr_list = [0] * self.num_envs
+        self.path_start_idx_list = [0] * self.num_envs
+        return out
+
+    def reset_segments(self):
+        self.seg_end.zero_()

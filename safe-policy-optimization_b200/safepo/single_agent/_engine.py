@@ -1,0 +1,332 @@
+"""Shared machinery of the four single-agent trainers (ppo_lag, focops, cpo, trpo_lag).
+
+What the reference spells out four times as python loops
+(safepo/single_agent/ppo_lag.py:159-349 and the byte-identical rollout blocks of
+cpo/focops/trpo_lag) is expressed here once on top of the libspo kernels:
+
+* ``Rollout``  -- the rollout / bootstrap control loop R0 (ppo_lag.py:159-235), vectorised:
+  one fused step kernel per env step (forward + sample + log-prob + store), the segment
+  rule applied to all envs by ``spo_store_transition``, episode accounting on the host in
+  numpy exactly in the reference's env-index order.
+* ``PolicyGradientUpdate`` -- ppo_lag.py:276-348 / focops.py:280-366: per pass one
+  persistent ``spo_pg_update`` launch + one ``spo_actor_kl`` launch; early stop, logged
+  losses and StopIter live in a device control block that is read once.
+* ``TrustRegionUpdate`` -- cpo.py:351-571 / trpo_lag.py:358-494 on ``spo_surrogate_grad``,
+  ``spo_conjugate_gradient``, ``spo_fvp``, ``spo_linesearch_eval``.
+
+RNG modes (``args.rng``): ``host`` consumes torch's CPU generator draw-for-draw like the
+reference on CPU (action noise, the discarded bootstrap samples of ppo_lag.py:206/211, the
+two int64 draws per DataLoader pass) so a run is comparable number-for-number;
+``device`` uses the in-kernel Philox stream and device-side permutations.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import random
+import time
+from collections import deque
+
+import numpy as np
+import torch
+
+from safepo import _lib as L
+from safepo.common.buffer import VectorizedOnPolicyBuffer
+from safepo.common.lagrange import Lagrange
+from safepo.common.logger import EpochLogger
+from safepo.common.model import ActorVCritic
+
+
+# ---------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------
+
+def seed_all(seed):
+    """ppo_lag.py:69-72."""
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+def reference_order(S):
+    """Sample order of one ``for batch in DataLoader(shuffle=True)`` pass of the reference
+    (ppo_lag.py:283-294): the iterator draws a base seed, the RandomSampler a second one,
+    both from the global CPU generator; the order is randperm(S) under the second."""
+    torch.empty((), dtype=torch.int64).random_()
+    s = int(torch.empty((), dtype=torch.int64).random_().item())
+    g = torch.Generator()
+    g.manual_seed(s)
+    return torch.randperm(S, generator=g)
+
+
+class LinearDecay:
+    """LinearLR(start_factor=1, end_factor=0, total_iters=epochs) on one lr
+    (ppo_lag.py:105-111), with torch's chained update so the float is identical."""
+
+    def __init__(self, lr, epochs):
+        self.lr, self.epochs, self.last = lr, epochs, 0
+
+    def step(self):
+        self.last += 1
+        if self.last <= self.epochs:
+            self.lr = self.lr * (1.0 + (0.0 - 1.0) / (self.epochs * 1.0 + (self.last - 1) * (0.0 - 1.0)))
+        return self.lr
+
+
+class AdamState:
+    """Adam moments / step counters of the three nets, packed like the parameters."""
+
+    def __init__(self, policy):
+        dev = policy.flat.device
+        self.m = torch.zeros_like(policy.flat)
+        self.v = torch.zeros_like(policy.flat)
+        self.t = torch.zeros(3, dtype=torch.int32, device=dev)
+
+
+def make_ctrl(device):
+    return torch.zeros(L.CTRL_BYTES, dtype=torch.uint8, device=device)
+
+
+def read_ctrl(ctrl):
+    return ctrl.cpu().numpy().view(L.CTRL_DTYPE)[0]
+
+
+# ---------------------------------------------------------------------------------------
+# rollout
+# ---------------------------------------------------------------------------------------
+
+class Rollout:
+    def __init__(self, env, policy, buffer, logger, args, device):
+        self.env, self.policy, self.buffer, self.logger, self.args = env, policy, buffer, logger, args
+        self.device = device
+        N, D = args.num_envs, policy.obs_dim
+        self.N, self.D, self.A = N, D, policy.act_dim
+        self.host_rng = getattr(args, "rng", "device") == "host"
+        self.ep_ret, self.ep_cost, self.ep_len = np.zeros(N), np.zeros(N), np.zeros(N)
+        self.rew_deque, self.cost_deque, self.len_deque = deque(maxlen=50), deque(maxlen=50), deque(maxlen=50)
+        # pinned staging: one H2D per env step carries next_obs | reward | cost | terminated | truncated
+        self.stage_h = torch.empty(N * (D + 2) + N, dtype=torch.float32).pin_memory()
+        self.stage_d = torch.empty_like(self.stage_h, device=device)
+        self.flags_h = torch.empty(2 * N, dtype=torch.uint8).pin_memory()
+        self.flags_d = torch.empty(2 * N, dtype=torch.uint8, device=device)
+        self.final_h = torch.empty(N, D, dtype=torch.float32).pin_memory()
+        self.final_d = torch.empty(N, D, dtype=torch.float32, device=device)
+        self.act_h = torch.empty(N, self.A, dtype=torch.float32).pin_memory()
+        self.obs_d = torch.empty(N, D, dtype=torch.float32, device=device)
+        self.bytes_h2d = 0
+        self.bytes_d2h = 0
+        obs, _ = env.reset()
+        self.obs_d.copy_(torch.as_tensor(np.asarray(obs), dtype=torch.float32))
+
+    def _burn_bootstrap_draws(self, terminated, truncated, epoch_end):
+        """The reference obtains bootstrap values with policy.step(..., deterministic=False)
+        (ppo_lag.py:204-213): every such call discards one [A] normal draw."""
+        for idx in range(self.N):
+            if (epoch_end or terminated[idx] or truncated[idx]) and not terminated[idx]:
+                if epoch_end:
+                    torch.empty(self.A).normal_()
+                if truncated[idx]:
+                    torch.empty(self.A).normal_()
+
+    def run(self, T):
+        """One epoch of rollout (T steps of all envs).  Returns wall-clock seconds."""
+        t0 = time.time()
+        N, D, A = self.N, self.D, self.A
+        pol, buf, env, logger = self.policy, self.buffer, self.env, self.logger
+        stage_h, stage_d = self.stage_h, self.stage_d
+        obs_view = stage_d[: N * D].view(N, D)
+        rew_view = stage_d[N * D: N * D + N]
+        cost_view = stage_d[N * D + N: N * D + 2 * N]
+        for t in range(T):
+            eps = torch.empty(N, A).normal_().to(self.device, non_blocking=True) if self.host_rng else None
+            act, _, _, _ = pol.step(self.obs_d, eps=eps, store=(buf.struct, t))
+            self.act_h.copy_(act, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            self.bytes_d2h += N * A * 4
+            action = self.act_h.numpy()
+            next_obs, reward, cost, terminated, truncated, info = env.step(action.squeeze() if N == 1 else action)
+            self.ep_ret += reward
+            self.ep_cost += cost
+            self.ep_len += 1
+            terminated = np.asarray(terminated, dtype=bool)
+            truncated = np.asarray(truncated, dtype=bool)
+            sh = stage_h.numpy()
+            sh[: N * D] = np.asarray(next_obs, dtype=np.float32).reshape(-1)
+            sh[N * D: N * D + N] = reward
+            sh[N * D + N: N * D + 2 * N] = cost
+            fh = self.flags_h.numpy()
+            fh[:N] = terminated
+            fh[N:] = truncated
+            stage_d.copy_(stage_h, non_blocking=True)
+            self.flags_d.copy_(self.flags_h, non_blocking=True)
+            self.bytes_h2d += stage_h.numel() * 4 + 2 * N
+            epoch_end = t >= T - 1
+            any_trunc = bool(truncated.any())
+            final_v = None
+            if any_trunc:
+                fin = info.get("final_observation_dense")
+                if fin is None:  # gymnasium convention: object array of per-env arrays / None
+                    fin = np.stack([a if a is not None else np.zeros(D) for a in info["final_observation"]])
+                self.final_h.numpy()[:] = np.asarray(fin, dtype=np.float32)
+                self.final_d.copy_(self.final_h, non_blocking=True)
+                self.bytes_h2d += N * D * 4
+                final_v = pol.values(self.final_d)     # raw final observation, ppo_lag.py:209-213
+            next_v = pol.values(obs_view) if epoch_end else None
+            buf.store_transition(t, rew_view, cost_view, self.flags_d[:N], self.flags_d[N:], epoch_end, next_v, final_v)
+            self.obs_d.copy_(obs_view)
+            if self.host_rng and (epoch_end or terminated.any() or any_trunc):
+                self._burn_bootstrap_draws(terminated, truncated, epoch_end)
+            finished = np.nonzero(terminated | truncated)[0]
+            for idx in finished:               # ascending env index, ppo_lag.py:199,216-230
+                self.rew_deque.append(self.ep_ret[idx])
+                self.cost_deque.append(self.ep_cost[idx])
+                self.len_deque.append(self.ep_len[idx])
+                logger.store(**{"Metrics/EpRet": np.mean(self.rew_deque), "Metrics/EpCost": np.mean(self.cost_deque),
+                                "Metrics/EpLen": np.mean(self.len_deque)})
+                self.ep_ret[idx] = self.ep_cost[idx] = self.ep_len[idx] = 0.0
+                logger.logged = False
+        torch.cuda.current_stream().synchronize()
+        return time.time() - t0
+
+
+# ---------------------------------------------------------------------------------------
+# PPO-Lag / FOCOPS update
+# ---------------------------------------------------------------------------------------
+
+class PolicyGradientUpdate:
+    def __init__(self, policy, cfg, kind, epochs, host_rng, device, focops_lam=1.5):
+        self.policy, self.cfg, self.kind, self.host_rng, self.device = policy, cfg, kind, host_rng, device
+        self.adam = AdamState(policy)
+        self.sched = LinearDecay(3e-4, epochs)
+        self.ctrl = make_ctrl(device)
+        self.hp = L.HParams(3e-4, 3e-4, 3e-4, 0.9, 0.999, 1e-8, cfg["max_grad_norm"],
+                            0.001 if cfg.get("use_critic_norm", True) else 0.0, 0.8, 1.2, focops_lam, cfg["target_kl"],
+                            2.0 if cfg.get("use_value_coefficient", False) else 1.0)
+        self.old_mean = None
+        self.old_log_std = torch.zeros(policy.act_dim, dtype=torch.float32, device=device)
+        self.old_std_full = None
+        self.launches = 0
+
+    def run(self, data, perms=None, refresh_old=True):
+        """data: dict from buffer.get(lam).  Returns dict(stop_iter, kl, losses(3)).
+        refresh_old=False keeps the old distribution of the previous call (tests drive the
+        loop one minibatch at a time)."""
+        pol, cfg, lib = self.policy, self.cfg, L.lib()
+        S = data["obs"].shape[0]
+        d = pol.dims
+        if self.old_mean is None or self.old_mean.shape[0] != S:
+            self.old_mean = torch.empty(S, pol.act_dim, dtype=torch.float32, device=self.device)
+            refresh_old = True
+        if refresh_old:
+            L.check(lib.spo_actor_forward(C.byref(d), L.ptr(pol.flat), L.ptr(data["obs"]), S, L.ptr(self.old_mean), L.stream()),
+                    "spo_actor_forward")
+            self.old_log_std.copy_(pol.flat[: pol.act_dim])
+        old_std = None
+        if self.kind == L.LOSS_FOCOPS:
+            old_std = torch.exp(self.old_log_std).expand(S, pol.act_dim).contiguous()
+        batch = L.Batch(L.ptr(data["obs"]), L.ptr(data["act"]), L.ptr(data["log_prob"]), L.ptr(data["target_value_r"]),
+                        L.ptr(data["target_value_c"]), L.ptr(data["adv"]), L.ptr(self.old_mean), L.ptr(old_std), S)
+        self.hp.lr_actor = self.sched.lr
+        self.ctrl.zero_()
+        self.launches += 3
+        for it in range(cfg["learning_iters"]):
+            if perms is not None:
+                perm = perms[it].to(self.device)
+            elif self.host_rng:
+                perm = reference_order(S).to(self.device)
+            else:
+                perm = torch.randperm(S, device=self.device)
+            L.check(lib.spo_pg_update(C.byref(d), L.ptr(pol.flat), L.ptr(self.adam.m), L.ptr(self.adam.v), L.ptr(self.adam.t),
+                                      C.byref(batch), L.ptr(perm), S, cfg["batch_size"], self.kind, C.byref(self.hp),
+                                      L.ptr(self.ctrl), L.stream()), "spo_pg_update")
+            L.check(lib.spo_actor_kl(C.byref(d), L.ptr(pol.flat), L.ptr(data["obs"]), L.ptr(self.old_mean),
+                                     L.ptr(self.old_log_std), S, 0, cfg["target_kl"], L.ptr(self.ctrl), L.stream()),
+                    "spo_actor_kl")
+            self.launches += 2
+            if self.host_rng or perms is not None:
+                # the reference stops drawing permutations once KL trips: stay in lock-step with its RNG
+                if int(read_ctrl(self.ctrl)["stop"]):
+                    break
+        c = read_ctrl(self.ctrl)
+        steps = max(int(c["steps"]), 1)
+        self.sched.step()
+        return {"stop_iter": int(c["passes"]), "kl": float(c["final_kl"]),
+                "loss_r": c["loss_sum"][0] / steps, "loss_c": c["loss_sum"][1] / steps, "loss_pi": c["loss_sum"][2] / steps,
+                "steps": int(c["steps"])}
+
+
+# ---------------------------------------------------------------------------------------
+# generic main() of the PPO-family scripts
+# ---------------------------------------------------------------------------------------
+
+def make_env(args):
+    if getattr(args, "env", "synthetic") == "mujoco":
+        from safepo.common.env import make_sa_mujoco_env  # needs safety_gymnasium on the host
+        return make_sa_mujoco_env(num_envs=args.num_envs, env_id=args.task, seed=args.seed)
+    from safepo.common.synthetic_env import make_synthetic_env
+    return make_synthetic_env(args.num_envs, args.task, args.seed, episode_len=getattr(args, "episode_len", 1000))
+
+
+def run_policy_gradient(args, config, algo, env=None, max_epochs=None, quiet=False):
+    """main() of ppo_lag.py / focops.py.  Returns (policy, logger, per-epoch timing list)."""
+    seed_all(args.seed)
+    if args.device != "cuda":
+        raise L.SpoError("this build has no CPU path: run with --device cuda")
+    device = torch.device(f"cuda:{args.device_id}")
+    torch.cuda.set_device(device)
+    if env is None:
+        env, obs_space, act_space = make_env(args)
+    else:
+        obs_space, act_space = env.observation_space, env.action_space
+    T = args.steps_per_epoch // args.num_envs
+    epochs = args.total_steps // args.steps_per_epoch
+    policy = ActorVCritic(obs_space.shape[0], act_space.shape[0], config["hidden_sizes"]).to(device)
+    buffer = VectorizedOnPolicyBuffer(obs_space, act_space, size=T, device=device, num_envs=args.num_envs,
+                                      gamma=config["gamma"], gae_mode=getattr(args, "gae", "scan"))
+    lagrange = Lagrange(args.cost_limit, args.lagrangian_multiplier_init, args.lagrangian_multiplier_lr,
+                        lagrangian_upper_bound=2.0 if algo == "focops" else None)
+    dict_args = dict(vars(args))
+    dict_args.update(config)
+    logger = EpochLogger(args.log_dir, seed=str(args.seed), verbose=not quiet, use_tensorboard=not quiet)
+    logger.save_config(dict_args)
+    logger.setup_torch_saver(policy.actor)
+    logger.log("Start with training.")
+    host_rng = getattr(args, "rng", "device") == "host"
+    roll = Rollout(env, policy, buffer, logger, args, device)
+    upd = PolicyGradientUpdate(policy, config, L.LOSS_PPO_CLIP if algo == "ppo_lag" else L.LOSS_FOCOPS, epochs, host_rng, device)
+    timings = []
+    n_epochs = epochs if max_epochs is None else min(epochs, max_epochs)
+    for epoch in range(n_epochs):
+        t_roll = roll.run(T)
+        t1 = time.time()
+        ep_costs = logger.get_stats("Metrics/EpCost")
+        lagrange.update_lagrange_multiplier(ep_costs)
+        data = buffer.get(lagrange.lagrangian_multiplier)
+        res = upd.run(data)
+        buffer.reset_segments()
+        torch.cuda.synchronize()
+        t_upd = time.time() - t1
+        timings.append({"rollout": t_roll, "update": t_upd, "stop_iter": res["stop_iter"], "steps": res["steps"]})
+        logger.store(**{"Loss/Loss_reward_critic": res["loss_r"], "Loss/Loss_cost_critic": res["loss_c"],
+                        "Loss/Loss_actor": res["loss_pi"]})
+        if not logger.logged:
+            for k in ("Metrics/EpRet", "Metrics/EpCost", "Metrics/EpLen"):
+                logger.log_tabular(k)
+            logger.log_tabular("Train/Epoch", epoch + 1)
+            logger.log_tabular("Train/TotalSteps", (epoch + 1) * args.steps_per_epoch)
+            logger.log_tabular("Train/StopIter", res["stop_iter"])
+            logger.log_tabular("Train/KL", res["kl"])
+            logger.log_tabular("Train/LagragianMultiplier", lagrange.lagrangian_multiplier)
+            logger.log_tabular("Train/LR", upd.sched.lr)
+            for k in ("Loss/Loss_reward_critic", "Loss/Loss_cost_critic", "Loss/Loss_actor"):
+                logger.log_tabular(k)
+            logger.log_tabular("Time/Rollout", t_roll)
+            logger.log_tabular("Time/Update", t_upd)
+            logger.log_tabular("Time/Total", t_roll + t_upd)
+            logger.log_tabular("Value/RewardAdv", data["adv_r"].mean().item())
+            logger.log_tabular("Value/CostAdv", data["adv_c"].mean().item())
+            logger.dump_tabular()
+            if (epoch + 1) % 100 == 0 or epoch == 0:
+                logger.torch_save(itr=epoch)
+                logger.save_state({"Normalizer": getattr(env, "obs_rms", None)}, itr=epoch)
+    logger.close()
+    return policy, logger, timings, {"rollout": roll, "update": upd, "lagrange": lagrange, "buffer": buffer}

@@ -1,0 +1,127 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/spo.h
+declares, host logic (Lagrange, logger, minibatch order, synthetic env) against the golden
+fixtures.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from safepo import _lib as L
+    lib = L.lib()
+    header = open(os.path.join(ROOT, "include", "spo.h")).read()
+    declared = set(re.findall(r"\b(spo_[a-z_]+)\s*\(", header))
+    declared -= {"spo_status"}
+    assert declared, "no declarations parsed"
+    assert declared == set(L.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.spo_version() == 100
+
+
+def test_param_layout_matches_reference_counts():
+    from safepo import _lib as L
+    assert L.param_count(L.dims(60, 2)) == (8196, 8129, 24454)
+    assert L.param_count(L.dims(88, 2)) == (9988, 9921, 9988 + 2 * 9921)
+    assert L.param_count(L.dims(27, 8)) == (6480, 6017, 6480 + 2 * 6017)
+    o = L.param_offsets(L.dims(60, 2), 0)
+    assert (o["log_std"], o["w1"]) == (0, 2)                          # log_std first (cpo.py:70-78)
+    with pytest.raises(L.SpoError):
+        L.param_count(L.dims(60, 2, hidden=128))                      # no silent fallback
+
+
+def test_lagrange_bit_exact(golden):
+    from safepo.common.lagrange import Lagrange
+    g = golden("lagrange")["lagrange"]
+    lag = Lagrange(25.0, 0.001, 0.035)
+    got = []
+    for jc in g["jc"]:
+        lag.update_lagrange_multiplier(jc)
+        got.append(lag.lagrangian_multiplier)
+    assert got == g["lam"]
+    capped = Lagrange(25.0, 0.001, 0.035, lagrangian_upper_bound=2.0)
+    got = []
+    for _ in g["capped"]:
+        capped.update_lagrange_multiplier(500.0)
+        got.append(capped.lagrangian_multiplier)
+    assert got == g["capped"]
+    nan = Lagrange(25.0, 0.001, 0.035)
+    nan.update_lagrange_multiplier(float("nan"))
+    assert np.isnan(nan.lagrangian_multiplier)                        # reference quirk A3
+
+
+def test_reference_minibatch_order(golden):
+    from safepo.single_agent._engine import reference_order, LinearDecay
+    g = golden("dataloader")["dataloader"]
+    torch.manual_seed(g["seed"])
+    for want in g["orders"]:
+        assert torch.equal(reference_order(g["S"]), want)
+    s = LinearDecay(3e-4, 2)
+    assert s.step() == 0.00015 and s.step() == 0.0
+
+
+def test_logger_semantics(tmp_path):
+    from safepo.common.logger import EpochLogger
+    lg = EpochLogger(str(tmp_path / "exp" / "task" / "algo" / "run"), seed="0", verbose=False, use_tensorboard=False)
+    assert lg.get_stats("Metrics/EpCost") == 0.0                      # before the key was ever logged
+    lg.store(**{"Metrics/EpCost": 3.0})
+    lg.store(**{"Metrics/EpCost": 5.0})
+    assert lg.get_stats("Metrics/EpCost") == 0.0
+    lg.log_tabular("Metrics/EpCost")
+    lg.log_tabular("Train/Epoch", 1)
+    lg.dump_tabular()
+    assert np.isnan(lg.get_stats("Metrics/EpCost"))                   # nothing stored since (A3)
+    lg.store(**{"Metrics/EpCost": 7.0})
+    assert lg.get_stats("Metrics/EpCost") == 7.0
+    lg.close()
+    rows = open(tmp_path / "exp" / "task" / "algo" / "run" / "progress.csv").read().strip().splitlines()
+    assert rows[0] == "Metrics/EpCost,Train/Epoch" and rows[1].startswith("4.0,1")
+
+
+def test_synthetic_env_contract():
+    from safepo.common.synthetic_env import SyntheticVecEnv
+    env = SyntheticVecEnv(4, 6, 2, episode_len=5, seed=1, stagger=True, p_terminate=0.1)
+    obs, _ = env.reset()
+    assert obs.shape == (4, 6) and obs.dtype == np.float32
+    seen_final = False
+    for _ in range(40):
+        o, r, c, term, trunc, info = env.step(np.zeros((4, 2)))
+        assert o.shape == (4, 6) and r.shape == (4,) and term.dtype == bool and not (term & trunc).any()
+        if (term | trunc).any():
+            fin = info["final_observation"]
+            assert fin.dtype == object and all((f is not None) == d for f, d in zip(fin, term | trunc))
+            seen_final = True
+    assert seen_final
+    env2 = SyntheticVecEnv(4, 6, 2, episode_len=5, seed=1, stagger=True, p_terminate=0.1)
+    env2.reset()
+    assert np.array_equal(env2.step(np.zeros((4, 2)))[0], SyntheticVecEnv(4, 6, 2, episode_len=5, seed=1, stagger=True, p_terminate=0.1).step(np.zeros((4, 2)))[0])
+
+
+def test_gae_np_oracle_equals_path_oracle(golden):
+    from oracle import spo_oracle as O
+    for c in golden("gae")["gae_cases"]:
+        a = O.gae_dual(c["rew"], c["cost"], c["v_r"], c["v_c"], c["seg_end"], c["boot_r"], c["boot_c"], c["gamma"], c["lam"], c["lam_c"])
+        b = O.gae_dual_np(c["rew"], c["cost"], c["v_r"], c["v_c"], c["seg_end"], c["boot_r"], c["boot_c"], c["gamma"], c["lam"], c["lam_c"])
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+
+
+def test_no_cpu_fallback():
+    from safepo import _lib as L
+    from safepo.common.buffer import VectorizedOnPolicyBuffer
+    from safepo.common.model import ActorVCritic
+
+    class Sp:
+        def __init__(self, d):
+            self.shape = (d,)
+    with pytest.raises(L.SpoError):
+        VectorizedOnPolicyBuffer(Sp(4), Sp(2), size=8, device="cpu", num_envs=2)
+    pol = ActorVCritic(4, 2)
+    with pytest.raises(L.SpoError):
+        pol.step(torch.zeros(3, 4))
