@@ -296,7 +296,8 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
               dls_lp[j] = __fsub_rn(__fdiv_rn(d2, var), 1.f);
               if (a.kind == SPO_LOSS_FOCOPS) {
                 // KL(new || old), torch _kl_normal_normal(p=new, q=old)
-                const float os = ax[AUX_OSTD + j], om = ax[AUX_OMEAN + j];
+                // padded rows carry zeros: keep their (discarded) arithmetic finite
+                const float os = valid ? ax[AUX_OSTD + j] : 1.f, om = ax[AUX_OMEAN + j];
                 const float sr = __fdiv_rn(std, os);
                 const float vr = __fmul_rn(sr, sr);
                 const float dm = __fdiv_rn(__fsub_rn(mean, om), os);

@@ -236,7 +236,7 @@ class PolicyGradientUpdate:
             else:
                 perm = torch.randperm(S, device=self.device)
             L.check(lib.spo_pg_update(C.byref(d), L.ptr(pol.flat), L.ptr(self.adam.m), L.ptr(self.adam.v), L.ptr(self.adam.t),
-                                      C.byref(batch), L.ptr(perm), S, cfg["batch_size"], self.kind, C.byref(self.hp),
+                                      C.byref(batch), L.ptr(perm), perm.numel(), cfg["batch_size"], self.kind, C.byref(self.hp),
                                       L.ptr(self.ctrl), L.stream()), "spo_pg_update")
             L.check(lib.spo_actor_kl(C.byref(d), L.ptr(pol.flat), L.ptr(data["obs"]), L.ptr(self.old_mean),
                                      L.ptr(self.old_log_std), S, 0, cfg["target_kl"], L.ptr(self.ctrl), L.stream()),

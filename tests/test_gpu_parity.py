@@ -230,9 +230,9 @@ def test_buffer_get_matches_reference_known_answer(golden):
     kat = golden("gae")["buffer_kat"]
     buf = VectorizedOnPolicyBuffer(Sp(1), Sp(1), size=4, device=dev, num_envs=2, gae_mode="exact")
     for t in range(4):
-        z = torch.tensor([float(t), 10.0 + t], device=dev)
-        buf.store(obs=torch.tensor([[t + 0.0], [t + 100.0]], device=dev), act=torch.zeros(2, 1, device=dev), reward=z,
-                  cost=z / 2, value_r=z / 10, value_c=z / 5, log_prob=torch.zeros(2, device=dev))
+        z = torch.tensor([float(t), 10.0 + t])      # inputs formed on the CPU like the fixture (CUDA divides via reciprocal)
+        buf.store(obs=torch.tensor([[t + 0.0], [t + 100.0]]), act=torch.zeros(2, 1), reward=z,
+                  cost=z / 2, value_r=z / 10, value_c=z / 5, log_prob=torch.zeros(2))
         if t == 1:
             buf.finish_path(idx=0)
         if t == 3:

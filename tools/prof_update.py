@@ -1,0 +1,26 @@
+"""Short update pass for ncu captures: STEPS minibatch steps of PPO-Lag at S=1,024,000."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "safe-policy-optimization_b200"))
+from safepo import _lib as L  # noqa: E402
+from safepo.single_agent._engine import PolicyGradientUpdate  # noqa: E402
+from safepo.common.model import ActorVCritic  # noqa: E402
+
+dev = torch.device("cuda:0")
+S, D, A = int(os.environ.get("S", 1024000)), 60, 2
+steps = int(os.environ.get("STEPS", 300))
+torch.manual_seed(0)
+pol = ActorVCritic(D, A).to(dev)
+data = {"obs": torch.randn(S, D, device=dev), "act": torch.randn(S, A, device=dev), "log_prob": torch.full((S,), -2.5, device=dev),
+        "target_value_r": torch.randn(S, device=dev), "target_value_c": torch.randn(S, device=dev), "adv": torch.randn(S, device=dev)}
+cfg = dict(hidden_sizes=[64, 64], gamma=0.99, target_kl=1e9, batch_size=64, learning_iters=1, max_grad_norm=40.0)
+upd = PolicyGradientUpdate(pol, cfg, L.LOSS_PPO_CLIP, epochs=100, host_rng=False, device=dev)
+perm = torch.randperm(S, device=dev)[: steps * 64]
+for _ in range(3):
+    res = upd.run(data, perms=[perm])
+torch.cuda.synchronize()
+print(res)
