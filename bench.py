@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Headline benchmark: env-steps/sec of PPO-Lag on SafetyPointGoal1-v0 shape
+(obs 60, act 2), 1024 envs per GPU, 1000 steps per env per epoch (BASELINE.json
+configs[1]), synthetic observations.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo (libspo kernels)
+    python bench.py --impl reference --gpus 1 --steps K --warmup W   # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one epoch of the hot path: T=1000 fused forward/sample/store launches over
+1024 envs, dual GAE + advantage statistics, then the PPO-Lag update (<= 40 passes of
+16000 minibatch steps with the KL early stop of ppo_lag.py:347).  Two measurements:
+
+  value : the environment stream is resident in HBM before the timed region starts
+          (DeviceTapeRollout); CUDA events on the launching stream, barrier + synchronize
+          on both sides, max over ranks.
+  e2e   : the public trainer path with a HOST vector env: every env step copies that
+          step's observations/rewards/costs/flags host->device from pinned memory and reads
+          the actions back (bytes counted from the tensors copied).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for the roofline and
+cpu_baseline definitions.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "safe-policy-optimization_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+TASK = "SafetyPointGoal1-v0"
+D_OBS, D_ACT = 60, 2
+BYTES_PER_SAMPLE_UPDATE = 4 * (D_OBS + D_ACT + 4) + 8      # 264 B gathered + 8 B index
+FLOPS_PER_SAMPLE_UPDATE = 3 * 48128                          # fwd + bwd of the three nets
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=("spo", "reference"), default="spo")
+    ap.add_argument("--num-envs", type=int, default=1024, help="envs per GPU")
+    ap.add_argument("--horizon", type=int, default=1000, help="steps per env per epoch (T)")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+
+def build_trainer(args, device, rank, resident):
+    """The public trainer objects of safepo.single_agent.ppo_lag, assembled once so that
+    epochs can be timed individually."""
+    from safepo import _lib as L
+    from safepo.common.buffer import VectorizedOnPolicyBuffer
+    from safepo.common.lagrange import Lagrange
+    from safepo.common.logger import EpochLogger
+    from safepo.common.model import ActorVCritic
+    from safepo.common.synthetic_env import SyntheticVecEnv
+    from safepo.single_agent import ppo_lag
+    from safepo.single_agent._engine import DeviceTapeRollout, PolicyGradientUpdate, Rollout, seed_all
+    from safepo.utils.config import single_agent_args
+
+    N, T = args.num_envs, args.horizon
+    a, _ = single_agent_args(["--num-envs", str(N), "--steps-per-epoch", str(N * T), "--total-steps", str(N * T * 1000),
+                              "--seed", str(rank), "--rng", "device"])
+    seed_all(rank)
+    env = SyntheticVecEnv(N, D_OBS, D_ACT, episode_len=T, seed=rank)
+    cfg = dict(ppo_lag.default_cfg)
+    policy = ActorVCritic(D_OBS, D_ACT, cfg["hidden_sizes"]).to(device)
+    buffer = VectorizedOnPolicyBuffer(env.observation_space, env.action_space, size=T, device=device, num_envs=N, gamma=cfg["gamma"])
+    lagrange = Lagrange(a.cost_limit, a.lagrangian_multiplier_init, a.lagrangian_multiplier_lr)
+    log_dir = os.path.join(tempfile.mkdtemp(prefix="spo_bench_"), "exp", TASK, "ppo_lag", f"rank{rank}")
+    logger = EpochLogger(log_dir, seed=str(rank), verbose=False, use_tensorboard=False)
+    roll = (DeviceTapeRollout if resident else Rollout)(env, policy, buffer, logger, a, device)
+    upd = PolicyGradientUpdate(policy, cfg, L.LOSS_PPO_CLIP, epochs=1000, host_rng=False, device=device)
+    return dict(env=env, policy=policy, buffer=buffer, lagrange=lagrange, logger=logger, roll=roll, upd=upd, T=T, N=N)
+
+
+def one_epoch(tr):
+    """Exactly the epoch body of run_policy_gradient (ppo_lag.main)."""
+    tr["roll"].run(tr["T"])
+    jc = tr["logger"].get_stats("Metrics/EpCost")
+    tr["lagrange"].update_lagrange_multiplier(jc)
+    data = tr["buffer"].get(tr["lagrange"].lagrangian_multiplier)
+    res = tr["upd"].run(data)
+    tr["buffer"].reset_segments()
+    lg = tr["logger"]
+    if not lg.logged:   # keep the logger's per-epoch state machine moving (A3)
+        for k in ("Metrics/EpRet", "Metrics/EpCost", "Metrics/EpLen"):
+            lg.log_tabular(k)
+        lg.dump_tabular()
+    return res
+
+
+def timed_epochs(tr, K, W, world, device):
+    import torch.distributed as dist
+    from safepo import _lib as L
+    for _ in range(W):
+        one_epoch(tr)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = L.LAUNCHES["n"]
+    h0, d0 = tr["roll"].bytes_h2d, tr["roll"].bytes_d2h
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stops, msteps = [], []
+    with ClockSampler(device.index) as clk:
+        e0.record()
+        for _ in range(K):
+            res = one_epoch(tr)
+            stops.append(res["stop_iter"]); msteps.append(res["steps"])
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return dict(ms=ms, launches=L.LAUNCHES["n"] - l0, stops=stops, msteps=msteps, clocks=clk.summary(),
+                h2d=(tr["roll"].bytes_h2d - h0) / K, d2h=(tr["roll"].bytes_d2h - d0) / K)
+
+
+def time_update_kernel(tr, device):
+    """Average duration of one spo_pg_update launch (one pass of 16000 minibatch steps),
+    CUDA events on the launching stream, 3 warm launches + 3 timed."""
+    import ctypes as C
+    from safepo import _lib as L
+    upd, pol = tr["upd"], tr["policy"]
+    data = tr["buffer"].get(0.0)
+    S = data["obs"].shape[0]
+    batch = L.Batch(L.ptr(data["obs"]), L.ptr(data["act"]), L.ptr(data["log_prob"]), L.ptr(data["target_value_r"]),
+                    L.ptr(data["target_value_c"]), L.ptr(data["adv"]), None, None, S)
+    upd.ctrl.zero_()
+    times = []
+    for i in range(6):
+        perm = torch.randperm(S, device=device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.lib().spo_pg_update(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(upd.adam.m), L.ptr(upd.adam.v), L.ptr(upd.adam.t),
+                                      C.byref(batch), L.ptr(perm), S, 64, L.LOSS_PPO_CLIP, C.byref(upd.hp), L.ptr(upd.ctrl),
+                                      L.stream()), "spo_pg_update")
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(e0.elapsed_time(e1))
+    tr["buffer"].reset_segments()
+    return float(np.mean(times)), (S + 63) // 64
+
+
+def cpu_baseline(args, passes, kind="port", threads=4):
+    """The oracle port of the reference's CPU path, timed on this box's host cores on a
+    bounded sample of the same workload: `r` vector env steps at N envs (rollout loop incl.
+    store + bootstraps) and `m` PPO-Lag minibatch steps; extrapolated to the workload with
+    the measured per-step costs and `passes` update passes."""
+    from oracle import spo_oracle as O
+    from oracle import trainers as TR
+    from safepo.common.synthetic_env import SyntheticVecEnv
+    from collections import deque
+    torch.set_num_threads(threads)
+    N, T = args.num_envs, args.horizon
+    torch.manual_seed(0)
+    env = SyntheticVecEnv(N, D_OBS, D_ACT, episode_len=T, seed=0)
+    pol = O.OraclePolicy(D_OBS, D_ACT)
+    opt = O.OracleOptim(pol)
+    r = 4
+    buf = TR.PathBuffer(N, r, D_OBS, D_ACT, 0.99)
+    log = TR.StatLog()
+    obs, _ = env.reset()
+    obs = torch.as_tensor(obs, dtype=torch.float32)
+    ep = (np.zeros(N), np.zeros(N), np.zeros(N))
+    dq = (deque(maxlen=50), deque(maxlen=50), deque(maxlen=50))
+    t0 = time.time()
+    obs = TR.rollout(pol, env, buf, obs, ep, dq, log, r, epoch_T=10 ** 9)      # r mid-epoch steps (no path closes)
+    t_roll = (time.time() - t0) / r                                            # s per vector env step
+    for i in range(N):
+        buf.finish_path(torch.zeros(1), torch.zeros(1), i)
+    data = buf.get()
+    buf1 = TR.PathBuffer(N, 1, D_OBS, D_ACT, 0.99)
+    t0e = time.time()
+    TR.rollout(pol, env, buf1, obs, ep, dq, log, 1)                            # the epoch-end step: N bootstrap forwards + GAE
+    t_end = time.time() - t0e
+    adv = data["adv_r"] - 0.1 * data["adv_c"]
+    S = data["obs"].shape[0]
+    budget = max(args.cpu_seconds - (time.time() - t0), 2.0)
+    t1 = time.time()
+    m = 0
+    perm = torch.randperm(S)
+    while time.time() - t1 < budget:
+        for s in range(0, S, 64):
+            idx = perm[s:s + 64]
+            b = {"obs": data["obs"][idx], "act": data["act"][idx], "log_prob": data["log_prob"][idx],
+                 "target_value_r": data["target_value_r"][idx], "target_value_c": data["target_value_c"][idx], "adv": adv[idx]}
+            O.minibatch_step(pol, opt, b, "ppo")
+            m += 1
+            if time.time() - t1 >= budget:
+                break
+    t_mb = (time.time() - t1) / m
+    t2 = time.time()
+    with torch.no_grad():
+        old_mean, old_std = O.actor_mean_std(pol, data["obs"])
+    O.full_batch_kl(pol, data["obs"], old_mean, old_std)
+    t_kl_per_sample = (time.time() - t2) / S
+    S_full = N * T
+    epoch_s = (T - 1) * t_roll + t_end + passes * ((S_full + 63) // 64) * t_mb + passes * S_full * t_kl_per_sample
+    return {"value": S_full / epoch_s, "unit": "env-steps/s", "cores": threads, "kind": kind,
+            "sample": (f"{r} vector env steps at {N} envs + {m} PPO-Lag minibatch steps (batch 64) on the oracle port; "
+                       f"extrapolated to S={S_full} with {passes} update pass(es): {t_roll*1e3:.1f} ms/env-step-vector, {t_end*1e3:.0f} ms epoch-end step, "
+                       f"{t_mb*1e3:.2f} ms/minibatch-step"),
+            "ms_per_minibatch_step": t_mb * 1e3, "ms_per_vector_env_step": t_roll * 1e3, "passes": passes}
+
+
+def run_spo(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl spo needs a CUDA device (there is no CPU fallback)")
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    K, W = args.steps, max(args.warmup, 0)
+    S = args.num_envs * args.horizon
+
+    tr = build_trainer(args, device, rank, resident=True)
+    val = timed_epochs(tr, K, W, world, device)
+    kern_ms, kern_steps = time_update_kernel(tr, device)
+    e2e = None
+    if not args.no_e2e:
+        tr2 = build_trainer(args, device, rank, resident=False)
+        e2e = timed_epochs(tr2, K, W, world, device)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, how = peaks()
+    value = S * K * world / (val["ms"] / 1e3)
+    passes = int(round(float(np.mean(val["stops"])))) or 1
+    alg_bytes = kern_steps * 64 * BYTES_PER_SAMPLE_UPDATE
+    achieved = alg_bytes / (kern_ms / 1e3) / 1e9
+    out = {
+        "metric": "env-steps/sec PPO-Lag SafetyPointGoal1 @1024 envs/GPU", "value": value, "unit": "env-steps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": val["ms"] / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1]: PPO-Lag SafetyPointGoal1-v0 shape (obs 60, act 2, hidden 64x64), "
+                               f"{args.num_envs} envs/GPU x {args.horizon} steps/epoch, batch 64, <=40 passes with KL early stop",
+                   "samples_per_step_per_gpu": S, "stop_iter": val["stops"], "minibatch_steps_per_epoch": val["msteps"],
+                   "us_per_minibatch_step": kern_ms * 1e3 / kern_steps, "ms_per_update_pass": kern_ms,
+                   "l2": "inputs larger than L2 (245.8 MB observation buffer per epoch vs 126 MB L2)",
+                   "parallelism": f"dp{world}" if world > 1 else "single"},
+        "clocks": val["clocks"],
+        "gpu_launches": val["launches"],
+        "roofline": {"kernel": "spo_update_kernel (one PPO-Lag pass = 16000 serial minibatch steps)", "bound": "hbm",
+                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                     "traffic": 387.2e6, "peak_source": how,
+                     "note": "serial-latency-bound chain of 64-row Adam steps (SURVEY H3): us_per_minibatch_step is the figure of merit"},
+    }
+    if e2e is not None:
+        out["e2e"] = {"value": S * K * world / (e2e["ms"] / 1e3), "unit": "env-steps/s", "h2d_bytes_per_step": e2e["h2d"],
+                      "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["ms"] / K, "stop_iter": e2e["stops"],
+                      "gpu_launches": e2e["launches"]}
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, passes)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the path (oracle port), all host threads
+# ---------------------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 4
+    K, W = args.steps, max(args.warmup, 0)
+    per = max(args.cpu_seconds / max(K + W, 1), 4.0)
+    vals = []
+    a2 = argparse.Namespace(**vars(args))
+    a2.cpu_seconds = per
+    # KL early stop: with 16000 Adam steps per pass at S=1,024,000 the reference's own rule
+    # (ppo_lag.py:347) trips after the first pass; the GPU arm logs the count it observed.
+    passes = 1
+    for i in range(K + W):
+        r = cpu_baseline(a2, passes, kind="port", threads=threads)
+        if i >= W:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    S = args.num_envs * args.horizon
+    out = {"impl": "reference", "metric": "env-steps/sec PPO-Lag SafetyPointGoal1 @1024 envs/GPU", "value": v, "unit": "env-steps/s",
+           "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": S / v * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"PPO-Lag SafetyPointGoal1-v0 shape, {args.num_envs} envs x {args.horizon} steps/epoch (bounded sample per step)",
+                      "passes_assumed": passes},
+           "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": vals[-1]["sample"]},
+           "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_spo(a)

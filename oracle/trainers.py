@@ -119,9 +119,10 @@ class PathBuffer:
         return data
 
 
-def rollout(pol, env, buf, obs, ep, deques, log, T, capture=None):
+def rollout(pol, env, buf, obs, ep, deques, log, T, epoch_T=None):
     """ppo_lag.py:162-235 (identical in cpo/focops/trpo_lag).  ``obs`` is the current
-    fp32 observation tensor; returns the next one."""
+    fp32 observation tensor; returns the next one.  ``epoch_T`` (bench only): length of the
+    epoch when just a window of T steps of it is being run."""
     N = buf.N
     ep_ret, ep_cost, ep_len = ep
     rew_dq, cost_dq, len_dq = deques
@@ -140,7 +141,7 @@ def rollout(pol, env, buf, obs, ep, deques, log, T, capture=None):
                                                   for a in info["final_observation"]]), dtype=torch.float32)
         buf.store(t, obs, act, reward, cost, v_r, v_c, logp)
         obs = next_obs
-        epoch_end = t >= T - 1
+        epoch_end = t >= (epoch_T if epoch_T is not None else T) - 1
         for idx in range(N):
             done, time_out = bool(terminated[idx]), bool(truncated[idx])
             if epoch_end or done or time_out:

@@ -102,7 +102,16 @@ EXPORTS = ("spo_version", "spo_last_error", "spo_sync_check", "spo_param_count",
            "spo_linesearch_eval", "spo_conjugate_gradient")
 
 
+# number of libspo kernels launched so far (bench.py reports the delta over its timed region)
+LAUNCHES = {"n": 0}
+_KERNEL_CALLS = {"spo_policy_step", "spo_critic_values", "spo_store_transition", "spo_gae_dual", "spo_adv_stats",
+                 "spo_adv_apply", "spo_pg_update", "spo_actor_forward", "spo_actor_kl", "spo_surrogate_grad", "spo_fvp",
+                 "spo_linesearch_eval"}
+
+
 def check(rc, what):
+    if what in _KERNEL_CALLS:
+        LAUNCHES["n"] += 1
     if rc != 0:
         raise SpoError(f"{what} failed ({rc}): {lib().spo_last_error().decode()}")
 

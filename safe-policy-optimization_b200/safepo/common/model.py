@@ -153,18 +153,22 @@ class ActorVCritic(nn.Module):
             raise L.SpoError(f"obs has {o2.shape[-1]} features, expected {self.obs_dim}")
         return o2.contiguous(), single
 
-    def step(self, obs, deterministic=False, eps=None, store=None):
+    def step(self, obs, deterministic=False, eps=None, store=None, outputs=True):
         """(action, log_prob, value_r, value_c) for ``obs`` of shape [N,D] or [D]
         (model.py:149-170).  ``eps`` [N,A]: standard-normal draws to use instead of the
         in-kernel Philox stream (parity with a host generator).  ``store=(rollout_struct, t)``
-        additionally writes the transition into slot t of a VectorizedOnPolicyBuffer."""
+        additionally writes the transition into slot t of a VectorizedOnPolicyBuffer;
+        ``outputs=False`` (only with ``store``) skips the separate output tensors."""
         o2, single = self._check(obs)
         n = o2.shape[0]
         dev = o2.device
-        act = torch.empty(n, self.act_dim, dtype=torch.float32, device=dev)
-        logp = torch.empty(n, dtype=torch.float32, device=dev)
-        v_r = torch.empty(n, dtype=torch.float32, device=dev)
-        v_c = torch.empty(n, dtype=torch.float32, device=dev)
+        if outputs or store is None:
+            act = torch.empty(n, self.act_dim, dtype=torch.float32, device=dev)
+            logp = torch.empty(n, dtype=torch.float32, device=dev)
+            v_r = torch.empty(n, dtype=torch.float32, device=dev)
+            v_c = torch.empty(n, dtype=torch.float32, device=dev)
+        else:
+            act = logp = v_r = v_c = None
         if eps is not None:
             eps = eps.reshape(n, self.act_dim).to(device=dev, dtype=torch.float32).contiguous()
         if self._philox_seed is None:
@@ -175,6 +179,8 @@ class ActorVCritic(nn.Module):
                                         self._philox_seed, self._philox_offset, int(bool(deterministic)), n,
                                         L.ptr(act), L.ptr(logp), L.ptr(v_r), L.ptr(v_c), st, t, L.stream()),
                 "spo_policy_step")
+        if act is None:
+            return None
         if single:
             return act[0], logp[0], v_r[0], v_c[0]
         return act, logp, v_r, v_c

@@ -188,6 +188,64 @@ class Rollout:
         return time.time() - t0
 
 
+class DeviceTapeRollout(Rollout):
+    """Rollout whose environment stream is already resident in HBM: the frame pools of a
+    SyntheticVecEnv are copied to the device once, every step reads its frame there, and
+    nothing crosses PCIe inside the loop (no action read-back either: the synthetic stream
+    does not depend on the action).  Episode accounting still runs on the host from the
+    env's own pools, so Jc / logging are identical to the host-env path."""
+
+    def __init__(self, env, policy, buffer, logger, args, device):
+        super().__init__(env, policy, buffer, logger, args, device)
+        f32 = dict(dtype=torch.float32, device=device)
+        self.obs_pool = torch.as_tensor(env._obs, **f32)
+        self.final_pool = torch.as_tensor(env._final, **f32)
+        self.rew_pool = torch.as_tensor(env._rew, **f32)
+        self.cost_pool = torch.as_tensor(env._cost, **f32)
+        self.zeros8 = torch.zeros(self.N, dtype=torch.uint8, device=device)
+        self.ones8 = torch.ones(self.N, dtype=torch.uint8, device=device)
+        self.k = 0  # frame index of the current observation
+
+    def _flags(self, arr):
+        if not arr.any():
+            return self.zeros8
+        if arr.all():
+            return self.ones8
+        return torch.as_tensor(arr.astype(np.uint8)).to(self.device, non_blocking=True)
+
+    def run(self, T):
+        t0 = time.time()
+        N, A = self.N, self.A
+        pol, buf, env, logger = self.policy, self.buffer, self.env, self.logger
+        for t in range(T):
+            eps = torch.empty(N, A).normal_().to(self.device, non_blocking=True) if self.host_rng else None
+            pol.step(self.obs_pool[self.k], eps=eps, store=(buf.struct, t), outputs=False)
+            _, reward, cost, terminated, truncated, info = env.step(None)
+            k = env._k % env._pool
+            self.ep_ret += reward
+            self.ep_cost += cost
+            self.ep_len += 1
+            epoch_end = t >= T - 1
+            any_trunc = bool(truncated.any())
+            final_v = pol.values(self.final_pool[k]) if any_trunc else None
+            next_v = pol.values(self.obs_pool[k]) if epoch_end else None
+            buf.store_transition(t, self.rew_pool[k], self.cost_pool[k], self._flags(terminated), self._flags(truncated),
+                                 epoch_end, next_v, final_v)
+            self.k = k
+            if self.host_rng and (epoch_end or terminated.any() or any_trunc):
+                self._burn_bootstrap_draws(terminated, truncated, epoch_end)
+            finished = np.nonzero(terminated | truncated)[0]
+            for idx in finished:
+                self.rew_deque.append(self.ep_ret[idx])
+                self.cost_deque.append(self.ep_cost[idx])
+                self.len_deque.append(self.ep_len[idx])
+                logger.store(**{"Metrics/EpRet": np.mean(self.rew_deque), "Metrics/EpCost": np.mean(self.cost_deque),
+                                "Metrics/EpLen": np.mean(self.len_deque)})
+                self.ep_ret[idx] = self.ep_cost[idx] = self.ep_len[idx] = 0.0
+                logger.logged = False
+        return time.time() - t0
+
+
 # ---------------------------------------------------------------------------------------
 # PPO-Lag / FOCOPS update
 # ---------------------------------------------------------------------------------------
@@ -291,7 +349,8 @@ def run_policy_gradient(args, config, algo, env=None, max_epochs=None, quiet=Fal
     logger.setup_torch_saver(policy.actor)
     logger.log("Start with training.")
     host_rng = getattr(args, "rng", "device") == "host"
-    roll = Rollout(env, policy, buffer, logger, args, device)
+    roll_cls = DeviceTapeRollout if getattr(args, "resident_env", False) else Rollout
+    roll = roll_cls(env, policy, buffer, logger, args, device)
     upd = PolicyGradientUpdate(policy, config, L.LOSS_PPO_CLIP if algo == "ppo_lag" else L.LOSS_FOCOPS, epochs, host_rng, device)
     timings = []
     n_epochs = epochs if max_epochs is None else min(epochs, max_epochs)
