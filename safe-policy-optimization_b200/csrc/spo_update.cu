@@ -5,8 +5,8 @@
 // forward of the three nets, losses, backward, critic L2 term, ONE joint grad-norm clip
 // over all three nets (ppo_lag.py:325), three Adam steps.
 //
-// Mapping: a thread-block cluster of 3 CTAs (4 when the driver refuses a cluster of 3:
-// the 4th CTA only joins the barriers), one net per CTA -- actor / reward critic / cost
+// Mapping: a thread-block cluster of 4 CTAs (the 4th only joins the barriers: a cluster of
+// 4 synchronises faster than one of 3 on B200), one net per CTA -- actor / reward critic / cost
 // critic.  Each CTA keeps its net's weights (both orientations), the Adam moments and
 // all activations of the 64-row tile in shared memory / registers for the whole pass;
 // the only traffic per step is the gather of the minibatch rows (cp.async, prefetched one
@@ -47,17 +47,25 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// One Adam step on a scalar, mirroring torch's _multi_tensor_adam op order:
+// One Adam step on a scalar in torch's _multi_tensor_adam op order:
 //   m = lerp(m, g, 1-b1) (fused mul-add);  v = v*b2 + ((1-b2)*g)*g;
 //   denom = sqrt(v)/sqrt(bc2) + eps;  p = p + (step_size*m)/denom,  step_size = -lr/bc1.
+// sqrt and the two divisions use the SFU approximations (sqrt.approx / div.approx,
+// <= 2 ulp): IEEE-exact versions cost ~60 issue slots per parameter (profiles/r01) for
+// differences far below the 1e-5 parity bar.
 struct AdamK {
   float w1, b2, w2, bc2s, eps, ss;  // w1 = 1-b1, w2 = 1-b2
 };
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, const AdamK& k) {
   m = fmaf(k.w1, __fsub_rn(g, m), m);
   v = __fadd_rn(__fmul_rn(v, k.b2), __fmul_rn(__fmul_rn(k.w2, g), g));
-  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), k.bc2s), k.eps);
-  return __fadd_rn(p, __fdiv_rn(__fmul_rn(k.ss, m), denom));
+  const float denom = __fadd_rn(__fdividef(sqrt_approx(v), k.bc2s), k.eps);
+  return __fadd_rn(p, __fdividef(__fmul_rn(k.ss, m), denom));
 }
 
 // small parameters of a net in the order b1[64] b2[64] w3[O*64] b3[O] log_std[A(actor)]
@@ -100,9 +108,10 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
   SpoNetSmem w;
   float* p = spo_carve_net(smem, D, O, true, w);
   float* log_std = p; p += 8;
-  float* msmall = p;  p += 672;
-  float* vsmall = p;  p += 672;
-  float* gsmall = p;  p += 672;
+  const int spn = spo_pad4(2 * SPO_HID + A * SPO_HID + 2 * A);   // small-parameter slots (actor-sized for all nets)
+  float* msmall = p;  p += spn;
+  float* vsmall = p;  p += spn;
+  float* gsmall = p;  p += spn;
   float* xbuf[2];
   xbuf[0] = p; p += SPO_ROWS * ldx;
   xbuf[1] = p; p += SPO_ROWS * ldx;
@@ -635,7 +644,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
 
 size_t update_smem_bytes(int D, int A, int nt1) {
   const int Dp = spo_pad4(D);
-  size_t f = spo_net_smem_floats(D, A > 1 ? A : 1, true) + 8 + 3 * 672 + 2 * SPO_ROWS * spo_ld(D) + 2 * SPO_ROWS * AUXW +
+  size_t f = spo_net_smem_floats(D, A > 1 ? A : 1, true) + 8 + 3 * spo_pad4(2 * SPO_HID + A * SPO_HID + 2 * A) + 2 * SPO_ROWS * spo_ld(D) + 2 * SPO_ROWS * AUXW +
              3 * SPO_ROWS * SPO_LDH + 3 * SPO_ROWS * SPO_MAX_ACT + 64 + 4 + (nt1 > 1 ? 2 * Dp * SPO_LDH : 0);
   return f * sizeof(float);
 }
@@ -644,10 +653,10 @@ template <int NT1>
 int launch_update(const UpdArgs& a, cudaStream_t stream) {
   const size_t smem = update_smem_bytes(a.D, a.A, NT1);
   SPO_REQUIRE(smem <= 227 * 1024, SPO_ERR_UNSUPPORTED, "spo_pg_update: obs_dim=%d needs %zu B of shared memory (> 227 KB)", a.D, smem);
-  static int cluster_size = 0;   // 3 preferred; 4 when the driver rejects a cluster of 3
+  static int cluster_size = 0;   // 4 preferred (barrier measured faster than for 3, profiles/r01_ubench.txt); 3 as fallback
   SPO_CUDA_TRY(cudaFuncSetAttribute(spo_update_kernel<NT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   for (int attempt = 0; attempt < 2; ++attempt) {
-    const int cs = cluster_size ? cluster_size : (attempt == 0 ? 3 : 4);
+    const int cs = cluster_size ? cluster_size : (attempt == 0 ? 4 : 3);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(cs);
     cfg.blockDim = dim3(SPO_THREADS);
@@ -666,7 +675,7 @@ int launch_update(const UpdArgs& a, cudaStream_t stream) {
       spo_set_error("spo_pg_update: launch failed (cluster=%d): %s", cs, cudaGetErrorString(e));
       return SPO_ERR_CUDA;
     }
-    (void)cudaGetLastError();  // clear and retry with a cluster of 4
+    (void)cudaGetLastError();  // clear and retry with the other cluster size
   }
   return SPO_ERR_CUDA;
 }

@@ -313,6 +313,314 @@ class PolicyGradientUpdate:
 
 
 # ---------------------------------------------------------------------------------------
+# CPO / TRPO-Lag update
+# ---------------------------------------------------------------------------------------
+
+class CriticRegression:
+    """cpo.py:534-571 / trpo_lag.py:457-494: minibatch regression of the two critics
+    (batch 128, lr 1e-3, 10 passes); the joint clip also sees the actor's stale .grad."""
+
+    def __init__(self, policy, cfg, host_rng, device, lr=1e-3):
+        self.policy, self.cfg, self.host_rng, self.device = policy, cfg, host_rng, device
+        self.adam = AdamState(policy)
+        self.ctrl = make_ctrl(device)
+        self.hp = L.HParams(0.0, lr, lr, 0.9, 0.999, 1e-8, cfg["max_grad_norm"],
+                            0.001 if cfg.get("use_critic_norm", True) else 0.0, 0.8, 1.2, 1.5, 0.0,
+                            2.0 if cfg.get("use_value_coefficient", False) else 1.0)
+
+    def run(self, data, stale_actor_grad_sumsq, perms=None):
+        pol, cfg, lib = self.policy, self.cfg, L.lib()
+        S = data["obs"].shape[0]
+        batch = L.Batch(L.ptr(data["obs"]), None, None, L.ptr(data["target_value_r"]), L.ptr(data["target_value_c"]),
+                        None, None, None, S)
+        self.ctrl.zero_()
+        self.ctrl.view(torch.float32)[L.CTRL_EXTRA_SUMSQ_F32_INDEX] = stale_actor_grad_sumsq
+        for it in range(cfg["learning_iters"]):
+            if perms is not None:
+                perm = perms[it].to(self.device)
+            elif self.host_rng:
+                perm = reference_order(S).to(self.device)
+            else:
+                perm = torch.randperm(S, device=self.device)
+            L.check(lib.spo_pg_update(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(self.adam.m), L.ptr(self.adam.v),
+                                      L.ptr(self.adam.t), C.byref(batch), L.ptr(perm), perm.numel(), cfg["batch_size"],
+                                      L.LOSS_CRITIC_ONLY, C.byref(self.hp), L.ptr(self.ctrl), L.stream()), "spo_pg_update")
+        c = read_ctrl(self.ctrl)
+        steps = max(int(c["steps"]), 1)
+        return {"loss_r": c["loss_sum"][0] / steps, "loss_c": c["loss_sum"][1] / steps, "steps": int(c["steps"])}
+
+
+class TrustRegionUpdate:
+    """Actor step of cpo.py:351-519 / trpo_lag.py:358-442 on the libspo kernels.  The flat
+    vectors (g, b, x, p, step) stay on the device; only the handful of scalars the case
+    analysis needs are read back."""
+
+    CG_ITERS, SEARCH_STEPS, STEP_FRACTION, DAMPING = 15, 15, 0.8, 0.1
+
+    def __init__(self, policy, cfg, device, logger=None):
+        self.policy, self.cfg, self.device, self.logger = policy, cfg, device, logger
+        P = policy.n_actor
+        f32 = dict(dtype=torch.float32, device=device)
+        self.g, self.b, self.x, self.p, self.Fx = (torch.zeros(P, **f32) for _ in range(5))
+        self.work = torch.zeros(4 * P + 8, **f32)
+        self.loss = torch.zeros(1, **f32)
+        self.out3 = torch.zeros(3, **f32)
+        self.old_mean = None
+        self.old_log_std = torch.zeros(policy.act_dim, **f32)
+
+    def _log(self, msg, color="green"):
+        if self.logger is not None:
+            self.logger.log(msg, color)
+
+    # -- kernels --
+    def _grad(self, data, adv, out):
+        pol = self.policy
+        S = data["obs"].shape[0]
+        L.check(L.lib().spo_surrogate_grad(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(data["obs"]), L.ptr(data["act"]),
+                                           L.ptr(data["log_prob"]), L.ptr(adv), S, L.ptr(self.loss), L.ptr(out), L.stream()),
+                "spo_surrogate_grad")
+        return self.loss.clone()
+
+    def _cg(self, data, rhs, out):
+        pol = self.policy
+        S = data["obs"].shape[0]
+        L.check(L.lib().spo_conjugate_gradient(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(data["obs"]), S, L.ptr(rhs),
+                                               self.CG_ITERS, self.DAMPING, 1e-10, 1e-6, L.ptr(out), L.ptr(self.work),
+                                               L.stream()), "spo_conjugate_gradient")
+        L.LAUNCHES["n"] += 2 * self.CG_ITERS + 1
+
+    def _fvp(self, data, v, out):
+        pol = self.policy
+        S = data["obs"].shape[0]
+        L.check(L.lib().spo_fvp(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(data["obs"]), S, L.ptr(v), self.DAMPING, L.ptr(out),
+                                L.stream()), "spo_fvp")
+
+    def _eval(self, data, adv_a, adv_b):
+        pol = self.policy
+        S = data["obs"].shape[0]
+        L.check(L.lib().spo_linesearch_eval(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(data["obs"]), L.ptr(data["act"]),
+                                            L.ptr(data["log_prob"]), L.ptr(adv_a), L.ptr(adv_b), L.ptr(self.old_mean),
+                                            L.ptr(self.old_log_std), S, L.ptr(self.out3), L.stream()), "spo_linesearch_eval")
+        return self.out3.cpu()
+
+    def _old_dist(self, data):
+        pol = self.policy
+        S = data["obs"].shape[0]
+        if self.old_mean is None or self.old_mean.shape[0] != S:
+            self.old_mean = torch.empty(S, pol.act_dim, dtype=torch.float32, device=self.device)
+        L.check(L.lib().spo_actor_forward(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(data["obs"]), S, L.ptr(self.old_mean),
+                                          L.stream()), "spo_actor_forward")
+        self.old_log_std.copy_(pol.flat[: pol.act_dim])
+
+    # -- CPO --
+    def run_cpo(self, data, ep_costs):
+        """cpo.py:351-519.  ep_costs = Jc - cost_limit (python float)."""
+        pol, kl_target = self.policy, self.cfg["target_kl"]
+        theta_old = pol.actor_flat().clone()
+        loss_r = self._grad(data, data["adv_r"], self.g)            # g = -grad(loss_pi_r) = grad mean(ratio*adv_r)
+        self._old_dist(data)
+        self._cg(data, self.g, self.x)
+        self._fvp(data, self.x, self.Fx)
+        loss_c = self._grad(data, data["adv_c"], self.b)            # b = grad mean(ratio*adv_c)
+        self._cg(data, self.b, self.p)
+        sc = torch.stack([torch.dot(self.x, self.Fx), torch.dot(self.g, self.p), torch.dot(self.b, self.p),
+                          torch.dot(self.b, self.b), loss_r[0], loss_c[0], torch.dot(self.g, self.g),
+                          torch.dot(self.x, self.x)]).cpu()
+        xHx, r, s, bb = sc[0], sc[1], sc[2], sc[3]
+        loss_reward_before, loss_cost_before = -float(sc[4]), float(sc[5])
+        assert torch.isfinite(self.x).all(), "x is not finite"
+        assert xHx.item() >= 0, "xHx is negative"
+        alpha = torch.sqrt(2 * kl_target / (xHx + 1e-8))
+        q = xHx
+        if bb <= 1e-6 and ep_costs < 0:
+            A_, B_, case = torch.zeros(1), torch.zeros(1), 4
+        else:
+            assert torch.isfinite(r).all() and torch.isfinite(s).all(), "r/s not finite"
+            A_ = q - r ** 2 / (s + 1e-8)
+            B_ = 2 * kl_target - ep_costs ** 2 / (s + 1e-8)
+            if ep_costs < 0 and B_ < 0:
+                case = 3
+            elif ep_costs < 0 <= B_:
+                case = 2
+            elif ep_costs >= 0 and B_ >= 0:
+                case = 1
+                self._log("Alert! Attempting feasible recovery!", "yellow")
+            else:
+                case = 0
+                self._log("Alert! Attempting infeasible recovery!", "red")
+        if case in (3, 4):
+            nu_star, lambda_star = torch.zeros(1), 1 / (alpha + 1e-8)
+            step = alpha.item() * self.x
+        elif case in (1, 2):
+            lambda_a, lambda_b = torch.sqrt(A_ / B_), torch.sqrt(q / (2 * kl_target))
+            r_num, eps_cost = r.item(), ep_costs + 1e-8
+            zero, inf = torch.as_tensor(0.0), torch.as_tensor(torch.inf)
+            if ep_costs < 0:
+                la, lb = torch.clamp(lambda_a, zero, r_num / eps_cost), torch.clamp(lambda_b, r_num / eps_cost, inf)
+            else:
+                la, lb = torch.clamp(lambda_a, r_num / eps_cost, inf), torch.clamp(lambda_b, zero, r_num / eps_cost)
+            f_a = -0.5 * (A_ / (la + 1e-8) + B_ * la) - r * ep_costs / (s + 1e-8)
+            f_b = -0.5 * (q / (lb + 1e-8) + 2 * kl_target * lb)
+            lambda_star = la if f_a >= f_b else lb
+            nu_star = torch.clamp(lambda_star * ep_costs - r, min=0) / (s + 1e-8)
+            step = (1.0 / (lambda_star + 1e-8)).item() * (self.x - nu_star.item() * self.p)
+        else:
+            lambda_star, nu_star = torch.zeros(1), torch.sqrt(2 * kl_target / (s + 1e-8))
+            step = -nu_star.item() * self.p
+        step_frac, acceptance, accepted, kl = 1.0, 0, False, 0.0
+        expected = float(torch.dot(self.g, step))
+        for i in range(self.SEARCH_STEPS):
+            pol.actor_flat().copy_(theta_old + step_frac * step)
+            acceptance = i + 1
+            o = self._eval(data, data["adv_r"], data["adv_c"])
+            loss_reward, loss_cost, kl = -float(o[0]), float(o[1]), float(o[2])
+            improve, cost_diff = loss_reward_before - loss_reward, loss_cost - loss_cost_before
+            self._log(f"Expected Improvement: {expected} Actual: {improve}")
+            if not np.isfinite(kl):
+                self._log("WARNING: KL not finite")
+                continue
+            if (improve < 0) if case > 1 else False:
+                self._log("INFO: did not improve improve <0")
+            elif cost_diff > max(-ep_costs, 0):
+                self._log(f"INFO: no improve {cost_diff} > {max(-ep_costs, 0)}")
+            elif kl > kl_target:
+                self._log(f"INFO: violated KL constraint {kl} at step {i + 1}.")
+            else:
+                self._log(f"Accept step at i={i + 1}")
+                accepted = True
+                break
+            step_frac *= self.STEP_FRACTION
+        if not accepted:
+            self._log("INFO: no suitable step found...")
+            step = torch.zeros_like(step)
+            acceptance = 0
+        pol.actor_flat().copy_(theta_old + step_frac * step)
+        return {"Misc/Alpha": alpha.item(), "Misc/FinalStepNorm": float(torch.norm(step)), "Misc/xHx": xHx.item(),
+                "Misc/gradient_norm": float(sc[6].sqrt()), "Misc/H_inv_g": float(sc[7].sqrt()), "Misc/AcceptanceStep": acceptance,
+                "Loss/Loss_actor": -float(sc[4]) + float(sc[5]), "Train/KL": kl, "case": case, "step_frac": step_frac,
+                "stale_sumsq": bb.to(self.device)}
+
+    # -- TRPO-Lag --
+    def run_trpo(self, data, advantage):
+        """trpo_lag.py:363-442."""
+        pol, kl_target = self.policy, self.cfg["target_kl"]
+        theta_old = pol.actor_flat().clone()
+        loss0 = self._grad(data, advantage, self.g)
+        self._old_dist(data)
+        self._cg(data, self.g, self.x)
+        self._fvp(data, self.x, self.Fx)
+        sc = torch.stack([torch.dot(self.x, self.Fx), loss0[0], torch.dot(self.g, self.g), torch.dot(self.x, self.x)]).cpu()
+        xHx = sc[0]
+        loss_before = -float(sc[1])
+        assert torch.isfinite(self.x).all(), "x is not finite"
+        assert xHx.item() >= 0, "xHx is negative"
+        alpha = torch.sqrt(2 * kl_target / (xHx + 1e-8))
+        step = self.x * alpha.item()
+        expected = float(torch.dot(self.g, step))
+        step_frac, final_kl, acceptance, accepted, loss_pi = 1.0, 0.0, 0, False, loss_before
+        for i in range(self.SEARCH_STEPS):
+            pol.actor_flat().copy_(theta_old + step_frac * step)
+            o = self._eval(data, advantage, None)
+            loss_pi, kl = -float(o[0]), float(o[2])
+            improve = loss_before - loss_pi
+            self._log(f"Expected Improvement: {expected} Actual: {improve}")
+            if not np.isfinite(loss_pi):
+                self._log("WARNING: loss_pi not finite")
+            elif improve < 0:
+                self._log("INFO: did not improve improve <0")
+            elif kl > kl_target:
+                self._log("INFO: violated KL constraint.")
+            else:
+                acceptance, final_kl, accepted = i + 1, kl, True
+                self._log(f"Accept step at i={acceptance}")
+                break
+            step_frac *= 0.8
+        if not accepted:
+            self._log("INFO: no suitable step found...")
+            step = torch.zeros_like(step)
+            acceptance = 0
+        pol.actor_flat().copy_(theta_old + step_frac * step)
+        return {"Misc/Alpha": alpha.item(), "Misc/FinalStepNorm": float(torch.norm(step)), "Misc/xHx": xHx.item(),
+                "Misc/gradient_norm": float(sc[2].sqrt()), "Misc/H_inv_g": float(sc[3].sqrt()), "Misc/AcceptanceStep": acceptance,
+                "Loss/Loss_actor": loss_pi, "Train/KL": final_kl, "step_frac": step_frac, "stale_sumsq": sc[2].to(self.device)}
+
+
+def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False):
+    """main() of cpo.py / trpo_lag.py."""
+    seed_all(args.seed)
+    if args.device != "cuda":
+        raise L.SpoError("this build has no CPU path: run with --device cuda")
+    device = torch.device(f"cuda:{args.device_id}")
+    torch.cuda.set_device(device)
+    if env is None:
+        env, obs_space, act_space = make_env(args)
+    else:
+        obs_space, act_space = env.observation_space, env.action_space
+    T = args.steps_per_epoch // args.num_envs
+    epochs = args.total_steps // args.steps_per_epoch
+    policy = ActorVCritic(obs_space.shape[0], act_space.shape[0], config["hidden_sizes"]).to(device)
+    buffer = VectorizedOnPolicyBuffer(obs_space, act_space, size=T, device=device, num_envs=args.num_envs,
+                                      gamma=config["gamma"], gae_mode=getattr(args, "gae", "scan"))
+    lagrange = None
+    if algo == "trpo_lag":
+        lagrange = Lagrange(args.cost_limit, args.lagrangian_multiplier_init, args.lagrangian_multiplier_lr)
+    dict_args = dict(vars(args))
+    dict_args.update(config)
+    logger = EpochLogger(args.log_dir, seed=str(args.seed), verbose=not quiet, use_tensorboard=not quiet)
+    logger.save_config(dict_args)
+    logger.setup_torch_saver(policy.actor)
+    logger.log("Start with training.")
+    host_rng = getattr(args, "rng", "device") == "host"
+    roll_cls = DeviceTapeRollout if getattr(args, "resident_env", False) else Rollout
+    roll = roll_cls(env, policy, buffer, logger, args, device)
+    trust = TrustRegionUpdate(policy, config, device, logger=None if quiet else logger)
+    critics = CriticRegression(policy, config, host_rng, device)
+    timings = []
+    n_epochs = epochs if max_epochs is None else min(epochs, max_epochs)
+    for epoch in range(n_epochs):
+        t_roll = roll.run(T)
+        t1 = time.time()
+        if algo == "trpo_lag":
+            lagrange.update_lagrange_multiplier(logger.get_stats("Metrics/EpCost"))
+            data = buffer.get(lagrange.lagrangian_multiplier)
+            res = trust.run_trpo(data, data["adv"])
+        else:
+            data = buffer.get(0.0)
+            ep_costs = logger.get_stats("Metrics/EpCost") - args.cost_limit
+            res = trust.run_cpo(data, ep_costs)
+        cres = critics.run(data, res["stale_sumsq"])
+        buffer.reset_segments()
+        torch.cuda.synchronize()
+        t_upd = time.time() - t1
+        timings.append({"rollout": t_roll, "update": t_upd, "steps": cres["steps"], "acceptance": res["Misc/AcceptanceStep"]})
+        logger.store(**{k: v for k, v in res.items() if k.startswith(("Misc/", "Loss/", "Train/"))})
+        logger.store(**{"Loss/Loss_reward_critic": cres["loss_r"], "Loss/Loss_cost_critic": cres["loss_c"]})
+        if not logger.logged:
+            for k in ("Metrics/EpRet", "Metrics/EpCost", "Metrics/EpLen"):
+                logger.log_tabular(k)
+            logger.log_tabular("Train/Epoch", epoch + 1)
+            logger.log_tabular("Train/TotalSteps", (epoch + 1) * args.steps_per_epoch)
+            if algo == "trpo_lag":
+                logger.log_tabular("Train/LagragianMultiplier", lagrange.lagrangian_multiplier)
+            logger.log_tabular("Train/KL")
+            for k in ("Loss/Loss_reward_critic", "Loss/Loss_cost_critic", "Loss/Loss_actor"):
+                logger.log_tabular(k)
+            logger.log_tabular("Time/Rollout", t_roll)
+            logger.log_tabular("Time/Update", t_upd)
+            logger.log_tabular("Time/Total", t_roll + t_upd)
+            logger.log_tabular("Value/RewardAdv", data["adv_r"].mean().item())
+            logger.log_tabular("Value/CostAdv", data["adv_c"].mean().item())
+            for k in ("Misc/Alpha", "Misc/FinalStepNorm", "Misc/xHx", "Misc/gradient_norm", "Misc/H_inv_g", "Misc/AcceptanceStep"):
+                logger.log_tabular(k)
+            logger.dump_tabular()
+            if (epoch + 1) % 100 == 0 or epoch == 0:
+                logger.torch_save(itr=epoch)
+                logger.save_state({"Normalizer": getattr(env, "obs_rms", None)}, itr=epoch)
+    logger.close()
+    return policy, logger, timings, {"rollout": roll, "trust": trust, "critics": critics, "lagrange": lagrange, "buffer": buffer}
+
+
+# ---------------------------------------------------------------------------------------
 # generic main() of the PPO-family scripts
 # ---------------------------------------------------------------------------------------
 

@@ -388,3 +388,104 @@ def test_trainer_tracks_oracle_trainer(tmp_path, algo):
     # first-epoch rollout (before any update) must agree to fp32 rounding: compare actor weights loosely after 2 epochs
     for k, v in opol.nets["actor"].items():
         assert float((pol.actor.state_dict()[k].cpu() - v.detach()).abs().max()) < 5e-3, k
+
+
+# ---------------------------------------------------------------------------------------
+# C1-C5: trust-region pieces
+# ---------------------------------------------------------------------------------------
+
+def _trust_setup(golden):
+    dev = _cuda()
+    from safepo.single_agent._engine import TrustRegionUpdate
+    c = golden("trust")["trust"]
+    pol = make_policy(c["state"], c["D"], c["A"])
+    cfg = dict(hidden_sizes=[64, 64], gamma=0.99, target_kl=0.01, batch_size=128, learning_iters=10, max_grad_norm=40.0)
+    tr = TrustRegionUpdate(pol, cfg, dev)
+    data = {k: v.to(dev).contiguous() for k, v in c["data"].items()}
+    return c, pol, tr, data, dev
+
+
+def test_surrogate_grad_vs_reference(golden):
+    c, pol, tr, data, dev = _trust_setup(golden)
+    loss = tr._grad(data, data["adv_r"], tr.g)
+    assert close(loss, c["surr"], rtol=RTOL, atol=1e-7)[0], (float(loss), float(c["surr"]))
+    err = (tr.g.cpu() - c["surr_grad"]).norm() / c["surr_grad"].norm()
+    assert float(err) < 1e-5, float(err)
+    ok, ea, er = close(tr.g, c["surr_grad"], rtol=1e-4, atol=1e-7)
+    assert ok, (ea, er)
+
+
+def test_fvp_closed_form_vs_reference_double_backprop(golden):
+    c, pol, tr, data, dev = _trust_setup(golden)
+    tr._fvp(data, c["v"].to(dev), tr.Fx)
+    err = (tr.Fx.cpu() - c["Fv"]).norm() / c["Fv"].norm()
+    assert float(err) < 1e-5, float(err)          # the closed form equals cpo.fvp
+    # linearity (size-independent property): F(2v) == 2 F(v) up to the damping-consistent scaling
+    out2 = torch.zeros_like(tr.Fx)
+    tr._fvp(data, (2 * c["v"]).to(dev), out2)
+    assert float((out2 - 2 * tr.Fx).abs().max()) < 1e-5 * float(tr.Fx.abs().max()) + 1e-7
+
+
+def test_conjugate_gradient_on_device_vs_reference(golden):
+    c, pol, tr, data, dev = _trust_setup(golden)
+    tr._cg(data, c["rhs"].to(dev), tr.x)
+    x = tr.x.cpu()
+    err = (x - c["cg_x"]).norm() / c["cg_x"].norm()
+    assert float(err) < 2e-3, float(err)          # 15 fp32 CG iterations amplify 1e-7-level FVP differences
+    # the solve itself: residual of (H + 0.1 I) x = b measured with the reference's autograd FVP on the oracle
+    opol = oracle_policy(c["state"], c["D"], c["A"])
+    r_mine = O.fvp_autograd(opol, c["data"]["obs"], x) - c["rhs"]
+    r_ref = O.fvp_autograd(opol, c["data"]["obs"], c["cg_x"]) - c["rhs"]
+    assert float(r_mine.norm()) <= 1.5 * float(r_ref.norm()) + 1e-6
+
+
+def test_linesearch_eval_vs_oracle(golden):
+    c, pol, tr, data, dev = _trust_setup(golden)
+    tr._old_dist(data)
+    opol = oracle_policy(c["state"], c["D"], c["A"])
+    with torch.no_grad():
+        om, os_ = O.actor_mean_std(opol, c["data"]["obs"])
+        om, os_ = om.clone(), os_.clone()
+    g = torch.Generator().manual_seed(2)
+    step = 0.02 * torch.randn(c["P"], generator=g)
+    pol.actor_flat().add_(step.to(dev))
+    O.set_flat_params(opol, O.flat_params(opol) + step)
+    out = tr._eval(data, data["adv_r"], data["adv_c"])
+    d = c["data"]
+    with torch.no_grad():
+        want0 = O.surrogate_loss(opol, d["obs"], d["act"], d["log_prob"], d["adv_r"])
+        want1 = O.surrogate_loss(opol, d["obs"], d["act"], d["log_prob"], d["adv_c"])
+        m, s = O.actor_mean_std(opol, d["obs"])
+        want2 = O.normal_kl(om, os_, m, s).mean()
+    for got, want in zip(out, (want0, want1, want2)):
+        assert close(got, want, rtol=2e-5, atol=1e-7)[0], (float(got), float(want))
+
+
+@pytest.mark.parametrize("algo", ["cpo", "trpo_lag"])
+def test_trust_region_trainer_tracks_oracle(tmp_path, algo):
+    import csv
+    import importlib
+    from safepo.common import synthetic_env as senv
+    from safepo.utils.config import single_agent_args
+    mod = importlib.import_module(f"safepo.single_agent.{algo}")
+    N, T, L_ep = 5, 160, 40
+    task = "SafetyCarButton1-v0" if algo == "cpo" else "SafetyPointGoal1-v0"
+    argv = ["--seed", "5", "--num-envs", str(N), "--steps-per-epoch", str(N * T), "--total-steps", str(2 * N * T), "--task", task,
+            "--rng", "host", "--gae", "exact", "--log-dir", str(tmp_path)]
+    args, _ = single_agent_args(argv)
+    args.log_dir = str(tmp_path / "exp" / task / algo / "run")
+    D, A = senv.TASK_DIMS[task]
+    env = senv.SyntheticVecEnv(N, D, A, episode_len=L_ep, seed=5, stagger=True, p_terminate=0.01)
+    pol, logger, timings, _ = mod.main(args, env=env, quiet=True)
+    oargs = TR.default_args(seed=5, num_envs=N, steps_per_epoch=N * T, total_steps=2 * N * T, task=task)
+    oenv = senv.SyntheticVecEnv(N, D, A, episode_len=L_ep, seed=5, stagger=True, p_terminate=0.01)
+    opol, olog, _ = TR.train(algo, oargs, oenv)
+    rows = list(csv.DictReader(open(tmp_path / "exp" / task / algo / "run" / "progress.csv")))
+    assert len(rows) == len(olog.rows) == 2
+    for got, want in zip(rows, olog.rows):
+        for k in ("Metrics/EpRet", "Metrics/EpCost", "Metrics/EpLen", "Train/Epoch", "Train/TotalSteps"):
+            assert float(got[k]) == pytest.approx(float(want[k]), rel=1e-6, abs=1e-9), k
+        assert int(float(got["Misc/AcceptanceStep"])) == int(want["Misc/AcceptanceStep"])
+        for k in ("Misc/Alpha", "Misc/xHx", "Misc/gradient_norm", "Misc/H_inv_g", "Misc/FinalStepNorm", "Loss/Loss_actor", "Train/KL",
+                  "Loss/Loss_reward_critic", "Loss/Loss_cost_critic"):
+            assert float(got[k]) == pytest.approx(float(want[k]), rel=5e-3, abs=5e-5), (k, got[k], want[k])
