@@ -176,6 +176,44 @@ int spo_pg_update(const spo_dims* d, float* params, float* adam_m, float* adam_v
                   const spo_batch* data, const int64_t* perm, int64_t perm_len, int batch,
                   spo_loss_kind kind, const spo_hparams* hp, spo_update_ctrl* ctrl, void* stream);
 
+/* ---- data-parallel variant: ranks own disjoint env shards and hold
+ * identical replicas of the weights; every minibatch step each net's gradient is summed
+ * over the ranks INSIDE the persistent kernel through peer-mapped memory over
+ * NVLink/NVSwitch (no NCCL call, no extra launch): a CTA publishes its gradient to its own
+ * staging buffer, raises a sequence flag (release.sys), then pulls the peers' buffers
+ * (acquire.sys + relaxed.sys loads) and accumulates them in rank order, so all ranks obtain
+ * bit-identical sums and the replicas never diverge.  The result is scaled by 1/world
+ * (global minibatch = world * batch).
+ *   grad_bufs[r] : rank r's staging buffer, 2*3*slot floats (slot from spo_comm_slot_floats)
+ *   flags[r]     : rank r's 3 uint32 sequence flags (zero-initialised)
+ *   seq_base     : number of minibatch steps all ranks have completed in earlier launches
+ * Both pointer tables live in DEVICE memory (world entries each). */
+typedef struct spo_comm {
+  int world, rank;
+  float* const* grad_bufs;
+  unsigned int* const* flags;
+  unsigned long long seq_base;
+  unsigned int spin_limit;   /* 0 = default (~2e8 polls) before the kernel gives up and sets ctrl->stop = 2 */
+} spo_comm;
+
+int spo_comm_slot_floats(const spo_dims* d, int* slot_floats);
+int spo_pg_update_dp(const spo_dims* d, float* params, float* adam_m, float* adam_v, int* adam_t,
+                     const spo_batch* data, const int64_t* perm, int64_t perm_len, int batch,
+                     spo_loss_kind kind, const spo_hparams* hp, spo_update_ctrl* ctrl,
+                     const spo_comm* comm, void* stream);
+/* Peer mapping helpers (CUDA IPC): the staging buffers must be plain cudaMalloc memory, so
+ * these are the only entry points that allocate.  handle is 64 bytes. */
+int spo_comm_alloc(size_t bytes, void** ptr);
+int spo_comm_free(void* ptr);
+int spo_comm_export(void* ptr, unsigned char* handle64);
+int spo_comm_import(const unsigned char* handle64, void** ptr);
+int spo_comm_close(void* imported_ptr);
+/* KL early-stop test split in two for multi-GPU: accumulate the local sum into
+ * ctrl->kl_sum, (all-reduce that double across ranks), then finalize with the global count. */
+int spo_actor_kl_accumulate(const spo_dims* d, const float* params, const float* obs, const float* old_mean,
+                            const float* old_log_std, int64_t count, spo_update_ctrl* ctrl, void* stream);
+int spo_kl_finalize(spo_update_ctrl* ctrl, double denom, float target_kl, void* stream);
+
 /* ---- U2: full-batch actor passes -------------------------------------------------------
  * spo_actor_forward: mean [S,A] of policy.actor(obs) (old_distribution, ppo_lag.py:277).
  * spo_actor_kl: KL(N(old_mean, exp(old_log_std)) || N(mean(obs), exp(log_std))) with

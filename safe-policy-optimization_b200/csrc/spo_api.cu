@@ -57,4 +57,39 @@ int spo_param_offsets(const spo_dims* d, int net, int* log_std, int* w1, int* b1
   return SPO_OK;
 }
 
+int spo_comm_alloc(size_t bytes, void** ptr) {
+  SPO_REQUIRE(ptr && bytes > 0, SPO_ERR_INVALID_ARG, "spo_comm_alloc: null output or zero size");
+  SPO_CUDA_TRY(cudaMalloc(ptr, bytes));
+  SPO_CUDA_TRY(cudaMemset(*ptr, 0, bytes));
+  SPO_CUDA_TRY(cudaDeviceSynchronize());
+  return SPO_OK;
+}
+
+int spo_comm_free(void* ptr) {
+  SPO_CUDA_TRY(cudaFree(ptr));
+  return SPO_OK;
+}
+
+int spo_comm_export(void* ptr, unsigned char* handle64) {
+  SPO_REQUIRE(ptr && handle64, SPO_ERR_INVALID_ARG, "spo_comm_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+  cudaIpcMemHandle_t h;
+  SPO_CUDA_TRY(cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, 64);
+  return SPO_OK;
+}
+
+int spo_comm_import(const unsigned char* handle64, void** ptr) {
+  SPO_REQUIRE(ptr && handle64, SPO_ERR_INVALID_ARG, "spo_comm_import: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  SPO_CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return SPO_OK;
+}
+
+int spo_comm_close(void* imported_ptr) {
+  SPO_CUDA_TRY(cudaIpcCloseMemHandle(imported_ptr));
+  return SPO_OK;
+}
+
 }  // extern "C"

@@ -18,7 +18,7 @@ struct FbArgs {
   const float* old_log_std;
   float* mean_out;
   int64_t count;
-  int D, A, mode, reduce;   // mode 0: write means, 1: KL
+  int D, A, mode, reduce;   // mode 0: write means, 1: KL (accumulate + finalize), 2: KL accumulate only
   float target_kl;
   spo_update_ctrl* ctrl;
 };
@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(SPO_THREADS) spo_fullbatch_kernel(const FbArgs
   __shared__ double red[SPO_THREADS / 32];
   __shared__ bool is_last;
   const int tid = threadIdx.x;
-  if (a.mode == 1 && *reinterpret_cast<volatile int*>(&a.ctrl->stop)) return;
+  if (a.mode >= 1 && *reinterpret_cast<volatile int*>(&a.ctrl->stop)) return;
   const int D = a.D, A = a.A, Dp = spo_pad4(D), ldx = spo_ld(D);
   const SpoNetOff off = spo_net_off(D, A, 0);
   SpoNetSmem w;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(SPO_THREADS) spo_fullbatch_kernel(const FbArgs
       acc += static_cast<double>(kl);
     }
   }
-  if (a.mode != 1) return;
+  if (a.mode == 0) return;
   acc = spo_warp_sum(acc);
   if ((tid & 31) == 0) red[tid >> 5] = acc;
   __syncthreads();
@@ -82,9 +82,12 @@ __global__ void __launch_bounds__(SPO_THREADS) spo_fullbatch_kernel(const FbArgs
     double s = 0.0;
     for (int i = 0; i < SPO_THREADS / 32; ++i) s += red[i];
     atomicAdd(&a.ctrl->kl_sum, s);
-    __threadfence();
-    const unsigned t = atomicAdd(&a.ctrl->ticket, 1u);
-    is_last = (t == gridDim.x - 1);
+    is_last = false;
+    if (a.mode == 1) {
+      __threadfence();
+      const unsigned t = atomicAdd(&a.ctrl->ticket, 1u);
+      is_last = (t == gridDim.x - 1);
+    }
   }
   __syncthreads();
   if (is_last && tid == 0) {
@@ -115,9 +118,37 @@ int launch_fullbatch(const FbArgs& a, cudaStream_t stream) {
   return SPO_OK;
 }
 
+__global__ void spo_kl_finalize_kernel(spo_update_ctrl* ctrl, double denom, float target_kl) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (ctrl->stop) { ctrl->kl_sum = 0.0; return; }
+  const float kl = static_cast<float>(ctrl->kl_sum / denom);
+  ctrl->final_kl = kl;
+  ctrl->passes += 1;
+  if (kl > target_kl) ctrl->stop = 1;
+  ctrl->kl_sum = 0.0;
+}
+
 }  // namespace
 
 extern "C" {
+
+int spo_actor_kl_accumulate(const spo_dims* d, const float* params, const float* obs, const float* old_mean,
+                            const float* old_log_std, int64_t count, spo_update_ctrl* ctrl, void* stream) {
+  int rc = spo_check_dims(d);
+  if (rc) return rc;
+  SPO_REQUIRE(params && obs && old_mean && old_log_std && ctrl && count > 0, SPO_ERR_INVALID_ARG, "spo_actor_kl_accumulate: null pointer or count<=0");
+  FbArgs a{};
+  a.params = params; a.obs = obs; a.old_mean = old_mean; a.old_log_std = old_log_std; a.count = count;
+  a.D = d->obs_dim; a.A = d->act_dim; a.mode = 2; a.ctrl = ctrl;
+  return launch_fullbatch(a, static_cast<cudaStream_t>(stream));
+}
+
+int spo_kl_finalize(spo_update_ctrl* ctrl, double denom, float target_kl, void* stream) {
+  SPO_REQUIRE(ctrl && denom > 0, SPO_ERR_INVALID_ARG, "spo_kl_finalize: null ctrl or denom<=0");
+  spo_kl_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(ctrl, denom, target_kl);
+  SPO_CUDA_TRY(cudaGetLastError());
+  return SPO_OK;
+}
 
 int spo_actor_forward(const spo_dims* d, const float* params, const float* obs, int64_t count,
                       float* mean_out, void* stream) {

@@ -36,7 +36,28 @@ struct UpdArgs {
   int batch, kind, D, A;
   spo_hparams hp;
   spo_update_ctrl* ctrl;
+  spo_comm comm;   // world <= 1: single GPU
 };
+
+// system-scope accesses for the cross-GPU gradient exchange (peer memory over NVLink)
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys_f(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
@@ -88,8 +109,10 @@ struct SmallMap {
 template <int NT1>
 __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArgs a) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ int comm_dead;   // a peer never showed up: stop waiting (ctrl->stop = 2 tells the host)
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
+  if (threadIdx.x == 0) comm_dead = 0;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   spo_update_ctrl* ctrl = a.ctrl;
   if (*reinterpret_cast<volatile int*>(&ctrl->stop)) return;  // whole cluster takes this branch together
@@ -457,6 +480,87 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
 
     if (!last_tile) continue;   // next tile of the same step accumulates into the same gradients
 
+    // ---------------- cross-GPU gradient sum (data-parallel ranks), in rank order ----------------
+    if (a.comm.world > 1 && active) {
+      __syncthreads();  // gsmall complete
+      const int world = a.comm.world, me = a.comm.rank;
+      const unsigned seq = static_cast<unsigned>(a.comm.seq_base + static_cast<unsigned long long>(step_idx) + 1ull);
+      const size_t slot = static_cast<size_t>(SPO_THREADS) * 16 * (1 + NT1) + spn;
+      const size_t slot_off = (static_cast<size_t>(seq & 1u) * 3 + net) * slot;
+      float4* mine = reinterpret_cast<float4*>(a.comm.grad_bufs[me] + slot_off);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mine[i * SPO_THREADS + tid] = make_float4(gW2[i][0], gW2[i][1], gW2[i][2], gW2[i][3]);
+#pragma unroll
+      for (int t = 0; t < NT1; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          mine[(4 + t * 4 + i) * SPO_THREADS + tid] = make_float4(gW1[t][i][0], gW1[t][i][1], gW1[t][i][2], gW1[t][i][3]);
+      float* mine_small = reinterpret_cast<float*>(mine + (4 + 4 * NT1) * SPO_THREADS);
+      for (int i = tid; i < SP; i += SPO_THREADS) mine_small[i] = gsmall[i];
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) st_release_sys(a.comm.flags[me] + net, seq);
+      if (tid < world && tid != me && !comm_dead) {
+        const unsigned limit = a.comm.spin_limit ? a.comm.spin_limit : 50000000u;
+        const unsigned* f = a.comm.flags[tid] + net;
+        unsigned polls = 0;
+        while (static_cast<int>(ld_acquire_sys(f) - seq) < 0) {
+          if (++polls > limit) { comm_dead = 1; atomicExch(&ctrl->stop, 2); break; }
+        }
+      }
+      __syncthreads();
+      float sW2[4][4], sW1[NT1][4][4];
+      spo_zero(sW2);
+#pragma unroll
+      for (int t = 0; t < NT1; ++t) spo_zero(sW1[t]);
+      for (int r = 0; r < world; ++r) {
+        if (r == me) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              sW2[i][j] += gW2[i][j];
+#pragma unroll
+              for (int t = 0; t < NT1; ++t) sW1[t][i][j] += gW1[t][i][j];
+            }
+        } else {
+          const float4* peer = reinterpret_cast<const float4*>(a.comm.grad_bufs[r] + slot_off);
+          float4 v2[4], v1[NT1][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v2[i] = ld_relaxed_sys_f4(peer + i * SPO_THREADS + tid);
+#pragma unroll
+          for (int t = 0; t < NT1; ++t)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v1[t][i] = ld_relaxed_sys_f4(peer + (4 + t * 4 + i) * SPO_THREADS + tid);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            sW2[i][0] += v2[i].x; sW2[i][1] += v2[i].y; sW2[i][2] += v2[i].z; sW2[i][3] += v2[i].w;
+#pragma unroll
+            for (int t = 0; t < NT1; ++t) {
+              sW1[t][i][0] += v1[t][i].x; sW1[t][i][1] += v1[t][i].y; sW1[t][i][2] += v1[t][i].z; sW1[t][i][3] += v1[t][i].w;
+            }
+          }
+        }
+      }
+      const float inv_w = __fdiv_rn(1.f, static_cast<float>(world));
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          gW2[i][j] = __fmul_rn(sW2[i][j], inv_w);
+#pragma unroll
+          for (int t = 0; t < NT1; ++t) gW1[t][i][j] = __fmul_rn(sW1[t][i][j], inv_w);
+        }
+      for (int i = tid; i < SP; i += SPO_THREADS) {
+        float sm_ = 0.f;
+        for (int r = 0; r < world; ++r) {
+          if (r == me) sm_ += gsmall[i];
+          else sm_ += ld_relaxed_sys_f(reinterpret_cast<const float*>(reinterpret_cast<const float4*>(a.comm.grad_bufs[r] + slot_off) + (4 + 4 * NT1) * SPO_THREADS) + i);
+        }
+        gsmall[i] = __fmul_rn(sm_, inv_w);
+      }
+    }
+
     // ---------------- joint gradient norm (cluster-wide), clip, Adam ----------------
     float ss = 0.f, th2 = 0.f;
     if (active) {
@@ -682,9 +786,25 @@ int launch_update(const UpdArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
+extern "C" int spo_comm_slot_floats(const spo_dims* d, int* slot_floats) {
+  int rc = spo_check_dims(d);
+  if (rc) return rc;
+  SPO_REQUIRE(slot_floats, SPO_ERR_INVALID_ARG, "spo_comm_slot_floats: null output");
+  const int nt1 = spo_pad4(d->obs_dim) <= 64 ? 1 : 2;
+  *slot_floats = SPO_THREADS * 16 * (1 + nt1) + spo_pad4(2 * SPO_HID + d->act_dim * SPO_HID + 2 * d->act_dim);
+  return SPO_OK;
+}
+
 extern "C" int spo_pg_update(const spo_dims* d, float* params, float* adam_m, float* adam_v, int* adam_t,
                              const spo_batch* data, const int64_t* perm, int64_t perm_len, int batch,
                              spo_loss_kind kind, const spo_hparams* hp, spo_update_ctrl* ctrl, void* stream) {
+  return spo_pg_update_dp(d, params, adam_m, adam_v, adam_t, data, perm, perm_len, batch, kind, hp, ctrl, nullptr, stream);
+}
+
+extern "C" int spo_pg_update_dp(const spo_dims* d, float* params, float* adam_m, float* adam_v, int* adam_t,
+                                const spo_batch* data, const int64_t* perm, int64_t perm_len, int batch,
+                                spo_loss_kind kind, const spo_hparams* hp, spo_update_ctrl* ctrl,
+                                const spo_comm* comm, void* stream) {
   int rc = spo_check_dims(d);
   if (rc) return rc;
   SPO_REQUIRE(params && adam_m && adam_v && adam_t && data && perm && hp && ctrl, SPO_ERR_INVALID_ARG, "spo_pg_update: null argument");
@@ -702,6 +822,13 @@ extern "C" int spo_pg_update(const spo_dims* d, float* params, float* adam_m, fl
   a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.adam_t = adam_t;
   a.data = *data; a.perm = perm; a.perm_len = perm_len; a.batch = batch; a.kind = kind;
   a.D = d->obs_dim; a.A = d->act_dim; a.hp = *hp; a.ctrl = ctrl;
+  if (comm && comm->world > 1) {
+    SPO_REQUIRE(comm->rank >= 0 && comm->rank < comm->world && comm->world <= 32 && comm->grad_bufs && comm->flags,
+                SPO_ERR_INVALID_ARG, "spo_pg_update_dp: bad spo_comm (world=%d rank=%d)", comm->world, comm->rank);
+    a.comm = *comm;
+  } else {
+    a.comm.world = 1;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (spo_pad4(d->obs_dim) <= 64) return launch_update<1>(a, st);
   return launch_update<2>(a, st);

@@ -45,11 +45,17 @@ class HParams(C.Structure):
                 ("focops_lam", C.c_float), ("focops_kl", C.c_float), ("value_coef", C.c_float)]
 
 
+class Comm(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("grad_bufs", C.c_void_p), ("flags", C.c_void_p),
+                ("seq_base", C.c_ulonglong), ("spin_limit", C.c_uint)]
+
+
 # numpy view of spo_update_ctrl (64 bytes): see include/spo.h
 CTRL_BYTES = 64
 CTRL_DTYPE = [("loss_sum", "<f8", 3), ("kl_sum", "<f8"), ("steps", "<i8"), ("stop", "<i4"), ("passes", "<i4"),
               ("final_kl", "<f4"), ("ticket", "<u4"), ("extra_sumsq", "<f4"), ("pad", "<i4")]
 CTRL_EXTRA_SUMSQ_F32_INDEX = 14  # byte offset 56
+CTRL_KL_SUM_F64_INDEX = 3        # byte offset 24
 
 LOSS_PPO_CLIP, LOSS_FOCOPS, LOSS_CRITIC_ONLY = 0, 1, 2
 
@@ -83,6 +89,15 @@ def _declare(L):
         "spo_adv_stats": [p, p, i64, p, p],
         "spo_adv_apply": [p, p, i64, p, i, i, f, f, p, p],
         "spo_pg_update": [PD, p, p, p, p, C.POINTER(Batch), p, i64, i, i, C.POINTER(HParams), p, p],
+        "spo_comm_slot_floats": [PD, C.POINTER(i)],
+        "spo_pg_update_dp": [PD, p, p, p, p, C.POINTER(Batch), p, i64, i, i, C.POINTER(HParams), p, C.POINTER(Comm), p],
+        "spo_comm_alloc": [C.c_size_t, C.POINTER(p)],
+        "spo_comm_free": [p],
+        "spo_comm_export": [p, C.c_char_p],
+        "spo_comm_import": [C.c_char_p, C.POINTER(p)],
+        "spo_comm_close": [p],
+        "spo_actor_kl_accumulate": [PD, p, p, p, p, i64, p, p],
+        "spo_kl_finalize": [p, d, f, p],
         "spo_actor_forward": [PD, p, p, i64, p, p],
         "spo_actor_kl": [PD, p, p, p, p, i64, i, f, p, p],
         "spo_surrogate_grad": [PD, p, p, p, p, p, i64, p, p, p],
@@ -99,14 +114,15 @@ def _declare(L):
 EXPORTS = ("spo_version", "spo_last_error", "spo_sync_check", "spo_param_count", "spo_param_offsets",
            "spo_policy_step", "spo_critic_values", "spo_store_transition", "spo_gae_dual", "spo_adv_stats",
            "spo_adv_apply", "spo_pg_update", "spo_actor_forward", "spo_actor_kl", "spo_surrogate_grad", "spo_fvp",
-           "spo_linesearch_eval", "spo_conjugate_gradient")
+           "spo_linesearch_eval", "spo_conjugate_gradient", "spo_comm_slot_floats", "spo_pg_update_dp", "spo_comm_alloc",
+           "spo_comm_free", "spo_comm_export", "spo_comm_import", "spo_comm_close", "spo_actor_kl_accumulate", "spo_kl_finalize")
 
 
 # number of libspo kernels launched so far (bench.py reports the delta over its timed region)
 LAUNCHES = {"n": 0}
 _KERNEL_CALLS = {"spo_policy_step", "spo_critic_values", "spo_store_transition", "spo_gae_dual", "spo_adv_stats",
                  "spo_adv_apply", "spo_pg_update", "spo_actor_forward", "spo_actor_kl", "spo_surrogate_grad", "spo_fvp",
-                 "spo_linesearch_eval"}
+                 "spo_linesearch_eval", "spo_pg_update_dp", "spo_actor_kl_accumulate", "spo_kl_finalize"}
 
 
 def check(rc, what):

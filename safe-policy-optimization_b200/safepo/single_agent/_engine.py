@@ -251,8 +251,12 @@ class DeviceTapeRollout(Rollout):
 # ---------------------------------------------------------------------------------------
 
 class PolicyGradientUpdate:
-    def __init__(self, policy, cfg, kind, epochs, host_rng, device, focops_lam=1.5):
+    def __init__(self, policy, cfg, kind, epochs, host_rng, device, focops_lam=1.5, dp=None):
         self.policy, self.cfg, self.kind, self.host_rng, self.device = policy, cfg, kind, host_rng, device
+        self.dp = dp          # safepo.common.dist.DataParallel or None
+        if dp is not None:
+            dp.broadcast(policy.flat)
+            dp.setup_peer_buffers(policy.dims, device)
         self.adam = AdamState(policy)
         self.sched = LinearDecay(3e-4, epochs)
         self.ctrl = make_ctrl(device)
@@ -293,12 +297,28 @@ class PolicyGradientUpdate:
                 perm = reference_order(S).to(self.device)
             else:
                 perm = torch.randperm(S, device=self.device)
-            L.check(lib.spo_pg_update(C.byref(d), L.ptr(pol.flat), L.ptr(self.adam.m), L.ptr(self.adam.v), L.ptr(self.adam.t),
-                                      C.byref(batch), L.ptr(perm), perm.numel(), cfg["batch_size"], self.kind, C.byref(self.hp),
-                                      L.ptr(self.ctrl), L.stream()), "spo_pg_update")
-            L.check(lib.spo_actor_kl(C.byref(d), L.ptr(pol.flat), L.ptr(data["obs"]), L.ptr(self.old_mean),
-                                     L.ptr(self.old_log_std), S, 0, cfg["target_kl"], L.ptr(self.ctrl), L.stream()),
-                    "spo_actor_kl")
+            if self.dp is None:
+                L.check(lib.spo_pg_update(C.byref(d), L.ptr(pol.flat), L.ptr(self.adam.m), L.ptr(self.adam.v), L.ptr(self.adam.t),
+                                          C.byref(batch), L.ptr(perm), perm.numel(), cfg["batch_size"], self.kind, C.byref(self.hp),
+                                          L.ptr(self.ctrl), L.stream()), "spo_pg_update")
+                L.check(lib.spo_actor_kl(C.byref(d), L.ptr(pol.flat), L.ptr(data["obs"]), L.ptr(self.old_mean),
+                                         L.ptr(self.old_log_std), S, 0, cfg["target_kl"], L.ptr(self.ctrl), L.stream()),
+                        "spo_actor_kl")
+            else:
+                # ranks hold equal-sized shards; gradients are summed inside the kernel over NVLink
+                comm = self.dp.comm_struct()
+                L.check(lib.spo_pg_update_dp(C.byref(d), L.ptr(pol.flat), L.ptr(self.adam.m), L.ptr(self.adam.v),
+                                             L.ptr(self.adam.t), C.byref(batch), L.ptr(perm), perm.numel(), cfg["batch_size"],
+                                             self.kind, C.byref(self.hp), L.ptr(self.ctrl), C.byref(comm), L.stream()),
+                        "spo_pg_update_dp")
+                self.dp.advance((perm.numel() + cfg["batch_size"] - 1) // cfg["batch_size"])
+                L.check(lib.spo_actor_kl_accumulate(C.byref(d), L.ptr(pol.flat), L.ptr(data["obs"]), L.ptr(self.old_mean),
+                                                    L.ptr(self.old_log_std), S, L.ptr(self.ctrl), L.stream()),
+                        "spo_actor_kl_accumulate")
+                kl_sum = self.ctrl.view(torch.float64)[L.CTRL_KL_SUM_F64_INDEX:L.CTRL_KL_SUM_F64_INDEX + 1]
+                self.dp.all_reduce_sum(kl_sum)
+                L.check(lib.spo_kl_finalize(L.ptr(self.ctrl), float(S * self.dp.world), cfg["target_kl"], L.stream()),
+                        "spo_kl_finalize")
             self.launches += 2
             if self.host_rng or perms is not None:
                 # the reference stops drawing permutations once KL trips: stay in lock-step with its RNG
@@ -632,8 +652,9 @@ def make_env(args):
     return make_synthetic_env(args.num_envs, args.task, args.seed, episode_len=getattr(args, "episode_len", 1000))
 
 
-def run_policy_gradient(args, config, algo, env=None, max_epochs=None, quiet=False):
-    """main() of ppo_lag.py / focops.py.  Returns (policy, logger, per-epoch timing list)."""
+def run_policy_gradient(args, config, algo, env=None, max_epochs=None, quiet=False, dp=None):
+    """main() of ppo_lag.py / focops.py.  Returns (policy, logger, per-epoch timing list).
+    ``dp``: a safepo.common.dist.DataParallel when launched one process per GPU."""
     seed_all(args.seed)
     if args.device != "cuda":
         raise L.SpoError("this build has no CPU path: run with --device cuda")
@@ -659,15 +680,16 @@ def run_policy_gradient(args, config, algo, env=None, max_epochs=None, quiet=Fal
     host_rng = getattr(args, "rng", "device") == "host"
     roll_cls = DeviceTapeRollout if getattr(args, "resident_env", False) else Rollout
     roll = roll_cls(env, policy, buffer, logger, args, device)
-    upd = PolicyGradientUpdate(policy, config, L.LOSS_PPO_CLIP if algo == "ppo_lag" else L.LOSS_FOCOPS, epochs, host_rng, device)
+    upd = PolicyGradientUpdate(policy, config, L.LOSS_PPO_CLIP if algo == "ppo_lag" else L.LOSS_FOCOPS, epochs, host_rng, device,
+                               dp=dp)
     timings = []
     n_epochs = epochs if max_epochs is None else min(epochs, max_epochs)
     for epoch in range(n_epochs):
         t_roll = roll.run(T)
         t1 = time.time()
-        ep_costs = logger.get_stats("Metrics/EpCost")
+        ep_costs = logger.get_stats("Metrics/EpCost") if dp is None else dp.mean_episode_cost(logger, device=device)
         lagrange.update_lagrange_multiplier(ep_costs)
-        data = buffer.get(lagrange.lagrangian_multiplier)
+        data = buffer.get(lagrange.lagrangian_multiplier, all_reduce=None if dp is None else dp.all_reduce_sum)
         res = upd.run(data)
         buffer.reset_segments()
         torch.cuda.synchronize()
