@@ -119,7 +119,7 @@ class ClockSampler:
 # our arm
 # ---------------------------------------------------------------------------------------
 
-def build_trainer(args, device, rank, resident):
+def build_trainer(args, device, rank, resident, dp=None):
     """The public trainer objects of safepo.single_agent.ppo_lag, assembled once so that
     epochs can be timed individually."""
     from safepo import _lib as L
@@ -144,16 +144,18 @@ def build_trainer(args, device, rank, resident):
     log_dir = os.path.join(tempfile.mkdtemp(prefix="spo_bench_"), "exp", TASK, "ppo_lag", f"rank{rank}")
     logger = EpochLogger(log_dir, seed=str(rank), verbose=False, use_tensorboard=False)
     roll = (DeviceTapeRollout if resident else Rollout)(env, policy, buffer, logger, a, device)
-    upd = PolicyGradientUpdate(policy, cfg, L.LOSS_PPO_CLIP, epochs=1000, host_rng=False, device=device)
-    return dict(env=env, policy=policy, buffer=buffer, lagrange=lagrange, logger=logger, roll=roll, upd=upd, T=T, N=N)
+    upd = PolicyGradientUpdate(policy, cfg, L.LOSS_PPO_CLIP, epochs=1000, host_rng=False, device=device, dp=dp)
+    return dict(env=env, policy=policy, buffer=buffer, lagrange=lagrange, logger=logger, roll=roll, upd=upd, T=T, N=N, dp=dp,
+                device=device)
 
 
 def one_epoch(tr):
     """Exactly the epoch body of run_policy_gradient (ppo_lag.main)."""
     tr["roll"].run(tr["T"])
-    jc = tr["logger"].get_stats("Metrics/EpCost")
+    dp = tr["dp"]
+    jc = tr["logger"].get_stats("Metrics/EpCost") if dp is None else dp.mean_episode_cost(tr["logger"], device=tr["device"])
     tr["lagrange"].update_lagrange_multiplier(jc)
-    data = tr["buffer"].get(tr["lagrange"].lagrangian_multiplier)
+    data = tr["buffer"].get(tr["lagrange"].lagrangian_multiplier, all_reduce=None if dp is None else dp.all_reduce_sum)
     res = tr["upd"].run(data)
     tr["buffer"].reset_segments()
     lg = tr["logger"]
@@ -297,13 +299,22 @@ def run_spo(args):
     K, W = args.steps, max(args.warmup, 0)
     S = args.num_envs * args.horizon
 
-    tr = build_trainer(args, device, rank, resident=True)
+    dp = None
+    if world > 1:
+        from safepo.common.dist import DataParallel
+        dp = DataParallel()
+    tr = build_trainer(args, device, rank, resident=True, dp=dp)
     val = timed_epochs(tr, K, W, world, device)
-    kern_ms, kern_steps = time_update_kernel(tr, device)
+    kern_ms, kern_steps = time_update_kernel(tr, device) if world == 1 else (float("nan"), 1)
     e2e = None
     if not args.no_e2e:
-        tr2 = build_trainer(args, device, rank, resident=False)
+        if dp is not None:
+            dp.close()
+            dp = DataParallel()
+        tr2 = build_trainer(args, device, rank, resident=False, dp=dp)
         e2e = timed_epochs(tr2, K, W, world, device)
+    if dp is not None:
+        dp.close()
 
     if rank != 0:
         if world > 1:
@@ -312,6 +323,9 @@ def run_spo(args):
     hbm, how = peaks()
     value = S * K * world / (val["ms"] / 1e3)
     passes = int(round(float(np.mean(val["stops"])))) or 1
+    if world > 1:   # per-launch timing is a single-GPU measurement; derive the per-step figure from the epoch
+        kern_steps = (S + 63) // 64
+        kern_ms = val["ms"] / K / max(passes, 1)
     alg_bytes = kern_steps * 64 * BYTES_PER_SAMPLE_UPDATE
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9
     out = {
@@ -323,7 +337,8 @@ def run_spo(args):
                    "samples_per_step_per_gpu": S, "stop_iter": val["stops"], "minibatch_steps_per_epoch": val["msteps"],
                    "us_per_minibatch_step": kern_ms * 1e3 / kern_steps, "ms_per_update_pass": kern_ms,
                    "l2": "inputs larger than L2 (245.8 MB observation buffer per epoch vs 126 MB L2)",
-                   "parallelism": f"dp{world}" if world > 1 else "single"},
+                   "parallelism": (f"dp{world}: envs sharded, per-rank batch 64 (global batch {64 * world}), in-kernel NVLink gradient sum per minibatch step"
+                                   if world > 1 else "single")},
         "clocks": val["clocks"],
         "gpu_launches": val["launches"],
         "roofline": {"kernel": "spo_update_kernel (one PPO-Lag pass = 16000 serial minibatch steps)", "bound": "hbm",
