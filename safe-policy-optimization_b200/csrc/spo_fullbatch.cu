@@ -9,6 +9,12 @@
 // pass's update kernel reads ctrl->stop itself).
 #include "spo_common.cuh"
 
+// tensor-core (tcgen05 + TMA) implementation for large batches, csrc/spo_tc_forward.cu:
+// 0 = ran, 1 = not applicable (small batch, D % 4 != 0, ...), < 0 = error
+int spo_tc_forward_launch(const spo_dims* d, const float* params, const float* obs, const float* old_mean,
+                          const float* old_log_std, float* mean_out, int64_t count, int mode, int reduce, float target_kl,
+                          spo_update_ctrl* ctrl, cudaStream_t stream);
+
 namespace {
 
 struct FbArgs {
@@ -137,6 +143,8 @@ int spo_actor_kl_accumulate(const spo_dims* d, const float* params, const float*
   int rc = spo_check_dims(d);
   if (rc) return rc;
   SPO_REQUIRE(params && obs && old_mean && old_log_std && ctrl && count > 0, SPO_ERR_INVALID_ARG, "spo_actor_kl_accumulate: null pointer or count<=0");
+  rc = spo_tc_forward_launch(d, params, obs, old_mean, old_log_std, nullptr, count, 2, 0, 0.f, ctrl, static_cast<cudaStream_t>(stream));
+  if (rc <= 0) return rc;
   FbArgs a{};
   a.params = params; a.obs = obs; a.old_mean = old_mean; a.old_log_std = old_log_std; a.count = count;
   a.D = d->obs_dim; a.A = d->act_dim; a.mode = 2; a.ctrl = ctrl;
@@ -155,6 +163,8 @@ int spo_actor_forward(const spo_dims* d, const float* params, const float* obs, 
   int rc = spo_check_dims(d);
   if (rc) return rc;
   SPO_REQUIRE(params && obs && mean_out && count > 0, SPO_ERR_INVALID_ARG, "spo_actor_forward: null pointer or count<=0");
+  rc = spo_tc_forward_launch(d, params, obs, nullptr, nullptr, mean_out, count, 0, 0, 0.f, nullptr, static_cast<cudaStream_t>(stream));
+  if (rc <= 0) return rc;
   FbArgs a{};
   a.params = params; a.obs = obs; a.mean_out = mean_out; a.count = count; a.D = d->obs_dim; a.A = d->act_dim; a.mode = 0;
   return launch_fullbatch(a, static_cast<cudaStream_t>(stream));
@@ -167,6 +177,8 @@ int spo_actor_kl(const spo_dims* d, const float* params, const float* obs, const
   if (rc) return rc;
   SPO_REQUIRE(params && obs && old_mean && old_log_std && ctrl && count > 0, SPO_ERR_INVALID_ARG, "spo_actor_kl: null pointer or count<=0");
   SPO_REQUIRE(reduce == 0 || reduce == 1, SPO_ERR_INVALID_ARG, "spo_actor_kl: reduce=%d", reduce);
+  rc = spo_tc_forward_launch(d, params, obs, old_mean, old_log_std, nullptr, count, 1, reduce, target_kl, ctrl, static_cast<cudaStream_t>(stream));
+  if (rc <= 0) return rc;
   FbArgs a{};
   a.params = params; a.obs = obs; a.old_mean = old_mean; a.old_log_std = old_log_std; a.count = count;
   a.D = d->obs_dim; a.A = d->act_dim; a.mode = 1; a.reduce = reduce; a.target_kl = target_kl; a.ctrl = ctrl;

@@ -489,3 +489,41 @@ def test_trust_region_trainer_tracks_oracle(tmp_path, algo):
         for k in ("Misc/Alpha", "Misc/xHx", "Misc/gradient_norm", "Misc/H_inv_g", "Misc/FinalStepNorm", "Loss/Loss_actor", "Train/KL",
                   "Loss/Loss_reward_critic", "Loss/Loss_cost_critic"):
             assert float(got[k]) == pytest.approx(float(want[k]), rel=5e-3, abs=5e-5), (k, got[k], want[k])
+
+
+# ---------------------------------------------------------------------------------------
+# tcgen05 / TMA full-batch forward (large S) against the oracle and the FFMA tile kernel
+# ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("D,A,S", [(60, 2, 4096 + 37), (60, 2, 128 * 1024), (28, 8, 2048 + 5), (64, 2, 1500)])
+def test_tensor_core_forward_and_kl_large_batch(D, A, S):
+    dev = _cuda()
+    from safepo import _lib as L
+    from safepo.common.model import ActorVCritic
+    from safepo.single_agent._engine import make_ctrl, read_ctrl
+    torch.manual_seed(D + A)
+    pol = ActorVCritic(D, A).to(dev)
+    with torch.no_grad():
+        pol.actor.log_std.copy_(torch.linspace(-0.4, 0.2, A))
+    opol = oracle_policy(policy_state(pol), D, A)
+    obs = torch.randn(S, D)
+    with torch.no_grad():
+        want, _ = O.actor_mean_std(opol, obs)
+    obs_d = obs.to(dev)
+    got = pol.actor_mean(obs_d)                                   # S >= 1024 and D % 4 == 0 -> tcgen05 path
+    ok, ea, er = close(got, want, rtol=RTOL, atol=2e-6)
+    assert ok, (D, A, S, ea, er)
+    chunks = torch.cat([pol.actor_mean(obs_d[i:i + 512]) for i in range(0, S, 512)])   # small batches -> FFMA tile kernel
+    assert float((chunks - got).abs().max()) < 5e-6
+    # KL against a perturbed "old" distribution
+    old_mean = (want + 0.05 * torch.randn(S, A)).contiguous()
+    old_ls = torch.linspace(-0.3, 0.1, A)
+    ctrl = make_ctrl(dev)
+    L.check(L.lib().spo_actor_kl(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(obs_d), L.ptr(old_mean.to(dev)), L.ptr(old_ls.to(dev)), S, 0,
+                                 1e9, L.ptr(ctrl), L.stream()), "spo_actor_kl")
+    r = read_ctrl(ctrl)
+    with torch.no_grad():
+        m, s = O.actor_mean_std(opol, obs)
+        want_kl = O.normal_kl(old_mean, torch.exp(old_ls), m, s).sum(-1, keepdim=True).mean().item()
+    assert abs(float(r["final_kl"]) - want_kl) <= 2e-5 * abs(want_kl) + 1e-7, (float(r["final_kl"]), want_kl)
+    assert int(r["passes"]) == 1
