@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-passes", type=int, default=40,
+                    help="update passes per epoch assumed by the reference arm (the GPU arm observes StopIter = 40 on this stream)")
     return ap.parse_args()
 
 
@@ -371,9 +373,10 @@ def run_reference(args):
     vals = []
     a2 = argparse.Namespace(**vars(args))
     a2.cpu_seconds = per
-    # KL early stop: with 16000 Adam steps per pass at S=1,024,000 the reference's own rule
-    # (ppo_lag.py:347) trips after the first pass; the GPU arm logs the count it observed.
-    passes = 1
+    # KL early stop (ppo_lag.py:347): on this synthetic stream (advantages uncorrelated with the
+    # observations) the KL never reaches target_kl, so all 40 passes run -- the GPU arm, which executes the
+    # same rule, logs StopIter = 40 in every epoch (profiles/r01_bench_default.json).
+    passes = args.ref_passes
     for i in range(K + W):
         r = cpu_baseline(a2, passes, kind="port", threads=threads)
         if i >= W:
