@@ -131,9 +131,24 @@ __device__ inline void spo_load_net(const float* __restrict__ params, const SpoN
 }
 
 // ---- register-tiled smem GEMM ----------------------------------------------------------
-// acc[mi][ni] += sum_k A[k][m0+mi] * B(n0+ni, k),  k in [0,K), K % 4 == 0.
+// Thread -> output tile map of a 64x64 output (256 threads, 4x4 outputs each).  A warp owns a
+// 32(m) x 16(n) patch: its 32 lanes cover 8 m-tiles x 4 n-tiles, so one warp-wide LDS.128 of
+// the A operand touches 8 distinct 16-byte chunks (128 contiguous bytes, one wavefront) and
+// one of the B operand 4 (profiles/r01_update_ncu.md: with the former 16 x 2 arrangement the
+// LSU was ~75 % busy next to the FMA pipe).
+//   m0           = first of 4 consecutive m
+//   spo_nb(tid)  = first of 4 consecutive n          (B k-major: float4 along n)
+//   spo_ns(tid)  = first of 4 n spaced 4 apart       (B n-major: rows ns, ns+4, ns+8, ns+12 --
+//                  the 4 n-tiles of a warp then read 4 consecutive rows per LDS, which are
+//                  conflict-free for every leading dimension == 4 (mod 8))
+__device__ __forceinline__ int spo_m0(int tid) { return ((((tid >> 5) & 1) << 3) + (tid & 7)) << 2; }
+__device__ __forceinline__ int spo_nb(int tid) { return (((tid >> 6) << 2) + ((tid >> 3) & 3)) << 2; }
+__device__ __forceinline__ int spo_ns(int tid) { return ((tid >> 6) << 4) + ((tid >> 3) & 3); }
+
+// acc[mi][ni] += sum_k A[k][m0+mi] * B(n(ni), k),  k in [0,K), K % 4 == 0.
 //   A is reduction-major: A[k*lda + m]   (float4 along m)
-//   B_N_MAJOR : B[n*ldb + k] (float4 along k)      else : B[k*ldb + n] (float4 along n)
+//   B_N_MAJOR : B[n*ldb + k] (float4 along k), n(ni) = n0 + 4*ni     (pass n0 = spo_ns(tid))
+//   else      : B[k*ldb + n] (float4 along n), n(ni) = n0 + ni       (pass n0 = spo_nb(tid))
 template <bool B_N_MAJOR>
 __device__ __forceinline__ void spo_tile_mma(float (&acc)[4][4], const float* __restrict__ A, int lda,
                                              const float* __restrict__ B, int ldb, int m0, int n0, int K) {
@@ -144,7 +159,7 @@ __device__ __forceinline__ void spo_tile_mma(float (&acc)[4][4], const float* __
     for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(A + (k + i) * lda + m0);
     if (B_N_MAJOR) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) b[i] = *reinterpret_cast<const float4*>(B + (n0 + i) * ldb + k);
+      for (int i = 0; i < 4; ++i) b[i] = *reinterpret_cast<const float4*>(B + (n0 + 4 * i) * ldb + k);
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
         const float bk[4] = {b[ni].x, b[ni].y, b[ni].z, b[ni].w};
@@ -187,14 +202,14 @@ __device__ __forceinline__ float spo_tanh(float x) { return tanhf(x); }
 
 // Hidden layer forward for a 64-row tile:  out[r][j] = tanh(b[j] + sum_k in[r][k] * wt[k][j]).
 // in: sample-major [64][ldin] with K (multiple of 4) valid columns; out: [64][LDH].
-// Thread tile: j = 4*(tid&15).., r = 4*(tid>>4)..
+// Thread tile: units j = m0..m0+3, rows r = ns, ns+4, ns+8, ns+12.
 __device__ __forceinline__ void spo_hidden_fwd(const float* __restrict__ in, int ldin, int K,
                                                const float* __restrict__ wt, const float* __restrict__ bias,
                                                float* __restrict__ out, int tid) {
-  const int m0 = (tid & 15) * 4, n0 = (tid >> 4) * 4;
+  const int m0 = spo_m0(tid), ns = spo_ns(tid);
   float acc[4][4];
   spo_zero(acc);
-  spo_tile_mma<true>(acc, wt, SPO_LDH, in, ldin, m0, n0, K);
+  spo_tile_mma<true>(acc, wt, SPO_LDH, in, ldin, m0, ns, K);
   const float4 b = *reinterpret_cast<const float4*>(bias + m0);
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni) {
@@ -203,7 +218,7 @@ __device__ __forceinline__ void spo_hidden_fwd(const float* __restrict__ in, int
     h.y = spo_tanh(acc[1][ni] + b.y);
     h.z = spo_tanh(acc[2][ni] + b.z);
     h.w = spo_tanh(acc[3][ni] + b.w);
-    *reinterpret_cast<float4*>(out + (n0 + ni) * SPO_LDH + m0) = h;
+    *reinterpret_cast<float4*>(out + (ns + 4 * ni) * SPO_LDH + m0) = h;
   }
 }
 

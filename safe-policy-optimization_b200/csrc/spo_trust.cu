@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_trust_kernel(const TrArgs 
   const int SP = 2 * SPO_HID + A * SPO_HID + 2 * A;
   for (int i = tid; i < 672; i += SPO_THREADS) gsmall[i] = 0.f;
 
-  const int j0 = (tid & 15) * 4, k0 = (tid >> 4) * 4;
+  const int j0 = spo_m0(tid), k0 = spo_nb(tid);   // 4x4 parameter tile (W2[j0..][k0..]; W1 tile 0 likewise)
+  const int rs = spo_ns(tid);                      // rows rs, rs+4, rs+8, rs+12 of the n-major GEMMs
   float gW2[4][4], gW1[NT1][4][4];
   spo_zero(gW2);
 #pragma unroll
@@ -148,35 +149,35 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_trust_kernel(const TrArgs 
       {  // dh1 = (x V1^T + c1) * (1 - h1^2)     -> b3
         float acc[4][4];
         spo_zero(acc);
-        spo_tile_mma<true>(acc, tv.w1t, SPO_LDH, x, ldx, j0, k0, Dp);   // m: unit j0.., n: row k0..
+        spo_tile_mma<true>(acc, tv.w1t, SPO_LDH, x, ldx, j0, rs, Dp);   // m: unit j0.., n: rows rs + 4*ni
         const float4 c = *reinterpret_cast<const float4*>(tv.b1 + j0);
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
-          const float4 h = *reinterpret_cast<const float4*>(h1 + (k0 + ni) * SPO_LDH + j0);
+          const float4 h = *reinterpret_cast<const float4*>(h1 + (rs + 4 * ni) * SPO_LDH + j0);
           float4 o;
           o.x = (acc[0][ni] + c.x) * (1.f - h.x * h.x);
           o.y = (acc[1][ni] + c.y) * (1.f - h.y * h.y);
           o.z = (acc[2][ni] + c.z) * (1.f - h.z * h.z);
           o.w = (acc[3][ni] + c.w) * (1.f - h.w * h.w);
-          *reinterpret_cast<float4*>(b3 + (k0 + ni) * SPO_LDH + j0) = o;
+          *reinterpret_cast<float4*>(b3 + (rs + 4 * ni) * SPO_LDH + j0) = o;
         }
       }
       __syncthreads();
       {  // dh2 = (dh1 W2^T + h1 V2^T + c2) * (1 - h2^2)     -> b4
         float acc[4][4];
         spo_zero(acc);
-        spo_tile_mma<true>(acc, w.w2t, SPO_LDH, b3, SPO_LDH, j0, k0, SPO_HID);
-        spo_tile_mma<true>(acc, tv.w2t, SPO_LDH, h1, SPO_LDH, j0, k0, SPO_HID);
+        spo_tile_mma<true>(acc, w.w2t, SPO_LDH, b3, SPO_LDH, j0, rs, SPO_HID);
+        spo_tile_mma<true>(acc, tv.w2t, SPO_LDH, h1, SPO_LDH, j0, rs, SPO_HID);
         const float4 c = *reinterpret_cast<const float4*>(tv.b2 + j0);
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
-          const float4 h = *reinterpret_cast<const float4*>(h2 + (k0 + ni) * SPO_LDH + j0);
+          const float4 h = *reinterpret_cast<const float4*>(h2 + (rs + 4 * ni) * SPO_LDH + j0);
           float4 o;
           o.x = (acc[0][ni] + c.x) * (1.f - h.x * h.x);
           o.y = (acc[1][ni] + c.y) * (1.f - h.y * h.y);
           o.z = (acc[2][ni] + c.z) * (1.f - h.z * h.z);
           o.w = (acc[3][ni] + c.w) * (1.f - h.w * h.w);
-          *reinterpret_cast<float4*>(b4 + (k0 + ni) * SPO_LDH + j0) = o;
+          *reinterpret_cast<float4*>(b4 + (rs + 4 * ni) * SPO_LDH + j0) = o;
         }
       }
       __syncthreads();
@@ -250,23 +251,22 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_trust_kernel(const TrArgs 
     {
       float acc[4][4];
       spo_zero(acc);
-      spo_tile_mma<true>(acc, w.w2, SPO_LDH, dz2, SPO_LDH, j0, k0, SPO_HID);   // m: input unit, n: row
+      spo_tile_mma<true>(acc, w.w2, SPO_LDH, dz2, SPO_LDH, j0, rs, SPO_HID);   // m: input unit, n: rows rs + 4*ni
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
-        const float4 h = *reinterpret_cast<const float4*>(h1 + (k0 + ni) * SPO_LDH + j0);
+        const float4 h = *reinterpret_cast<const float4*>(h1 + (rs + 4 * ni) * SPO_LDH + j0);
         float4 o4;
         o4.x = acc[0][ni] * (1.f - h.x * h.x);
         o4.y = acc[1][ni] * (1.f - h.y * h.y);
         o4.z = acc[2][ni] * (1.f - h.z * h.z);
         o4.w = acc[3][ni] * (1.f - h.w * h.w);
-        *reinterpret_cast<float4*>(dz1 + (k0 + ni) * SPO_LDH + j0) = o4;
+        *reinterpret_cast<float4*>(dz1 + (rs + 4 * ni) * SPO_LDH + j0) = o4;
       }
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NT1; ++i) {
-      const int id = tid + i * SPO_THREADS;
-      const int tj = (id & 15) * 4, tk = (id >> 4) * 4;
+      const int tj = (i == 0) ? j0 : (tid & 15) * 4, tk = (i == 0) ? k0 : 64 + (tid >> 4) * 4;
       if (tk < Dp) spo_tile_mma<false>(gW1[i], dz1, SPO_LDH, x, ldx, tj, tk, SPO_ROWS);
     }
     if (tid < SPO_HID) {
@@ -304,8 +304,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_trust_kernel(const TrArgs 
       for (int ni = 0; ni < 4; ++ni) atomicAdd(a.out + off.w2 + (j0 + mi) * SPO_HID + k0 + ni, gW2[mi][ni]);
 #pragma unroll
     for (int i = 0; i < NT1; ++i) {
-      const int id = tid + i * SPO_THREADS;
-      const int tj = (id & 15) * 4, tk = (id >> 4) * 4;
+      const int tj = (i == 0) ? j0 : (tid & 15) * 4, tk = (i == 0) ? k0 : 64 + (tid >> 4) * 4;
       if (tk < Dp) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)

@@ -21,6 +21,22 @@
 
 namespace cg = cooperative_groups;
 
+// Optional phase timers (build with -DSPO_PHASE_TIMERS): thread 0 of every CTA accumulates
+// clock64() deltas per phase of the step; read back with spo_debug_phase_cycles().
+#ifdef SPO_PHASE_TIMERS
+__device__ unsigned long long g_phase_cycles[4][16];
+#define PHASE_MARK(idx)                                                   \
+  do {                                                                    \
+    if (tid == 0) {                                                       \
+      const long long now__ = clock64();                                  \
+      atomicAdd(&g_phase_cycles[rank & 3][idx], static_cast<unsigned long long>(now__ - phase_t__)); \
+      phase_t__ = now__;                                                  \
+    }                                                                     \
+  } while (0)
+#else
+#define PHASE_MARK(idx) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int AUXW = 28;       // per-row side data: act[8] | logp adv tgt _ | old_mean[8] | old_std[8]
@@ -168,8 +184,9 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
     for (int i = tid; i < 2 * SPO_ROWS * ldx; i += SPO_THREADS) xbuf[0][i] = 0.f;       // xbuf[0],[1] contiguous
     for (int i = tid; i < 2 * SPO_ROWS * AUXW; i += SPO_THREADS) auxbuf[0][i] = 0.f;
   }
-  // thread tiles: W2[j0..+3][k0..+3]; W1 tile i covers j0 = 4*(id&15), k0 = 4*(id>>4), id = tid + 256*i
-  const int j0 = (tid & 15) * 4, k0 = (tid >> 4) * 4;
+  // thread tiles: W2[j0..+3][k0..+3] (warp-tile map of spo_common.cuh); W1 tile 0 likewise over k < 64,
+  // W1 tile 1 (obs_dim > 64) covers j = 4*(tid&15), k = 64 + 4*(tid>>4)
+  const int j0 = spo_m0(tid), k0 = spo_nb(tid);
   float mW2[4][4], vW2[4][4], mW1[NT1 == 1 ? 4 : 1][4], vW1[NT1 == 1 ? 4 : 1][4];
   if (active) {
 #pragma unroll
@@ -207,6 +224,21 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
   const float vcoef = (net == 1) ? a.hp.value_coef : 1.f;
   const float reg = is_actor ? 0.f : __fmul_rn(vcoef, __fmul_rn(a.hp.critic_l2, 2.f));
 
+  // copies of one observation tile owned by this thread: item i = tid + 256*it covers
+  // (row, chunk) = (i / per_row, i % per_row); decoded once (the per-step integer divisions
+  // were 4 % of the step in profiles/r01_update_ncu.md)
+  constexpr int PF_MAX = (NT1 == 1) ? 4 : 8;
+  int pf_rc[PF_MAX];
+  int pf_n = 0;
+  const int per_row = ((D & 3) == 0) ? (D >> 2) : D;
+  const bool pf_fast = SPO_ROWS * per_row <= PF_MAX * SPO_THREADS;
+#pragma unroll
+  for (int it = 0; it < PF_MAX; ++it) {
+    const int i = tid + it * SPO_THREADS;
+    pf_rc[it] = 0xFF;
+    if (pf_fast && i < SPO_ROWS * per_row) { pf_rc[it] = (i / per_row) | ((i % per_row) << 8); pf_n = it + 1; }
+  }
+
   // gather + async copy of one tile (64 rows) into buffer b
   auto prefetch = [&](int64_t q, int b) {
     if (!active || q >= n_tiles) return;
@@ -219,7 +251,18 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
     rows = rows < 0 ? 0 : (rows > SPO_ROWS ? SPO_ROWS : rows);
     float* x = xbuf[b];
     float* aux = auxbuf[b];
-    if ((D & 3) == 0) {
+    if (pf_fast) {
+      // (row, chunk) of this thread's copies were decoded once before the loop
+#pragma unroll
+      for (int it = 0; it < PF_MAX; ++it) {
+        const int r = pf_rc[it] & 0xFF, c = pf_rc[it] >> 8;
+        if (it < pf_n && r < rows) {
+          const int64_t g = a.perm[first + r];
+          if ((D & 3) == 0) cp_async16(x + r * ldx + 4 * c, a.data.obs + g * D + 4 * c);
+          else cp_async4(x + r * ldx + c, a.data.obs + g * D + c);
+        }
+      }
+    } else if ((D & 3) == 0) {
       const int c4 = D >> 2;
       for (int i = tid; i < rows * c4; i += SPO_THREADS) {
         const int r = i / c4, c = i - r * c4;
@@ -270,6 +313,9 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
   float step_loss = 0.f;        // thread 0: loss numerator of the current step (sum over its tiles)
   float step_aux0 = 0.f, step_aux1 = 0.f;  // FOCOPS: sum(ratio*adv), sum(mask)
   int64_t step_idx = 0;
+#ifdef SPO_PHASE_TIMERS
+  long long phase_t__ = clock64();
+#endif
 
   for (int64_t q = 0; q < n_tiles; ++q) {
     const int cur = static_cast<int>(q & 1);
@@ -290,13 +336,16 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
 
     const float* x = xbuf[cur];
     const float* aux = auxbuf[cur];
+    PHASE_MARK(0);   // wait for the gather + issue the next one
 
     if (active) {
       // ---------------- forward ----------------
       spo_hidden_fwd(x, ldx, Dp, w.w1t, w.b1, h1, tid);
       __syncthreads();
+      PHASE_MARK(1);
       spo_hidden_fwd(h1, SPO_LDH, SPO_HID, w.w2t, w.b2, h2, tid);
       __syncthreads();
+      PHASE_MARK(2);
       spo_out_fwd(h2, w.w3, w.b3, O, y, SPO_MAX_ACT, tid, SPO_THREADS);
       __syncthreads();
 
@@ -402,6 +451,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
         __syncthreads();
       }
 
+      PHASE_MARK(3);   // output layer + loss rows
       // ---------------- backward ----------------
       // (a) small grads of the output layer: dW3[o][k], db3[o], dlog_std[j]
       for (int i = tid; i < O * SPO_HID + O + sm.A_ls; i += SPO_THREADS) {
@@ -437,6 +487,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
         }
       }
       __syncthreads();
+      PHASE_MARK(4);   // small grads + dz2
       // (c) dW2[j][k] += sum_r dz2[r][j] * h1[r][k];  db2[j] += sum_r dz2[r][j]
       spo_tile_mma<false>(gW2, dz2, SPO_LDH, h1, SPO_LDH, j0, k0, SPO_ROWS);
       if (tid < SPO_HID) {
@@ -449,25 +500,26 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       {
         float acc[4][4];
         spo_zero(acc);
-        const int m0 = (tid & 15) * 4, n0 = (tid >> 4) * 4;   // m: input unit k, n: row r
-        spo_tile_mma<true>(acc, w.w2, SPO_LDH, dz2, SPO_LDH, m0, n0, SPO_HID);
+        const int m0 = spo_m0(tid), ns = spo_ns(tid);   // m: input unit k, n: row r (ns, ns+4, ...)
+        spo_tile_mma<true>(acc, w.w2, SPO_LDH, dz2, SPO_LDH, m0, ns, SPO_HID);
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) {
-          const float4 h = *reinterpret_cast<const float4*>(h1 + (n0 + ni) * SPO_LDH + m0);
+          const int r = ns + 4 * ni;
+          const float4 h = *reinterpret_cast<const float4*>(h1 + r * SPO_LDH + m0);
           float4 o4;
           o4.x = acc[0][ni] * (1.f - h.x * h.x);
           o4.y = acc[1][ni] * (1.f - h.y * h.y);
           o4.z = acc[2][ni] * (1.f - h.z * h.z);
           o4.w = acc[3][ni] * (1.f - h.w * h.w);
-          *reinterpret_cast<float4*>(dz1 + (n0 + ni) * SPO_LDH + m0) = o4;
+          *reinterpret_cast<float4*>(dz1 + r * SPO_LDH + m0) = o4;
         }
       }
       __syncthreads();
+      PHASE_MARK(5);   // dW2 + dh1
       // (e) dW1[j][k] += sum_r dz1[r][j] * x[r][k];  db1[j] += sum_r dz1[r][j]
 #pragma unroll
       for (int i = 0; i < NT1; ++i) {
-        const int id = tid + i * SPO_THREADS;
-        const int tj = (id & 15) * 4, tk = (id >> 4) * 4;
+        const int tj = (i == 0) ? j0 : (tid & 15) * 4, tk = (i == 0) ? k0 : 64 + (tid >> 4) * 4;
         if (tk < Dp) spo_tile_mma<false>(gW1[i], dz1, SPO_LDH, x, ldx, tj, tk, SPO_ROWS);
       }
       if (tid < SPO_HID) {
@@ -478,6 +530,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       }
     }  // active
 
+    PHASE_MARK(6);   // dW1
     if (!last_tile) continue;   // next tile of the same step accumulates into the same gradients
 
     // ---------------- cross-GPU gradient sum (data-parallel ranks), in rank order ----------------
@@ -561,6 +614,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       }
     }
 
+    PHASE_MARK(7);   // cross-GPU gradient exchange
     // ---------------- joint gradient norm (cluster-wide), clip, Adam ----------------
     float ss = 0.f, th2 = 0.f;
     if (active) {
@@ -577,8 +631,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
         }
 #pragma unroll
       for (int i = 0; i < NT1; ++i) {
-        const int id = tid + i * SPO_THREADS;
-        const int tj = (id & 15) * 4, tk = (id >> 4) * 4;
+        const int tj = (i == 0) ? j0 : (tid & 15) * 4, tk = (i == 0) ? k0 : 64 + (tid >> 4) * 4;
         if (tk < Dp) {
 #pragma unroll
           for (int mi = 0; mi < 4; ++mi)
@@ -627,7 +680,9 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       }
       step_loss = 0.f; step_aux0 = 0.f; step_aux1 = 0.f;
     }
+    PHASE_MARK(8);   // regulariser + sum of squares + block reduction
     cluster.sync();
+    PHASE_MARK(9);   // cluster barrier (includes waiting for the slowest net)
     float total = 0.f;
     {
       const unsigned nblk = cluster.num_blocks();
@@ -659,8 +714,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       // W1 (transposed image only)
 #pragma unroll
       for (int i = 0; i < NT1; ++i) {
-        const int id = tid + i * SPO_THREADS;
-        const int tj = (id & 15) * 4, tk = (id >> 4) * 4;
+        const int tj = (i == 0) ? j0 : (tid & 15) * 4, tk = (i == 0) ? k0 : 64 + (tid >> 4) * 4;
         if (tk < Dp) {
 #pragma unroll
           for (int mi = 0; mi < 4; ++mi)
@@ -692,6 +746,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
         gsmall[i] = 0.f;
       }
     }
+    PHASE_MARK(10);  // Adam
     ++step_idx;
     // the __syncthreads at the top of the next iteration orders these weight writes
     // before the next forward
@@ -785,6 +840,17 @@ int launch_update(const UpdArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace
+
+#ifdef SPO_PHASE_TIMERS
+extern "C" int spo_debug_phase_cycles(unsigned long long* out64, int reset) {
+  SPO_CUDA_TRY(cudaMemcpyFromSymbol(out64, g_phase_cycles, sizeof(unsigned long long) * 64));
+  if (reset) {
+    unsigned long long z[64] = {0};
+    SPO_CUDA_TRY(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)));
+  }
+  return SPO_OK;
+}
+#endif
 
 extern "C" int spo_comm_slot_floats(const spo_dims* d, int* slot_floats) {
   int rc = spo_check_dims(d);

@@ -340,9 +340,10 @@ def test_full_batch_kl_vs_reference(golden):
     ctrl = make_ctrl(dev)
     obs = c["data"]["obs"].to(dev)
     old_ls = c["init"]["actor"]["log_std"].to(dev)
+    old_mean_d = old_mean.contiguous().to(dev)      # keep device operands alive across the asynchronous launch
     for reduce, scale in ((0, 1.0), (1, 1.0 / c["A"])):
         ctrl.zero_()
-        L.check(L.lib().spo_actor_kl(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(obs), L.ptr(old_mean.contiguous().to(dev)),
+        L.check(L.lib().spo_actor_kl(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(obs), L.ptr(old_mean_d),
                                      L.ptr(old_ls), obs.shape[0], reduce, 0.02, L.ptr(ctrl), L.stream()), "spo_actor_kl")
         r = read_ctrl(ctrl)
         want = float(c["kls"][-1]) * scale
@@ -519,7 +520,8 @@ def test_tensor_core_forward_and_kl_large_batch(D, A, S):
     old_mean = (want + 0.05 * torch.randn(S, A)).contiguous()
     old_ls = torch.linspace(-0.3, 0.1, A)
     ctrl = make_ctrl(dev)
-    L.check(L.lib().spo_actor_kl(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(obs_d), L.ptr(old_mean.to(dev)), L.ptr(old_ls.to(dev)), S, 0,
+    old_mean_d, old_ls_d = old_mean.to(dev), old_ls.to(dev)      # keep alive across the asynchronous launch
+    L.check(L.lib().spo_actor_kl(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(obs_d), L.ptr(old_mean_d), L.ptr(old_ls_d), S, 0,
                                  1e9, L.ptr(ctrl), L.stream()), "spo_actor_kl")
     r = read_ctrl(ctrl)
     with torch.no_grad():

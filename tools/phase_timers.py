@@ -1,0 +1,40 @@
+"""Per-phase cycle breakdown of one spo_update_kernel pass (needs tools/libspo_timers.so,
+a build of libspo with -DSPO_PHASE_TIMERS for spo_update.cu)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "safe-policy-optimization_b200"))
+from safepo import _lib as L  # noqa: E402
+
+L.LIB_PATH = os.path.join(ROOT, "tools", "libspo_timers.so")
+from safepo.single_agent._engine import PolicyGradientUpdate  # noqa: E402
+from safepo.common.model import ActorVCritic  # noqa: E402
+
+dev = torch.device("cuda:0")
+S, D, A = 1024000, 60, 2
+steps = int(os.environ.get("STEPS", 4000))
+torch.manual_seed(0)
+pol = ActorVCritic(D, A).to(dev)
+data = {"obs": torch.randn(S, D, device=dev), "act": torch.randn(S, A, device=dev), "log_prob": torch.full((S,), -2.5, device=dev),
+        "target_value_r": torch.randn(S, device=dev), "target_value_c": torch.randn(S, device=dev), "adv": torch.randn(S, device=dev)}
+cfg = dict(hidden_sizes=[64, 64], gamma=0.99, target_kl=1e9, batch_size=64, learning_iters=1, max_grad_norm=40.0)
+upd = PolicyGradientUpdate(pol, cfg, L.LOSS_PPO_CLIP, epochs=100, host_rng=False, device=dev)
+perm = torch.randperm(S, device=dev)[: steps * 64]
+upd.run(data, perms=[perm])
+torch.cuda.synchronize()
+lib = L.lib()
+buf = (C.c_ulonglong * 64)()
+lib.spo_debug_phase_cycles.argtypes = [C.c_void_p, C.c_int]
+lib.spo_debug_phase_cycles(buf, 1)
+upd.run(data, perms=[perm])
+torch.cuda.synchronize()
+lib.spo_debug_phase_cycles(buf, 1)
+names = ["gather wait/issue", "fwd L1", "fwd L2", "out+loss", "small grads+dz2", "dW2+dh1", "dW1", "dp exchange", "reg+sumsq", "cluster sync",
+         "adam"]
+for rank, net in enumerate(("actor", "reward critic", "cost critic")):
+    row = [buf[rank * 16 + i] / steps for i in range(11)]
+    print(f"{net:14s} total {sum(row):8.0f} cyc/step | " + " ".join(f"{n}={v:.0f}" for n, v in zip(names, row)))
