@@ -5,6 +5,12 @@
 // forward of the three nets, losses, backward, critic L2 term, ONE joint grad-norm clip
 // over all three nets (ppo_lag.py:325), three Adam steps.
 //
+// GEMMs: every 64x64xK product of the step runs on the tensor pipe as warp-level
+// mma.sync.m16n8k8 TF32 with the 3xTF32 split in registers (csrc/spo_mma.cuh) -- the FFMA
+// register-tile version of r01 was bound by shared-memory bandwidth at 4.1-4.8 k cycles per
+// GEMM (profiles/r01_update_phase_cycles.md).  Accumulator fragments of the dW products
+// are the gradients; their owner threads also hold the Adam moments in registers.
+//
 // Mapping: a thread-block cluster of 4 CTAs (the 4th only joins the barriers: a cluster of
 // 4 synchronises faster than one of 3 on B200), one net per CTA -- actor / reward critic / cost
 // critic.  Each CTA keeps its net's weights (both orientations), the Adam moments and
@@ -17,7 +23,9 @@
 // one), so this kernel is latency-bound by construction: what is optimised is
 // microseconds per step, not bandwidth.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include "spo_common.cuh"
+#include "spo_mma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -122,6 +130,18 @@ struct SmallMap {
   }
 };
 
+// leading dimension of the observation tile / W1 image: K padded to a multiple of 8, +4 floats
+// (== 4 mod 8: rows g = 0..7 of an mma fragment fall in 8 different bank groups)
+__host__ __device__ inline int upd_ldx(int D) { return ((D + 7) & ~7) + 4; }
+
+// element e16 = (mt*2 + nt)*4 + e of the 32 x 16 warp patch of a 64-wide output owned by thread tid
+__device__ __forceinline__ void frag_rc(int tid, int e16, int col_base, int& row, int& col) {
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int mt = e16 >> 3, nt = (e16 >> 2) & 1, e = e16 & 3;
+  row = (warp & 1) * 32 + mt * 16 + g + ((e >> 1) << 3);
+  col = col_base + (warp >> 1) * 16 + nt * 8 + 2 * t + (e & 1);
+}
+
 template <int NT1>
 __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -133,7 +153,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
   spo_update_ctrl* ctrl = a.ctrl;
   if (*reinterpret_cast<volatile int*>(&ctrl->stop)) return;  // whole cluster takes this branch together
 
-  const int D = a.D, A = a.A, Dp = spo_pad4(D), ldx = spo_ld(D);
+  const int D = a.D, A = a.A, K8 = (D + 7) & ~7, ldx = upd_ldx(D);
   const bool idle = rank >= 3;
   const int net = idle ? 2 : static_cast<int>(rank);
   const bool is_actor = (net == 0) && !idle;
@@ -142,10 +162,20 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
   const int O = off.out;
   const SmallMap sm{O, is_actor ? A : 0};
   const int SP = sm.count();
+  const int mb = (wid & 1) * 32, nb = (wid >> 1) * 16;   // warp patch of every 64x64 product
+  const int g8 = lane >> 2, t4 = lane & 3;
 
-  // ---- shared memory carve-up ----
-  SpoNetSmem w;
-  float* p = spo_carve_net(smem, D, O, true, w);
+  // ---- shared memory carve-up (weights in nn.Linear orientation [out][in]) ----
+  float* p = smem;
+  float* w1 = p;  p += SPO_HID * ldx;
+  float* b1 = p;  p += SPO_HID;
+  float* w2 = p;  p += SPO_HID * SPO_LDH;
+  float* b2 = p;  p += SPO_HID;
+  // every CTA of the cluster carves the SAME layout (actor-sized output layer): the peers read
+  // xchg through distributed shared memory at their own offset of it
+  const int Oc = A > 1 ? A : 1;
+  float* w3 = p;  p += spo_pad4(Oc * SPO_HID);
+  float* b3 = p;  p += spo_pad4(Oc);
   float* log_std = p; p += 8;
   const int spn = spo_pad4(2 * SPO_HID + A * SPO_HID + 2 * A);   // small-parameter slots (actor-sized for all nets)
   float* msmall = p;  p += spn;
@@ -165,8 +195,8 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
   float* dls = p; p += SPO_ROWS * SPO_MAX_ACT;   // per-row d loss / d log_std
   float* red = p; p += 64;                       // block-reduction scratch
   float* xchg = p; p += 4;                       // [parity] CTA grad sumsq, read by peers through DSMEM
-  float* m1s = nullptr; float* v1s = nullptr;    // W1 moments in smem when they do not fit registers
-  if (NT1 > 1) { m1s = p; p += Dp * SPO_LDH; v1s = p; p += Dp * SPO_LDH; }
+  float* mv1b = nullptr;                         // moments of the second W1 column block (obs_dim > 64): thread-private slots
+  if (NT1 > 1) { mv1b = p; p += 2 * 16 * SPO_THREADS; }
   float* dz1 = h2;
 
   const int tps = (a.batch + SPO_ROWS - 1) / SPO_ROWS;                    // tiles per step
@@ -175,7 +205,17 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
 
   // ---- one-time loads ----
   if (!idle) {
-    spo_load_net(a.params, off, D, w, tid, SPO_THREADS);
+    for (int i = tid; i < SPO_HID * ldx; i += SPO_THREADS) {
+      const int j = i / ldx, k = i - j * ldx;
+      w1[i] = (k < D) ? __ldg(a.params + off.w1 + j * D + k) : 0.f;
+    }
+    for (int i = tid; i < SPO_HID * SPO_LDH; i += SPO_THREADS) {
+      const int j = i / SPO_LDH, k = i - j * SPO_LDH;
+      w2[i] = (k < SPO_HID) ? __ldg(a.params + off.w2 + j * SPO_HID + k) : 0.f;
+    }
+    for (int i = tid; i < SPO_HID; i += SPO_THREADS) { b1[i] = __ldg(a.params + off.b1 + i); b2[i] = __ldg(a.params + off.b2 + i); }
+    for (int i = tid; i < O * SPO_HID; i += SPO_THREADS) w3[i] = __ldg(a.params + off.w3 + i);
+    for (int i = tid; i < O; i += SPO_THREADS) b3[i] = __ldg(a.params + off.b3 + i);
     for (int i = tid; i < SP; i += SPO_THREADS) {
       msmall[i] = a.adam_m[sm.goff(off, i)];
       vsmall[i] = a.adam_v[sm.goff(off, i)];
@@ -184,35 +224,22 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
     for (int i = tid; i < 2 * SPO_ROWS * ldx; i += SPO_THREADS) xbuf[0][i] = 0.f;       // xbuf[0],[1] contiguous
     for (int i = tid; i < 2 * SPO_ROWS * AUXW; i += SPO_THREADS) auxbuf[0][i] = 0.f;
   }
-  // thread tiles: W2[j0..+3][k0..+3] (warp-tile map of spo_common.cuh); W1 tile 0 likewise over k < 64,
-  // W1 tile 1 (obs_dim > 64) covers j = 4*(tid&15), k = 64 + 4*(tid>>4)
-  const int j0 = spo_m0(tid), k0 = spo_nb(tid);
-  float mW2[4][4], vW2[4][4], mW1[NT1 == 1 ? 4 : 1][4], vW1[NT1 == 1 ? 4 : 1][4];
+  // Adam moments of this thread's fragment elements: W2 and the first 64 input columns of W1 in registers
+  float mW2[16], vW2[16], mW1[16], vW1[16];
   if (active) {
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        const int g = off.w2 + (j0 + mi) * SPO_HID + k0 + ni;
-        mW2[mi][ni] = a.adam_m[g];
-        vW2[mi][ni] = a.adam_v[g];
-      }
-    if (NT1 == 1) {
-#pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-          const bool ok = (k0 + ni) < D;
-          const int g = off.w1 + (j0 + mi) * D + k0 + ni;
-          mW1[mi][ni] = ok ? a.adam_m[g] : 0.f;
-          vW1[mi][ni] = ok ? a.adam_v[g] : 0.f;
-        }
-    } else {
-      for (int i = tid; i < Dp * SPO_HID; i += SPO_THREADS) {
-        const int k = i >> 6, j = i & 63;
-        const bool ok = k < D;
-        m1s[k * SPO_LDH + j] = ok ? a.adam_m[off.w1 + j * D + k] : 0.f;
-        v1s[k * SPO_LDH + j] = ok ? a.adam_v[off.w1 + j * D + k] : 0.f;
+    for (int e = 0; e < 16; ++e) {
+      int j, k;
+      frag_rc(tid, e, 0, j, k);
+      mW2[e] = a.adam_m[off.w2 + j * SPO_HID + k];
+      vW2[e] = a.adam_v[off.w2 + j * SPO_HID + k];
+      const bool ok = k < D;
+      mW1[e] = ok ? a.adam_m[off.w1 + j * D + k] : 0.f;
+      vW1[e] = ok ? a.adam_v[off.w1 + j * D + k] : 0.f;
+      if (NT1 > 1) {
+        const bool ok2 = (k + 64) < D;
+        mv1b[e * SPO_THREADS + tid] = ok2 ? a.adam_m[off.w1 + j * D + k + 64] : 0.f;
+        mv1b[(16 + e) * SPO_THREADS + tid] = ok2 ? a.adam_v[off.w1 + j * D + k + 64] : 0.f;
       }
     }
   }
@@ -225,8 +252,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
   const float reg = is_actor ? 0.f : __fmul_rn(vcoef, __fmul_rn(a.hp.critic_l2, 2.f));
 
   // copies of one observation tile owned by this thread: item i = tid + 256*it covers
-  // (row, chunk) = (i / per_row, i % per_row); decoded once (the per-step integer divisions
-  // were 4 % of the step in profiles/r01_update_ncu.md)
+  // (row, chunk) = (i / per_row, i % per_row); decoded once
   constexpr int PF_MAX = (NT1 == 1) ? 4 : 8;
   int pf_rc[PF_MAX];
   int pf_n = 0;
@@ -252,7 +278,6 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
     float* x = xbuf[b];
     float* aux = auxbuf[b];
     if (pf_fast) {
-      // (row, chunk) of this thread's copies were decoded once before the loop
 #pragma unroll
       for (int it = 0; it < PF_MAX; ++it) {
         const int r = pf_rc[it] & 0xFF, c = pf_rc[it] >> 8;
@@ -299,15 +324,34 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
     }
   };
 
+  // hidden layer: out[r][j] = tanh(b[j] + sum_k in[r][k] * W[j][k]) on the tensor pipe
+  auto hidden = [&](const float* in, int ldin, int K, const float* W, int ldw, const float* bias, float* out) {
+    float acc[2][2][4];
+    spo_mma_zero(acc);
+    spo_warp_mma_3xtf32(acc, in, ldin, 1, W, 1, ldw, mb, nb, K);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int r = mb + mt * 16 + g8, j = nb + nt * 8 + 2 * t4;
+        const float2 bb = *reinterpret_cast<const float2*>(bias + j);
+        *reinterpret_cast<float2*>(out + r * SPO_LDH + j) = make_float2(spo_tanh(acc[mt][nt][0] + bb.x), spo_tanh(acc[mt][nt][1] + bb.y));
+        *reinterpret_cast<float2*>(out + (r + 8) * SPO_LDH + j) = make_float2(spo_tanh(acc[mt][nt][2] + bb.x), spo_tanh(acc[mt][nt][3] + bb.y));
+      }
+  };
+
   __syncthreads();
   prefetch(0, 0);
   cp_async_commit();
 
-  // gradient accumulators (persist across the tiles of one step)
-  float gW2[4][4], gW1[NT1][4][4];
-  spo_zero(gW2);
+  // gradient accumulators = accumulator fragments of the dW products (persist across the tiles of a step)
+  float gW2[16], gW1[NT1][16];
 #pragma unroll
-  for (int i = 0; i < NT1; ++i) spo_zero(gW1[i]);
+  for (int e = 0; e < 16; ++e) {
+    gW2[e] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NT1; ++i) gW1[i][e] = 0.f;
+  }
   for (int i = tid; i < SP; i += SPO_THREADS) gsmall[i] = 0.f;
   double acc_loss = 0.0;        // thread 0: sum over steps of this net's logged loss
   float step_loss = 0.f;        // thread 0: loss numerator of the current step (sum over its tiles)
@@ -340,13 +384,13 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
 
     if (active) {
       // ---------------- forward ----------------
-      spo_hidden_fwd(x, ldx, Dp, w.w1t, w.b1, h1, tid);
+      hidden(x, ldx, K8, w1, ldx, b1, h1);
       __syncthreads();
       PHASE_MARK(1);
-      spo_hidden_fwd(h1, SPO_LDH, SPO_HID, w.w2t, w.b2, h2, tid);
+      hidden(h1, SPO_LDH, SPO_HID, w2, SPO_LDH, b2, h2);
       __syncthreads();
       PHASE_MARK(2);
-      spo_out_fwd(h2, w.w3, w.b3, O, y, SPO_MAX_ACT, tid, SPO_THREADS);
+      spo_out_fwd(h2, w3, b3, O, y, SPO_MAX_ACT, tid, SPO_THREADS);
       __syncthreads();
 
       // ---------------- loss and d loss / d output, one thread per row ----------------
@@ -478,7 +522,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
           float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int o = 0; o < O; ++o) {
             const float d = dy[r * SPO_MAX_ACT + o];
-            const float4 wv = *reinterpret_cast<const float4*>(w.w3 + o * SPO_HID + kk);
+            const float4 wv = *reinterpret_cast<const float4*>(w3 + o * SPO_HID + kk);
             s.x = fmaf(d, wv.x, s.x); s.y = fmaf(d, wv.y, s.y); s.z = fmaf(d, wv.z, s.z); s.w = fmaf(d, wv.w, s.w);
           }
           const float4 h = *reinterpret_cast<const float4*>(h2 + r * SPO_LDH + kk);
@@ -489,7 +533,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       __syncthreads();
       PHASE_MARK(4);   // small grads + dz2
       // (c) dW2[j][k] += sum_r dz2[r][j] * h1[r][k];  db2[j] += sum_r dz2[r][j]
-      spo_tile_mma<false>(gW2, dz2, SPO_LDH, h1, SPO_LDH, j0, k0, SPO_ROWS);
+      spo_warp_mma_3xtf32(reinterpret_cast<float (&)[2][2][4]>(gW2), dz2, 1, SPO_LDH, h1, SPO_LDH, 1, mb, nb, SPO_ROWS);
       if (tid < SPO_HID) {
         float s = 0.f;
 #pragma unroll 8
@@ -498,30 +542,29 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       }
       // (d) dz1[r][k] = (sum_j dz2[r][j] * W2[j][k]) * (1 - h1[r][k]^2)   -> overwrites h2
       {
-        float acc[4][4];
-        spo_zero(acc);
-        const int m0 = spo_m0(tid), ns = spo_ns(tid);   // m: input unit k, n: row r (ns, ns+4, ...)
-        spo_tile_mma<true>(acc, w.w2, SPO_LDH, dz2, SPO_LDH, m0, ns, SPO_HID);
+        float acc[2][2][4];
+        spo_mma_zero(acc);
+        spo_warp_mma_3xtf32(acc, dz2, SPO_LDH, 1, w2, SPO_LDH, 1, mb, nb, SPO_HID);
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-          const int r = ns + 4 * ni;
-          const float4 h = *reinterpret_cast<const float4*>(h1 + r * SPO_LDH + m0);
-          float4 o4;
-          o4.x = acc[0][ni] * (1.f - h.x * h.x);
-          o4.y = acc[1][ni] * (1.f - h.y * h.y);
-          o4.z = acc[2][ni] * (1.f - h.z * h.z);
-          o4.w = acc[3][ni] * (1.f - h.w * h.w);
-          *reinterpret_cast<float4*>(dz1 + r * SPO_LDH + m0) = o4;
-        }
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            const int r = mb + mt * 16 + g8, k = nb + nt * 8 + 2 * t4;
+            const float2 ha = *reinterpret_cast<const float2*>(h1 + r * SPO_LDH + k);
+            const float2 hb = *reinterpret_cast<const float2*>(h1 + (r + 8) * SPO_LDH + k);
+            *reinterpret_cast<float2*>(dz1 + r * SPO_LDH + k) =
+                make_float2(acc[mt][nt][0] * (1.f - ha.x * ha.x), acc[mt][nt][1] * (1.f - ha.y * ha.y));
+            *reinterpret_cast<float2*>(dz1 + (r + 8) * SPO_LDH + k) =
+                make_float2(acc[mt][nt][2] * (1.f - hb.x * hb.x), acc[mt][nt][3] * (1.f - hb.y * hb.y));
+          }
       }
       __syncthreads();
       PHASE_MARK(5);   // dW2 + dh1
       // (e) dW1[j][k] += sum_r dz1[r][j] * x[r][k];  db1[j] += sum_r dz1[r][j]
 #pragma unroll
-      for (int i = 0; i < NT1; ++i) {
-        const int tj = (i == 0) ? j0 : (tid & 15) * 4, tk = (i == 0) ? k0 : 64 + (tid >> 4) * 4;
-        if (tk < Dp) spo_tile_mma<false>(gW1[i], dz1, SPO_LDH, x, ldx, tj, tk, SPO_ROWS);
-      }
+      for (int i = 0; i < NT1; ++i)
+        if (i * 64 + nb < K8)
+          spo_warp_mma_3xtf32(reinterpret_cast<float (&)[2][2][4]>(gW1[i]), dz1, 1, SPO_LDH, x, ldx, 1, mb, i * 64 + nb, SPO_ROWS);
       if (tid < SPO_HID) {
         float s = 0.f;
 #pragma unroll 8
@@ -542,12 +585,12 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       const size_t slot_off = (static_cast<size_t>(seq & 1u) * 3 + net) * slot;
       float4* mine = reinterpret_cast<float4*>(a.comm.grad_bufs[me] + slot_off);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) mine[i * SPO_THREADS + tid] = make_float4(gW2[i][0], gW2[i][1], gW2[i][2], gW2[i][3]);
+      for (int i = 0; i < 4; ++i) mine[i * SPO_THREADS + tid] = make_float4(gW2[4 * i], gW2[4 * i + 1], gW2[4 * i + 2], gW2[4 * i + 3]);
 #pragma unroll
       for (int t = 0; t < NT1; ++t)
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          mine[(4 + t * 4 + i) * SPO_THREADS + tid] = make_float4(gW1[t][i][0], gW1[t][i][1], gW1[t][i][2], gW1[t][i][3]);
+          mine[(4 + t * 4 + i) * SPO_THREADS + tid] = make_float4(gW1[t][4 * i], gW1[t][4 * i + 1], gW1[t][4 * i + 2], gW1[t][4 * i + 3]);
       float* mine_small = reinterpret_cast<float*>(mine + (4 + 4 * NT1) * SPO_THREADS);
       for (int i = tid; i < SP; i += SPO_THREADS) mine_small[i] = gsmall[i];
       __threadfence_system();
@@ -562,20 +605,21 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
         }
       }
       __syncthreads();
-      float sW2[4][4], sW1[NT1][4][4];
-      spo_zero(sW2);
+      float sW2[16], sW1[NT1][16];
 #pragma unroll
-      for (int t = 0; t < NT1; ++t) spo_zero(sW1[t]);
+      for (int e = 0; e < 16; ++e) {
+        sW2[e] = 0.f;
+#pragma unroll
+        for (int t = 0; t < NT1; ++t) sW1[t][e] = 0.f;
+      }
       for (int r = 0; r < world; ++r) {
         if (r == me) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int e = 0; e < 16; ++e) {
+            sW2[e] += gW2[e];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              sW2[i][j] += gW2[i][j];
-#pragma unroll
-              for (int t = 0; t < NT1; ++t) sW1[t][i][j] += gW1[t][i][j];
-            }
+            for (int t = 0; t < NT1; ++t) sW1[t][e] += gW1[t][e];
+          }
         } else {
           const float4* peer = reinterpret_cast<const float4*>(a.comm.grad_bufs[r] + slot_off);
           float4 v2[4], v1[NT1][4];
@@ -587,23 +631,21 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
             for (int i = 0; i < 4; ++i) v1[t][i] = ld_relaxed_sys_f4(peer + (4 + t * 4 + i) * SPO_THREADS + tid);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            sW2[i][0] += v2[i].x; sW2[i][1] += v2[i].y; sW2[i][2] += v2[i].z; sW2[i][3] += v2[i].w;
+            sW2[4 * i] += v2[i].x; sW2[4 * i + 1] += v2[i].y; sW2[4 * i + 2] += v2[i].z; sW2[4 * i + 3] += v2[i].w;
 #pragma unroll
             for (int t = 0; t < NT1; ++t) {
-              sW1[t][i][0] += v1[t][i].x; sW1[t][i][1] += v1[t][i].y; sW1[t][i][2] += v1[t][i].z; sW1[t][i][3] += v1[t][i].w;
+              sW1[t][4 * i] += v1[t][i].x; sW1[t][4 * i + 1] += v1[t][i].y; sW1[t][4 * i + 2] += v1[t][i].z; sW1[t][4 * i + 3] += v1[t][i].w;
             }
           }
         }
       }
       const float inv_w = __fdiv_rn(1.f, static_cast<float>(world));
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int e = 0; e < 16; ++e) {
+        gW2[e] = __fmul_rn(sW2[e], inv_w);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          gW2[i][j] = __fmul_rn(sW2[i][j], inv_w);
-#pragma unroll
-          for (int t = 0; t < NT1; ++t) gW1[t][i][j] = __fmul_rn(sW1[t][i][j], inv_w);
-        }
+        for (int t = 0; t < NT1; ++t) gW1[t][e] = __fmul_rn(sW1[t][e], inv_w);
+      }
       for (int i = tid; i < SP; i += SPO_THREADS) {
         float sm_ = 0.f;
         for (int r = 0; r < world; ++r) {
@@ -620,37 +662,34 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
     if (active) {
       __syncthreads();  // gsmall complete
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+      for (int e = 0; e < 16; ++e) {
+        int j, k;
+        frag_rc(tid, e, 0, j, k);
+        const float th = w2[j * SPO_LDH + k];
+        const float g = fmaf(reg, th, gW2[e]);
+        gW2[e] = g;
+        ss = fmaf(g, g, ss);
+        th2 = fmaf(th, th, th2);
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-          const float th = w.w2[(j0 + mi) * SPO_LDH + k0 + ni];
-          const float g = fmaf(reg, th, gW2[mi][ni]);
-          gW2[mi][ni] = g;
-          ss = fmaf(g, g, ss);
-          th2 = fmaf(th, th, th2);
-        }
-#pragma unroll
-      for (int i = 0; i < NT1; ++i) {
-        const int tj = (i == 0) ? j0 : (tid & 15) * 4, tk = (i == 0) ? k0 : 64 + (tid >> 4) * 4;
-        if (tk < Dp) {
-#pragma unroll
-          for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-              const float th = w.w1t[(tk + ni) * SPO_LDH + tj + mi];
-              const float g = fmaf(reg, th, gW1[i][mi][ni]);
-              gW1[i][mi][ni] = g;
-              ss = fmaf(g, g, ss);
-              th2 = fmaf(th, th, th2);
-            }
+        for (int i = 0; i < NT1; ++i) {
+          const int kk = k + 64 * i;
+          if (kk < D) {
+            const float t1 = w1[j * ldx + kk];
+            const float g1 = fmaf(reg, t1, gW1[i][e]);
+            gW1[i][e] = g1;
+            ss = fmaf(g1, g1, ss);
+            th2 = fmaf(t1, t1, th2);
+          } else {
+            gW1[i][e] = 0.f;
+          }
         }
       }
       for (int i = tid; i < SP; i += SPO_THREADS) {
         float th;
-        if (i < SPO_HID) th = w.b1[i];
-        else if (i < 2 * SPO_HID) th = w.b2[i - SPO_HID];
-        else if (i < 2 * SPO_HID + O * SPO_HID) th = w.w3[i - 2 * SPO_HID];
-        else if (i < 2 * SPO_HID + O * SPO_HID + O) th = w.b3[i - 2 * SPO_HID - O * SPO_HID];
+        if (i < SPO_HID) th = b1[i];
+        else if (i < 2 * SPO_HID) th = b2[i - SPO_HID];
+        else if (i < 2 * SPO_HID + O * SPO_HID) th = w3[i - 2 * SPO_HID];
+        else if (i < 2 * SPO_HID + O * SPO_HID + O) th = b3[i - 2 * SPO_HID - O * SPO_HID];
         else th = log_std[i - 2 * SPO_HID - O * SPO_HID - O];
         const float g = fmaf(reg, th, gsmall[i]);
         gsmall[i] = g;
@@ -700,45 +739,35 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       k.bc2s = static_cast<float>(sqrt(1.0 - b2pow));
       k.eps = a.hp.adam_eps;
       k.ss = static_cast<float>(-(static_cast<double>(lr) / (1.0 - b1pow)));
-      // W2 (natural + transposed images)
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-          const int ia = (j0 + mi) * SPO_LDH + k0 + ni;
-          const float nw = adam_update(w.w2[ia], __fmul_rn(gW2[mi][ni], clip), mW2[mi][ni], vW2[mi][ni], k);
-          w.w2[ia] = nw;
-          w.w2t[(k0 + ni) * SPO_LDH + j0 + mi] = nw;
-          gW2[mi][ni] = 0.f;
+      for (int e = 0; e < 16; ++e) {
+        int j, kc;
+        frag_rc(tid, e, 0, j, kc);
+        float* pw = w2 + j * SPO_LDH + kc;
+        *pw = adam_update(*pw, __fmul_rn(gW2[e], clip), mW2[e], vW2[e], k);
+        gW2[e] = 0.f;
+        if (kc < D) {
+          float* p1 = w1 + j * ldx + kc;
+          *p1 = adam_update(*p1, __fmul_rn(gW1[0][e], clip), mW1[e], vW1[e], k);
         }
-      // W1 (transposed image only)
-#pragma unroll
-      for (int i = 0; i < NT1; ++i) {
-        const int tj = (i == 0) ? j0 : (tid & 15) * 4, tk = (i == 0) ? k0 : 64 + (tid >> 4) * 4;
-        if (tk < Dp) {
-#pragma unroll
-          for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-              const int ia = (tk + ni) * SPO_LDH + tj + mi;
-              const float g = __fmul_rn(gW1[i][mi][ni], clip);
-              if (NT1 == 1) {
-                w.w1t[ia] = adam_update(w.w1t[ia], g, mW1[mi][ni], vW1[mi][ni], k);
-              } else {
-                float m = m1s[ia], v = v1s[ia];
-                w.w1t[ia] = adam_update(w.w1t[ia], g, m, v, k);
-                m1s[ia] = m; v1s[ia] = v;
-              }
-              gW1[i][mi][ni] = 0.f;
-            }
+        gW1[0][e] = 0.f;
+        if (NT1 > 1) {
+          if (kc + 64 < D) {
+            float* p1 = w1 + j * ldx + kc + 64;
+            float m = mv1b[e * SPO_THREADS + tid], v = mv1b[(16 + e) * SPO_THREADS + tid];
+            *p1 = adam_update(*p1, __fmul_rn(gW1[NT1 - 1][e], clip), m, v, k);
+            mv1b[e * SPO_THREADS + tid] = m;
+            mv1b[(16 + e) * SPO_THREADS + tid] = v;
+          }
+          gW1[NT1 - 1][e] = 0.f;
         }
       }
       for (int i = tid; i < SP; i += SPO_THREADS) {
         float* th;
-        if (i < SPO_HID) th = w.b1 + i;
-        else if (i < 2 * SPO_HID) th = w.b2 + (i - SPO_HID);
-        else if (i < 2 * SPO_HID + O * SPO_HID) th = w.w3 + (i - 2 * SPO_HID);
-        else if (i < 2 * SPO_HID + O * SPO_HID + O) th = w.b3 + (i - 2 * SPO_HID - O * SPO_HID);
+        if (i < SPO_HID) th = b1 + i;
+        else if (i < 2 * SPO_HID) th = b2 + (i - SPO_HID);
+        else if (i < 2 * SPO_HID + O * SPO_HID) th = w3 + (i - 2 * SPO_HID);
+        else if (i < 2 * SPO_HID + O * SPO_HID + O) th = b3 + (i - 2 * SPO_HID - O * SPO_HID);
         else th = log_std + (i - 2 * SPO_HID - O * SPO_HID - O);
         float m = msmall[i], v = vsmall[i];
         *th = adam_update(*th, __fmul_rn(gsmall[i], clip), m, v, k);
@@ -758,20 +787,16 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
   if (active) {
     for (int i = tid; i < SPO_HID * D; i += SPO_THREADS) {
       const int j = i / D, kx = i - j * D;
-      a.params[off.w1 + i] = w.w1t[kx * SPO_LDH + j];
-      if (NT1 > 1) {
-        a.adam_m[off.w1 + i] = m1s[kx * SPO_LDH + j];
-        a.adam_v[off.w1 + i] = v1s[kx * SPO_LDH + j];
-      }
+      a.params[off.w1 + i] = w1[j * ldx + kx];
     }
     for (int i = tid; i < SPO_HID * SPO_HID; i += SPO_THREADS)
-      a.params[off.w2 + i] = w.w2[(i >> 6) * SPO_LDH + (i & 63)];
+      a.params[off.w2 + i] = w2[(i >> 6) * SPO_LDH + (i & 63)];
     for (int i = tid; i < SP; i += SPO_THREADS) {
       float th;
-      if (i < SPO_HID) th = w.b1[i];
-      else if (i < 2 * SPO_HID) th = w.b2[i - SPO_HID];
-      else if (i < 2 * SPO_HID + O * SPO_HID) th = w.w3[i - 2 * SPO_HID];
-      else if (i < 2 * SPO_HID + O * SPO_HID + O) th = w.b3[i - 2 * SPO_HID - O * SPO_HID];
+      if (i < SPO_HID) th = b1[i];
+      else if (i < 2 * SPO_HID) th = b2[i - SPO_HID];
+      else if (i < 2 * SPO_HID + O * SPO_HID) th = w3[i - 2 * SPO_HID];
+      else if (i < 2 * SPO_HID + O * SPO_HID + O) th = b3[i - 2 * SPO_HID - O * SPO_HID];
       else th = log_std[i - 2 * SPO_HID - O * SPO_HID - O];
       const int g = sm.goff(off, i);
       a.params[g] = th;
@@ -779,18 +804,20 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       a.adam_v[g] = vsmall[i];
     }
 #pragma unroll
-    for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        const int g = off.w2 + (j0 + mi) * SPO_HID + k0 + ni;
-        a.adam_m[g] = mW2[mi][ni];
-        a.adam_v[g] = vW2[mi][ni];
-        if (NT1 == 1 && (k0 + ni) < D) {
-          const int g1 = off.w1 + (j0 + mi) * D + k0 + ni;
-          a.adam_m[g1] = mW1[mi][ni];
-          a.adam_v[g1] = vW1[mi][ni];
-        }
+    for (int e = 0; e < 16; ++e) {
+      int j, kc;
+      frag_rc(tid, e, 0, j, kc);
+      a.adam_m[off.w2 + j * SPO_HID + kc] = mW2[e];
+      a.adam_v[off.w2 + j * SPO_HID + kc] = vW2[e];
+      if (kc < D) {
+        a.adam_m[off.w1 + j * D + kc] = mW1[e];
+        a.adam_v[off.w1 + j * D + kc] = vW1[e];
       }
+      if (NT1 > 1 && kc + 64 < D) {
+        a.adam_m[off.w1 + j * D + kc + 64] = mv1b[e * SPO_THREADS + tid];
+        a.adam_v[off.w1 + j * D + kc + 64] = mv1b[(16 + e) * SPO_THREADS + tid];
+      }
+    }
     if (tid == 0) {
       a.adam_t[net] = t0 + static_cast<int>(n_steps);
       const int slot = (net == 0) ? 2 : (net == 1 ? 0 : 1);
@@ -802,9 +829,11 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
 }
 
 size_t update_smem_bytes(int D, int A, int nt1) {
-  const int Dp = spo_pad4(D);
-  size_t f = spo_net_smem_floats(D, A > 1 ? A : 1, true) + 8 + 3 * spo_pad4(2 * SPO_HID + A * SPO_HID + 2 * A) + 2 * SPO_ROWS * spo_ld(D) + 2 * SPO_ROWS * AUXW +
-             3 * SPO_ROWS * SPO_LDH + 3 * SPO_ROWS * SPO_MAX_ACT + 64 + 4 + (nt1 > 1 ? 2 * Dp * SPO_LDH : 0);
+  const int O = A > 1 ? A : 1;
+  const int ldx = upd_ldx(D);
+  size_t f = SPO_HID * ldx + SPO_HID + SPO_HID * SPO_LDH + SPO_HID + spo_pad4(O * SPO_HID) + spo_pad4(O) + 8 +
+             3 * spo_pad4(2 * SPO_HID + A * SPO_HID + 2 * A) + 2 * SPO_ROWS * ldx + 2 * SPO_ROWS * AUXW + 3 * SPO_ROWS * SPO_LDH +
+             3 * SPO_ROWS * SPO_MAX_ACT + 64 + 4 + (nt1 > 1 ? 2 * 16 * SPO_THREADS : 0);
   return f * sizeof(float);
 }
 
@@ -814,6 +843,10 @@ int launch_update(const UpdArgs& a, cudaStream_t stream) {
   SPO_REQUIRE(smem <= 227 * 1024, SPO_ERR_UNSUPPORTED, "spo_pg_update: obs_dim=%d needs %zu B of shared memory (> 227 KB)", a.D, smem);
   static int cluster_size = 0;   // 4 preferred (barrier measured faster than for 3, profiles/r01_ubench.txt); 3 as fallback
   SPO_CUDA_TRY(cudaFuncSetAttribute(spo_update_kernel<NT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  if (!cluster_size) {
+    const char* env = getenv("SPO_CLUSTER");   // debugging aid: pin the cluster size (3 or 4)
+    if (env && (env[0] == '3' || env[0] == '4')) cluster_size = env[0] - '0';
+  }
   for (int attempt = 0; attempt < 2; ++attempt) {
     const int cs = cluster_size ? cluster_size : (attempt == 0 ? 4 : 3);
     cudaLaunchConfig_t cfg{};
@@ -856,7 +889,7 @@ extern "C" int spo_comm_slot_floats(const spo_dims* d, int* slot_floats) {
   int rc = spo_check_dims(d);
   if (rc) return rc;
   SPO_REQUIRE(slot_floats, SPO_ERR_INVALID_ARG, "spo_comm_slot_floats: null output");
-  const int nt1 = spo_pad4(d->obs_dim) <= 64 ? 1 : 2;
+  const int nt1 = d->obs_dim <= 64 ? 1 : 2;
   *slot_floats = SPO_THREADS * 16 * (1 + nt1) + spo_pad4(2 * SPO_HID + d->act_dim * SPO_HID + 2 * d->act_dim);
   return SPO_OK;
 }
@@ -896,6 +929,6 @@ extern "C" int spo_pg_update_dp(const spo_dims* d, float* params, float* adam_m,
     a.comm.world = 1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (spo_pad4(d->obs_dim) <= 64) return launch_update<1>(a, st);
+  if (d->obs_dim <= 64) return launch_update<1>(a, st);
   return launch_update<2>(a, st);
 }
