@@ -179,13 +179,14 @@ int spo_pg_update(const spo_dims* d, float* params, float* adam_m, float* adam_v
 /* ---- data-parallel variant: ranks own disjoint env shards and hold
  * identical replicas of the weights; every minibatch step each net's gradient is summed
  * over the ranks INSIDE the persistent kernel through peer-mapped memory over
- * NVLink/NVSwitch (no NCCL call, no extra launch): a CTA publishes its gradient to its own
- * staging buffer, raises a sequence flag (release.sys), then pulls the peers' buffers
- * (acquire.sys + relaxed.sys loads) and accumulates them in rank order, so all ranks obtain
- * bit-identical sums and the replicas never diverge.  The result is scaled by 1/world
- * (global minibatch = world * batch).
- *   grad_bufs[r] : rank r's staging buffer, 2*3*slot floats (slot from spo_comm_slot_floats)
- *   flags[r]     : rank r's 3 uint32 sequence flags (zero-initialised)
+ * NVLink/NVSwitch (no NCCL call, no extra launch): a CTA pushes its gradient into a
+ * staging slot of every peer (posted remote stores), fences, raises the peer's sequence flag
+ * (release.sys), then waits on its own flags (acquire.sys) and accumulates the slots it
+ * received in rank order, so all ranks obtain bit-identical sums and the replicas never
+ * diverge.  The result is scaled by 1/world (global minibatch = world * batch).
+ *   grad_bufs[r] : rank r's staging memory, 2 * world * 3 * slot floats, indexed
+ *                  [parity][source rank][net][slot] (slot from spo_comm_slot_floats)
+ *   flags[r]     : rank r's world*3 uint32 sequence flags [source rank][net] (zero-initialised)
  *   seq_base     : number of minibatch steps all ranks have completed in earlier launches
  * Both pointer tables live in DEVICE memory (world entries each). */
 typedef struct spo_comm {

@@ -23,29 +23,31 @@ __device__ __forceinline__ void spo_mma_tf32(float (&d)[4], const uint32_t (&a)[
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-__device__ __forceinline__ void spo_mma_zero(float (&acc)[2][2][4]) {
+template <int MT>
+__device__ __forceinline__ void spo_mma_zero(float (&acc)[MT][2][4]) {
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
 }
 
-// acc (warp patch of 32 rows x 16 cols at (m_base, n_base)) += A * B over k in [0, K), K % 8 == 0.
+// acc (warp patch of 16*MT rows x 16 cols at (m_base, n_base)) += A * B over k in [0, K), K % 8 == 0.
 //   A(m, k) = A[m * a_sm + k * a_sk]      B(k, n) = B[k * b_sk + n * b_sn]      (shared memory)
 // Fragment ownership (g = lane >> 2, t = lane & 3), per 16 x 8 mma tile (mt, nt):
 //   acc[mt][nt][0..3] = C(m_base+16mt+g, n_base+8nt+2t), (.., +1), (row+8, ..), (row+8, +1)
-__device__ __forceinline__ void spo_warp_mma_3xtf32(float (&acc)[2][2][4], const float* __restrict__ A, int a_sm, int a_sk,
+template <int MT>
+__device__ __forceinline__ void spo_warp_mma_3xtf32(float (&acc)[MT][2][4], const float* __restrict__ A, int a_sm, int a_sk,
                                                     const float* __restrict__ B, int b_sk, int b_sn, int m_base, int n_base, int K) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const float* a_ptr = A + (m_base + g) * a_sm + t * a_sk;
   const float* b_ptr = B + t * b_sk + (n_base + g) * b_sn;
 #pragma unroll 2
   for (int k0 = 0; k0 < K; k0 += 8) {
-    uint32_t ah[2][4], al[2][4], bh[2][2], bl[2][2];
+    uint32_t ah[MT][4], al[MT][4], bh[2][2], bl[2][2];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < MT; ++mt) {
       const float* p = a_ptr + mt * 16 * a_sm + k0 * a_sk;
       spo_split_tf32(p[0], ah[mt][0], al[mt][0]);
       spo_split_tf32(p[8 * a_sm], ah[mt][1], al[mt][1]);
@@ -59,7 +61,7 @@ __device__ __forceinline__ void spo_warp_mma_3xtf32(float (&acc)[2][2][4], const
       spo_split_tf32(p[4 * b_sk], bh[nt][1], bl[nt][1]);
     }
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
         spo_mma_tf32(acc[mt][nt], al[mt], bh[nt]);

@@ -130,20 +130,24 @@ struct SmallMap {
   }
 };
 
+constexpr int UT = 512;   // threads per CTA: 16 warps, 4 per scheduler -- every phase of the step is a short dependent
+                          // chain, so latency hiding (not issue width) sets the pace (profiles/r01_update_phase_cycles.md)
+constexpr int FE = 8;     // accumulator-fragment elements per thread per 64x64 product (16 x 16 patch per warp)
+
 // leading dimension of the observation tile / W1 image: K padded to a multiple of 8, +4 floats
 // (== 4 mod 8: rows g = 0..7 of an mma fragment fall in 8 different bank groups)
 __host__ __device__ inline int upd_ldx(int D) { return ((D + 7) & ~7) + 4; }
 
-// element e16 = (mt*2 + nt)*4 + e of the 32 x 16 warp patch of a 64-wide output owned by thread tid
-__device__ __forceinline__ void frag_rc(int tid, int e16, int col_base, int& row, int& col) {
+// element e = nt*4 + c of the 16 x 16 warp patch of a 64-wide output owned by thread tid
+__device__ __forceinline__ void frag_rc(int tid, int e8, int col_base, int& row, int& col) {
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int mt = e16 >> 3, nt = (e16 >> 2) & 1, e = e16 & 3;
-  row = (warp & 1) * 32 + mt * 16 + g + ((e >> 1) << 3);
-  col = col_base + (warp >> 1) * 16 + nt * 8 + 2 * t + (e & 1);
+  const int nt = e8 >> 2, e = e8 & 3;
+  row = (warp & 3) * 16 + g + ((e >> 1) << 3);
+  col = col_base + (warp >> 2) * 16 + nt * 8 + 2 * t + (e & 1);
 }
 
 template <int NT1>
-__global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArgs a) {
+__global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ int comm_dead;   // a peer never showed up: stop waiting (ctrl->stop = 2 tells the host)
   cg::cluster_group cluster = cg::this_cluster();
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
   const int O = off.out;
   const SmallMap sm{O, is_actor ? A : 0};
   const int SP = sm.count();
-  const int mb = (wid & 1) * 32, nb = (wid >> 1) * 16;   // warp patch of every 64x64 product
+  const int mb = (wid & 3) * 16, nb = (wid >> 2) * 16;   // 16 x 16 warp patch of every 64x64 product
   const int g8 = lane >> 2, t4 = lane & 3;
 
   // ---- shared memory carve-up (weights in nn.Linear orientation [out][in]) ----
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
   float* red = p; p += 64;                       // block-reduction scratch
   float* xchg = p; p += 4;                       // [parity] CTA grad sumsq, read by peers through DSMEM
   float* mv1b = nullptr;                         // moments of the second W1 column block (obs_dim > 64): thread-private slots
-  if (NT1 > 1) { mv1b = p; p += 2 * 16 * SPO_THREADS; }
+  if (NT1 > 1) { mv1b = p; p += 2 * FE * UT; }
   float* dz1 = h2;
 
   const int tps = (a.batch + SPO_ROWS - 1) / SPO_ROWS;                    // tiles per step
@@ -205,30 +209,30 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
 
   // ---- one-time loads ----
   if (!idle) {
-    for (int i = tid; i < SPO_HID * ldx; i += SPO_THREADS) {
+    for (int i = tid; i < SPO_HID * ldx; i += UT) {
       const int j = i / ldx, k = i - j * ldx;
       w1[i] = (k < D) ? __ldg(a.params + off.w1 + j * D + k) : 0.f;
     }
-    for (int i = tid; i < SPO_HID * SPO_LDH; i += SPO_THREADS) {
+    for (int i = tid; i < SPO_HID * SPO_LDH; i += UT) {
       const int j = i / SPO_LDH, k = i - j * SPO_LDH;
       w2[i] = (k < SPO_HID) ? __ldg(a.params + off.w2 + j * SPO_HID + k) : 0.f;
     }
-    for (int i = tid; i < SPO_HID; i += SPO_THREADS) { b1[i] = __ldg(a.params + off.b1 + i); b2[i] = __ldg(a.params + off.b2 + i); }
-    for (int i = tid; i < O * SPO_HID; i += SPO_THREADS) w3[i] = __ldg(a.params + off.w3 + i);
-    for (int i = tid; i < O; i += SPO_THREADS) b3[i] = __ldg(a.params + off.b3 + i);
-    for (int i = tid; i < SP; i += SPO_THREADS) {
+    for (int i = tid; i < SPO_HID; i += UT) { b1[i] = __ldg(a.params + off.b1 + i); b2[i] = __ldg(a.params + off.b2 + i); }
+    for (int i = tid; i < O * SPO_HID; i += UT) w3[i] = __ldg(a.params + off.w3 + i);
+    for (int i = tid; i < O; i += UT) b3[i] = __ldg(a.params + off.b3 + i);
+    for (int i = tid; i < SP; i += UT) {
       msmall[i] = a.adam_m[sm.goff(off, i)];
       vsmall[i] = a.adam_v[sm.goff(off, i)];
     }
     if (is_actor && tid < A) log_std[tid] = a.params[off.log_std + tid];
-    for (int i = tid; i < 2 * SPO_ROWS * ldx; i += SPO_THREADS) xbuf[0][i] = 0.f;       // xbuf[0],[1] contiguous
-    for (int i = tid; i < 2 * SPO_ROWS * AUXW; i += SPO_THREADS) auxbuf[0][i] = 0.f;
+    for (int i = tid; i < 2 * SPO_ROWS * ldx; i += UT) xbuf[0][i] = 0.f;       // xbuf[0],[1] contiguous
+    for (int i = tid; i < 2 * SPO_ROWS * AUXW; i += UT) auxbuf[0][i] = 0.f;
   }
   // Adam moments of this thread's fragment elements: W2 and the first 64 input columns of W1 in registers
-  float mW2[16], vW2[16], mW1[16], vW1[16];
+  float mW2[FE], vW2[FE], mW1[FE], vW1[FE];
   if (active) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
+    for (int e = 0; e < FE; ++e) {
       int j, k;
       frag_rc(tid, e, 0, j, k);
       mW2[e] = a.adam_m[off.w2 + j * SPO_HID + k];
@@ -238,8 +242,8 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       vW1[e] = ok ? a.adam_v[off.w1 + j * D + k] : 0.f;
       if (NT1 > 1) {
         const bool ok2 = (k + 64) < D;
-        mv1b[e * SPO_THREADS + tid] = ok2 ? a.adam_m[off.w1 + j * D + k + 64] : 0.f;
-        mv1b[(16 + e) * SPO_THREADS + tid] = ok2 ? a.adam_v[off.w1 + j * D + k + 64] : 0.f;
+        mv1b[e * UT + tid] = ok2 ? a.adam_m[off.w1 + j * D + k + 64] : 0.f;
+        mv1b[(FE + e) * UT + tid] = ok2 ? a.adam_v[off.w1 + j * D + k + 64] : 0.f;
       }
     }
   }
@@ -253,14 +257,14 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
 
   // copies of one observation tile owned by this thread: item i = tid + 256*it covers
   // (row, chunk) = (i / per_row, i % per_row); decoded once
-  constexpr int PF_MAX = (NT1 == 1) ? 4 : 8;
+  constexpr int PF_MAX = (NT1 == 1) ? 2 : 4;
   int pf_rc[PF_MAX];
   int pf_n = 0;
   const int per_row = ((D & 3) == 0) ? (D >> 2) : D;
-  const bool pf_fast = SPO_ROWS * per_row <= PF_MAX * SPO_THREADS;
+  const bool pf_fast = SPO_ROWS * per_row <= PF_MAX * UT;
 #pragma unroll
   for (int it = 0; it < PF_MAX; ++it) {
-    const int i = tid + it * SPO_THREADS;
+    const int i = tid + it * UT;
     pf_rc[it] = 0xFF;
     if (pf_fast && i < SPO_ROWS * per_row) { pf_rc[it] = (i / per_row) | ((i % per_row) << 8); pf_n = it + 1; }
   }
@@ -289,13 +293,13 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       }
     } else if ((D & 3) == 0) {
       const int c4 = D >> 2;
-      for (int i = tid; i < rows * c4; i += SPO_THREADS) {
+      for (int i = tid; i < rows * c4; i += UT) {
         const int r = i / c4, c = i - r * c4;
         const int64_t g = a.perm[first + r];
         cp_async16(x + r * ldx + 4 * c, a.data.obs + g * D + 4 * c);
       }
     } else {
-      for (int i = tid; i < rows * D; i += SPO_THREADS) {
+      for (int i = tid; i < rows * D; i += UT) {
         const int r = i / D, c = i - r * D;
         const int64_t g = a.perm[first + r];
         cp_async4(x + r * ldx + c, a.data.obs + g * D + c);
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
     }
     if (is_actor) {
       const int per = A + 2 + (a.kind == SPO_LOSS_FOCOPS ? 2 * A : 0);
-      for (int i = tid; i < rows * per; i += SPO_THREADS) {
+      for (int i = tid; i < rows * per; i += UT) {
         const int r = i / per, c = i - r * per;
         const int64_t g = a.perm[first + r];
         float* dst = aux + r * AUXW;
@@ -315,29 +319,27 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       }
     } else {
       const float* tg = (net == 1) ? a.data.target_r : a.data.target_c;
-      for (int r = tid; r < rows; r += SPO_THREADS) cp_async4(aux + r * AUXW + AUX_TGT, tg + a.perm[first + r]);
+      for (int r = tid; r < rows; r += UT) cp_async4(aux + r * AUXW + AUX_TGT, tg + a.perm[first + r]);
     }
     // rows beyond the valid range must read as zeros (only the final, short step has any)
     if (rows < SPO_ROWS) {
-      for (int i = tid; i < (SPO_ROWS - rows) * ldx; i += SPO_THREADS) x[rows * ldx + i] = 0.f;
-      for (int i = tid; i < (SPO_ROWS - rows) * AUXW; i += SPO_THREADS) aux[rows * AUXW + i] = 0.f;
+      for (int i = tid; i < (SPO_ROWS - rows) * ldx; i += UT) x[rows * ldx + i] = 0.f;
+      for (int i = tid; i < (SPO_ROWS - rows) * AUXW; i += UT) aux[rows * AUXW + i] = 0.f;
     }
   };
 
   // hidden layer: out[r][j] = tanh(b[j] + sum_k in[r][k] * W[j][k]) on the tensor pipe
   auto hidden = [&](const float* in, int ldin, int K, const float* W, int ldw, const float* bias, float* out) {
-    float acc[2][2][4];
-    spo_mma_zero(acc);
-    spo_warp_mma_3xtf32(acc, in, ldin, 1, W, 1, ldw, mb, nb, K);
+    float acc[1][2][4];
+    spo_mma_zero<1>(acc);
+    spo_warp_mma_3xtf32<1>(acc, in, ldin, 1, W, 1, ldw, mb, nb, K);
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const int r = mb + mt * 16 + g8, j = nb + nt * 8 + 2 * t4;
-        const float2 bb = *reinterpret_cast<const float2*>(bias + j);
-        *reinterpret_cast<float2*>(out + r * SPO_LDH + j) = make_float2(spo_tanh(acc[mt][nt][0] + bb.x), spo_tanh(acc[mt][nt][1] + bb.y));
-        *reinterpret_cast<float2*>(out + (r + 8) * SPO_LDH + j) = make_float2(spo_tanh(acc[mt][nt][2] + bb.x), spo_tanh(acc[mt][nt][3] + bb.y));
-      }
+    for (int nt = 0; nt < 2; ++nt) {
+      const int r = mb + g8, j = nb + nt * 8 + 2 * t4;
+      const float2 bb = *reinterpret_cast<const float2*>(bias + j);
+      *reinterpret_cast<float2*>(out + r * SPO_LDH + j) = make_float2(spo_tanh(acc[0][nt][0] + bb.x), spo_tanh(acc[0][nt][1] + bb.y));
+      *reinterpret_cast<float2*>(out + (r + 8) * SPO_LDH + j) = make_float2(spo_tanh(acc[0][nt][2] + bb.x), spo_tanh(acc[0][nt][3] + bb.y));
+    }
   };
 
   __syncthreads();
@@ -345,14 +347,14 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
   cp_async_commit();
 
   // gradient accumulators = accumulator fragments of the dW products (persist across the tiles of a step)
-  float gW2[16], gW1[NT1][16];
+  float gW2[FE], gW1[NT1][FE];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) {
+  for (int e = 0; e < FE; ++e) {
     gW2[e] = 0.f;
 #pragma unroll
     for (int i = 0; i < NT1; ++i) gW1[i][e] = 0.f;
   }
-  for (int i = tid; i < SP; i += SPO_THREADS) gsmall[i] = 0.f;
+  for (int i = tid; i < SP; i += UT) gsmall[i] = 0.f;
   double acc_loss = 0.0;        // thread 0: sum over steps of this net's logged loss
   float step_loss = 0.f;        // thread 0: loss numerator of the current step (sum over its tiles)
   float step_aux0 = 0.f, step_aux1 = 0.f;  // FOCOPS: sum(ratio*adv), sum(mask)
@@ -390,7 +392,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       hidden(h1, SPO_LDH, SPO_HID, w2, SPO_LDH, b2, h2);
       __syncthreads();
       PHASE_MARK(2);
-      spo_out_fwd(h2, w3, b3, O, y, SPO_MAX_ACT, tid, SPO_THREADS);
+      spo_out_fwd(h2, w3, b3, O, y, SPO_MAX_ACT, tid, UT);
       __syncthreads();
 
       // ---------------- loss and d loss / d output, one thread per row ----------------
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       PHASE_MARK(3);   // output layer + loss rows
       // ---------------- backward ----------------
       // (a) small grads of the output layer: dW3[o][k], db3[o], dlog_std[j]
-      for (int i = tid; i < O * SPO_HID + O + sm.A_ls; i += SPO_THREADS) {
+      for (int i = tid; i < O * SPO_HID + O + sm.A_ls; i += UT) {
         float s = 0.f;
         if (i < O * SPO_HID) {
           const int o = i >> 6, k = i & 63;
@@ -515,9 +517,9 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       }
       // (b) dz2[r][k] = (sum_o dy[r][o] * w3[o][k]) * (1 - h2[r][k]^2)
       {
-        const int r0 = (tid >> 4) * 4, kk = (tid & 15) * 4;
+        const int r0 = (tid >> 4) * 2, kk = (tid & 15) * 4;
 #pragma unroll
-        for (int ri = 0; ri < 4; ++ri) {
+        for (int ri = 0; ri < 2; ++ri) {
           const int r = r0 + ri;
           float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int o = 0; o < O; ++o) {
@@ -533,7 +535,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       __syncthreads();
       PHASE_MARK(4);   // small grads + dz2
       // (c) dW2[j][k] += sum_r dz2[r][j] * h1[r][k];  db2[j] += sum_r dz2[r][j]
-      spo_warp_mma_3xtf32(reinterpret_cast<float (&)[2][2][4]>(gW2), dz2, 1, SPO_LDH, h1, SPO_LDH, 1, mb, nb, SPO_ROWS);
+      spo_warp_mma_3xtf32<1>(reinterpret_cast<float (&)[1][2][4]>(gW2), dz2, 1, SPO_LDH, h1, SPO_LDH, 1, mb, nb, SPO_ROWS);
       if (tid < SPO_HID) {
         float s = 0.f;
 #pragma unroll 8
@@ -542,21 +544,19 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       }
       // (d) dz1[r][k] = (sum_j dz2[r][j] * W2[j][k]) * (1 - h1[r][k]^2)   -> overwrites h2
       {
-        float acc[2][2][4];
-        spo_mma_zero(acc);
-        spo_warp_mma_3xtf32(acc, dz2, SPO_LDH, 1, w2, SPO_LDH, 1, mb, nb, SPO_HID);
+        float acc[1][2][4];
+        spo_mma_zero<1>(acc);
+        spo_warp_mma_3xtf32<1>(acc, dz2, SPO_LDH, 1, w2, SPO_LDH, 1, mb, nb, SPO_HID);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-          for (int nt = 0; nt < 2; ++nt) {
-            const int r = mb + mt * 16 + g8, k = nb + nt * 8 + 2 * t4;
-            const float2 ha = *reinterpret_cast<const float2*>(h1 + r * SPO_LDH + k);
-            const float2 hb = *reinterpret_cast<const float2*>(h1 + (r + 8) * SPO_LDH + k);
-            *reinterpret_cast<float2*>(dz1 + r * SPO_LDH + k) =
-                make_float2(acc[mt][nt][0] * (1.f - ha.x * ha.x), acc[mt][nt][1] * (1.f - ha.y * ha.y));
-            *reinterpret_cast<float2*>(dz1 + (r + 8) * SPO_LDH + k) =
-                make_float2(acc[mt][nt][2] * (1.f - hb.x * hb.x), acc[mt][nt][3] * (1.f - hb.y * hb.y));
-          }
+        for (int nt = 0; nt < 2; ++nt) {
+          const int r = mb + g8, k = nb + nt * 8 + 2 * t4;
+          const float2 ha = *reinterpret_cast<const float2*>(h1 + r * SPO_LDH + k);
+          const float2 hb = *reinterpret_cast<const float2*>(h1 + (r + 8) * SPO_LDH + k);
+          *reinterpret_cast<float2*>(dz1 + r * SPO_LDH + k) =
+              make_float2(acc[0][nt][0] * (1.f - ha.x * ha.x), acc[0][nt][1] * (1.f - ha.y * ha.y));
+          *reinterpret_cast<float2*>(dz1 + (r + 8) * SPO_LDH + k) =
+              make_float2(acc[0][nt][2] * (1.f - hb.x * hb.x), acc[0][nt][3] * (1.f - hb.y * hb.y));
+        }
       }
       __syncthreads();
       PHASE_MARK(5);   // dW2 + dh1
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
 #pragma unroll
       for (int i = 0; i < NT1; ++i)
         if (i * 64 + nb < K8)
-          spo_warp_mma_3xtf32(reinterpret_cast<float (&)[2][2][4]>(gW1[i]), dz1, 1, SPO_LDH, x, ldx, 1, mb, i * 64 + nb, SPO_ROWS);
+          spo_warp_mma_3xtf32<1>(reinterpret_cast<float (&)[1][2][4]>(gW1[i]), dz1, 1, SPO_LDH, x, ldx, 1, mb, i * 64 + nb, SPO_ROWS);
       if (tid < SPO_HID) {
         float s = 0.f;
 #pragma unroll 8
@@ -577,37 +577,46 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
     if (!last_tile) continue;   // next tile of the same step accumulates into the same gradients
 
     // ---------------- cross-GPU gradient sum (data-parallel ranks), in rank order ----------------
+    // Push protocol: every rank stores its gradient straight into each peer's staging slot
+    // [parity][source rank][net] over NVLink (posted remote stores), fences, then raises the
+    // peer's flag [source rank][net] = seq.  A receiver only polls and reads its OWN memory.
+    // Slot reuse is safe: a slot of parity p is rewritten at step s+2, after this rank saw every
+    // peer's flag of step s+1, which a peer raises only after it finished reading step s.
     if (a.comm.world > 1 && active) {
       __syncthreads();  // gsmall complete
+      constexpr int Q = FE / 4;   // float4s per tile per thread
       const int world = a.comm.world, me = a.comm.rank;
       const unsigned seq = static_cast<unsigned>(a.comm.seq_base + static_cast<unsigned long long>(step_idx) + 1ull);
-      const size_t slot = static_cast<size_t>(SPO_THREADS) * 16 * (1 + NT1) + spn;
-      const size_t slot_off = (static_cast<size_t>(seq & 1u) * 3 + net) * slot;
-      float4* mine = reinterpret_cast<float4*>(a.comm.grad_bufs[me] + slot_off);
+      const size_t slot = static_cast<size_t>(UT) * FE * (1 + NT1) + spn;
+      const size_t par_off = static_cast<size_t>(seq & 1u) * world * 3 * slot;
+      for (int r = 0; r < world; ++r) {
+        if (r == me) continue;
+        float4* dst = reinterpret_cast<float4*>(a.comm.grad_bufs[r] + par_off + (static_cast<size_t>(me) * 3 + net) * slot);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) mine[i * SPO_THREADS + tid] = make_float4(gW2[4 * i], gW2[4 * i + 1], gW2[4 * i + 2], gW2[4 * i + 3]);
+        for (int i = 0; i < Q; ++i) dst[i * UT + tid] = make_float4(gW2[4 * i], gW2[4 * i + 1], gW2[4 * i + 2], gW2[4 * i + 3]);
 #pragma unroll
-      for (int t = 0; t < NT1; ++t)
+        for (int t = 0; t < NT1; ++t)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          mine[(4 + t * 4 + i) * SPO_THREADS + tid] = make_float4(gW1[t][4 * i], gW1[t][4 * i + 1], gW1[t][4 * i + 2], gW1[t][4 * i + 3]);
-      float* mine_small = reinterpret_cast<float*>(mine + (4 + 4 * NT1) * SPO_THREADS);
-      for (int i = tid; i < SP; i += SPO_THREADS) mine_small[i] = gsmall[i];
+          for (int i = 0; i < Q; ++i)
+            dst[(Q + t * Q + i) * UT + tid] = make_float4(gW1[t][4 * i], gW1[t][4 * i + 1], gW1[t][4 * i + 2], gW1[t][4 * i + 3]);
+        float* dst_small = reinterpret_cast<float*>(dst + (Q + Q * NT1) * UT);
+        for (int i = tid; i < SP; i += UT) dst_small[i] = gsmall[i];
+      }
       __threadfence_system();
       __syncthreads();
-      if (tid == 0) st_release_sys(a.comm.flags[me] + net, seq);
+      if (tid < world && tid != me) st_release_sys(a.comm.flags[tid] + me * 3 + net, seq);
       if (tid < world && tid != me && !comm_dead) {
-        const unsigned limit = a.comm.spin_limit ? a.comm.spin_limit : 50000000u;
-        const unsigned* f = a.comm.flags[tid] + net;
+        const unsigned limit = a.comm.spin_limit ? a.comm.spin_limit : 400000000u;
+        const unsigned* f = a.comm.flags[me] + tid * 3 + net;     // local memory
         unsigned polls = 0;
         while (static_cast<int>(ld_acquire_sys(f) - seq) < 0) {
           if (++polls > limit) { comm_dead = 1; atomicExch(&ctrl->stop, 2); break; }
         }
       }
       __syncthreads();
-      float sW2[16], sW1[NT1][16];
+      float sW2[FE], sW1[NT1][FE];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
+      for (int e = 0; e < FE; ++e) {
         sW2[e] = 0.f;
 #pragma unroll
         for (int t = 0; t < NT1; ++t) sW1[t][e] = 0.f;
@@ -615,22 +624,22 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       for (int r = 0; r < world; ++r) {
         if (r == me) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
+          for (int e = 0; e < FE; ++e) {
             sW2[e] += gW2[e];
 #pragma unroll
             for (int t = 0; t < NT1; ++t) sW1[t][e] += gW1[t][e];
           }
         } else {
-          const float4* peer = reinterpret_cast<const float4*>(a.comm.grad_bufs[r] + slot_off);
-          float4 v2[4], v1[NT1][4];
+          const float4* src = reinterpret_cast<const float4*>(a.comm.grad_bufs[me] + par_off + (static_cast<size_t>(r) * 3 + net) * slot);
+          float4 v2[Q], v1[NT1][Q];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v2[i] = ld_relaxed_sys_f4(peer + i * SPO_THREADS + tid);
+          for (int i = 0; i < Q; ++i) v2[i] = ld_relaxed_sys_f4(src + i * UT + tid);
 #pragma unroll
           for (int t = 0; t < NT1; ++t)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v1[t][i] = ld_relaxed_sys_f4(peer + (4 + t * 4 + i) * SPO_THREADS + tid);
+            for (int i = 0; i < Q; ++i) v1[t][i] = ld_relaxed_sys_f4(src + (Q + t * Q + i) * UT + tid);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < Q; ++i) {
             sW2[4 * i] += v2[i].x; sW2[4 * i + 1] += v2[i].y; sW2[4 * i + 2] += v2[i].z; sW2[4 * i + 3] += v2[i].w;
 #pragma unroll
             for (int t = 0; t < NT1; ++t) {
@@ -641,16 +650,17 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       }
       const float inv_w = __fdiv_rn(1.f, static_cast<float>(world));
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
+      for (int e = 0; e < FE; ++e) {
         gW2[e] = __fmul_rn(sW2[e], inv_w);
 #pragma unroll
         for (int t = 0; t < NT1; ++t) gW1[t][e] = __fmul_rn(sW1[t][e], inv_w);
       }
-      for (int i = tid; i < SP; i += SPO_THREADS) {
+      for (int i = tid; i < SP; i += UT) {
         float sm_ = 0.f;
         for (int r = 0; r < world; ++r) {
           if (r == me) sm_ += gsmall[i];
-          else sm_ += ld_relaxed_sys_f(reinterpret_cast<const float*>(reinterpret_cast<const float4*>(a.comm.grad_bufs[r] + slot_off) + (4 + 4 * NT1) * SPO_THREADS) + i);
+          else sm_ += ld_relaxed_sys_f(reinterpret_cast<const float*>(reinterpret_cast<const float4*>(
+                          a.comm.grad_bufs[me] + par_off + (static_cast<size_t>(r) * 3 + net) * slot) + (Q + Q * NT1) * UT) + i);
         }
         gsmall[i] = __fmul_rn(sm_, inv_w);
       }
@@ -662,7 +672,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
     if (active) {
       __syncthreads();  // gsmall complete
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
+      for (int e = 0; e < FE; ++e) {
         int j, k;
         frag_rc(tid, e, 0, j, k);
         const float th = w2[j * SPO_LDH + k];
@@ -684,7 +694,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
           }
         }
       }
-      for (int i = tid; i < SP; i += SPO_THREADS) {
+      for (int i = tid; i < SP; i += UT) {
         float th;
         if (i < SPO_HID) th = b1[i];
         else if (i < 2 * SPO_HID) th = b2[i - SPO_HID];
@@ -705,7 +715,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
     if (tid == 0) {
       float s = extra_sumsq, t2 = 0.f;
       if (active) {
-        for (int i = 0; i < SPO_THREADS / 32; ++i) { s += red[16 + i]; t2 += red[32 + i]; }
+        for (int i = 0; i < UT / 32; ++i) { s += red[16 + i]; t2 += red[32 + i]; }
       }
       xchg[par] = idle ? 0.f : s;
       // logged loss of this step (ppo_lag.py:330-336): critics include the L2 term
@@ -740,7 +750,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       k.eps = a.hp.adam_eps;
       k.ss = static_cast<float>(-(static_cast<double>(lr) / (1.0 - b1pow)));
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
+      for (int e = 0; e < FE; ++e) {
         int j, kc;
         frag_rc(tid, e, 0, j, kc);
         float* pw = w2 + j * SPO_LDH + kc;
@@ -754,15 +764,15 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
         if (NT1 > 1) {
           if (kc + 64 < D) {
             float* p1 = w1 + j * ldx + kc + 64;
-            float m = mv1b[e * SPO_THREADS + tid], v = mv1b[(16 + e) * SPO_THREADS + tid];
+            float m = mv1b[e * UT + tid], v = mv1b[(FE + e) * UT + tid];
             *p1 = adam_update(*p1, __fmul_rn(gW1[NT1 - 1][e], clip), m, v, k);
-            mv1b[e * SPO_THREADS + tid] = m;
-            mv1b[(16 + e) * SPO_THREADS + tid] = v;
+            mv1b[e * UT + tid] = m;
+            mv1b[(FE + e) * UT + tid] = v;
           }
           gW1[NT1 - 1][e] = 0.f;
         }
       }
-      for (int i = tid; i < SP; i += SPO_THREADS) {
+      for (int i = tid; i < SP; i += UT) {
         float* th;
         if (i < SPO_HID) th = b1 + i;
         else if (i < 2 * SPO_HID) th = b2 + (i - SPO_HID);
@@ -785,13 +795,13 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
 
   // ---- write back: weights, moments, step counters, logged losses ----
   if (active) {
-    for (int i = tid; i < SPO_HID * D; i += SPO_THREADS) {
+    for (int i = tid; i < SPO_HID * D; i += UT) {
       const int j = i / D, kx = i - j * D;
       a.params[off.w1 + i] = w1[j * ldx + kx];
     }
-    for (int i = tid; i < SPO_HID * SPO_HID; i += SPO_THREADS)
+    for (int i = tid; i < SPO_HID * SPO_HID; i += UT)
       a.params[off.w2 + i] = w2[(i >> 6) * SPO_LDH + (i & 63)];
-    for (int i = tid; i < SP; i += SPO_THREADS) {
+    for (int i = tid; i < SP; i += UT) {
       float th;
       if (i < SPO_HID) th = b1[i];
       else if (i < 2 * SPO_HID) th = b2[i - SPO_HID];
@@ -804,7 +814,7 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
       a.adam_v[g] = vsmall[i];
     }
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
+    for (int e = 0; e < FE; ++e) {
       int j, kc;
       frag_rc(tid, e, 0, j, kc);
       a.adam_m[off.w2 + j * SPO_HID + kc] = mW2[e];
@@ -814,8 +824,8 @@ __global__ void __launch_bounds__(SPO_THREADS, 1) spo_update_kernel(const UpdArg
         a.adam_v[off.w1 + j * D + kc] = vW1[e];
       }
       if (NT1 > 1 && kc + 64 < D) {
-        a.adam_m[off.w1 + j * D + kc + 64] = mv1b[e * SPO_THREADS + tid];
-        a.adam_v[off.w1 + j * D + kc + 64] = mv1b[(16 + e) * SPO_THREADS + tid];
+        a.adam_m[off.w1 + j * D + kc + 64] = mv1b[e * UT + tid];
+        a.adam_v[off.w1 + j * D + kc + 64] = mv1b[(FE + e) * UT + tid];
       }
     }
     if (tid == 0) {
@@ -833,7 +843,7 @@ size_t update_smem_bytes(int D, int A, int nt1) {
   const int ldx = upd_ldx(D);
   size_t f = SPO_HID * ldx + SPO_HID + SPO_HID * SPO_LDH + SPO_HID + spo_pad4(O * SPO_HID) + spo_pad4(O) + 8 +
              3 * spo_pad4(2 * SPO_HID + A * SPO_HID + 2 * A) + 2 * SPO_ROWS * ldx + 2 * SPO_ROWS * AUXW + 3 * SPO_ROWS * SPO_LDH +
-             3 * SPO_ROWS * SPO_MAX_ACT + 64 + 4 + (nt1 > 1 ? 2 * 16 * SPO_THREADS : 0);
+             3 * SPO_ROWS * SPO_MAX_ACT + 64 + 4 + (nt1 > 1 ? 2 * FE * UT : 0);
   return f * sizeof(float);
 }
 
@@ -851,7 +861,7 @@ int launch_update(const UpdArgs& a, cudaStream_t stream) {
     const int cs = cluster_size ? cluster_size : (attempt == 0 ? 4 : 3);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(cs);
-    cfg.blockDim = dim3(SPO_THREADS);
+    cfg.blockDim = dim3(UT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -890,7 +900,7 @@ extern "C" int spo_comm_slot_floats(const spo_dims* d, int* slot_floats) {
   if (rc) return rc;
   SPO_REQUIRE(slot_floats, SPO_ERR_INVALID_ARG, "spo_comm_slot_floats: null output");
   const int nt1 = d->obs_dim <= 64 ? 1 : 2;
-  *slot_floats = SPO_THREADS * 16 * (1 + nt1) + spo_pad4(2 * SPO_HID + d->act_dim * SPO_HID + 2 * d->act_dim);
+  *slot_floats = UT * FE * (1 + nt1) + spo_pad4(2 * SPO_HID + d->act_dim * SPO_HID + 2 * d->act_dim);
   return SPO_OK;
 }
 

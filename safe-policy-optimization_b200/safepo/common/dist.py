@@ -2,8 +2,9 @@
 
 Exchange steps of the hot path and who performs them:
 
-* per minibatch step -- the gradient of each net: summed INSIDE ``spo_pg_update_dp`` over
-  peer-mapped staging buffers (NVLink/NVSwitch loads, sequence flags), see csrc/spo_update.cu.
+* per minibatch step -- the gradient of each net: summed INSIDE ``spo_pg_update_dp``: every
+  rank pushes its gradient into peer-mapped staging slots over NVLink/NVSwitch and raises
+  sequence flags; receivers only touch their own memory (csrc/spo_update.cu).
   This module only allocates those buffers, exchanges their CUDA-IPC handles through
   ``torch.distributed`` and hands the kernel the device-side pointer tables.
 * per pass -- the KL sum (one fp64): ``all_reduce`` between ``spo_actor_kl_accumulate`` and
@@ -64,9 +65,9 @@ class DataParallel:
         lib = L.lib()
         slot = C.c_int()
         L.check(lib.spo_comm_slot_floats(C.byref(dims), C.byref(slot)), "spo_comm_slot_floats")
-        nbytes_grad = 2 * 3 * slot.value * 4
+        nbytes_grad = 2 * self.world * 3 * slot.value * 4      # [parity][source rank][net][slot]
         own = []
-        for nbytes in (nbytes_grad, 256):
+        for nbytes in (nbytes_grad, max(256, 4 * 3 * self.world)):
             ptr = C.c_void_p()
             L.check(lib.spo_comm_alloc(nbytes, C.byref(ptr)), "spo_comm_alloc")
             own.append(ptr.value)

@@ -14,9 +14,9 @@ __global__ void k_test(const float* A, int a_sm, int a_sk, const float* B, int b
   for (int i = threadIdx.x; i < 64 * 72; i += blockDim.x) { As[i] = A[i]; Bs[i] = B[i]; }
   __syncthreads();
   float acc[2][2][4];
-  spo_mma_zero(acc);
+  spo_mma_zero<2>(acc);
   const int warp = threadIdx.x >> 5;
-  spo_warp_mma_3xtf32(acc, As, a_sm, a_sk, Bs, b_sk, b_sn, (warp & 1) * 32, (warp >> 1) * 16, K);
+  spo_warp_mma_3xtf32<2>(acc, As, a_sm, a_sk, Bs, b_sk, b_sn, (warp & 1) * 32, (warp >> 1) * 16, K);
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   for (int mt = 0; mt < 2; ++mt)
     for (int nt = 0; nt < 2; ++nt) {
