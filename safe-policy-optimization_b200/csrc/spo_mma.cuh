@@ -4,17 +4,21 @@
 // Why this path for the 64-row tiles (profiles/r01_update_phase_cycles.md): a 4x4
 // register-tiled FFMA GEMM pulls 2 B of shared-memory operands per FMA and is bound by the
 // 128 B/clk shared-memory return bandwidth (4.1 k cycles per 64^3 GEMM); mma fragments need
-// 0.19 B per FMA, the split x = hi + lo (hi = rna_tf32(x), lo = rna_tf32(x - hi)) costs three
-// ALU ops per loaded element on an otherwise idle pipe, and lo*hi + hi*lo + hi*hi
+// 0.19 B per FMA, the split x = hi + lo costs two
+// full-rate ALU ops per loaded element, and lo*hi + hi*lo + hi*hi
 // (small terms first) matches fp32 accumulation to ~3e-7 relative.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// hi = x with the 13 low mantissa bits cleared (what the tensor core would read anyway),
+// lo = x - hi exactly (<= 13 significant bits; the hardware keeps its top 11).  One LOP3 and one
+// FADD on the full-rate pipes -- cvt.rna.tf32.f32 is a quarter-rate conversion and was a
+// co-bottleneck of the tile GEMMs.  Accuracy with small terms first: 1.2e-6 max abs error on
+// |values| <= 2.8 at K = 64 (tools/tc_test.cu, split = 1) vs 7.8e-7 for rounded splits.
 __device__ __forceinline__ void spo_split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 __device__ __forceinline__ void spo_mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {

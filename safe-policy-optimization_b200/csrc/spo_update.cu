@@ -328,11 +328,15 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     }
   };
 
+#ifdef SPO_PHASE_TIMERS
+  long long phase_t__ = clock64();
+#endif
   // hidden layer: out[r][j] = tanh(b[j] + sum_k in[r][k] * W[j][k]) on the tensor pipe
   auto hidden = [&](const float* in, int ldin, int K, const float* W, int ldw, const float* bias, float* out) {
     float acc[1][2][4];
     spo_mma_zero<1>(acc);
     spo_warp_mma_3xtf32<1>(acc, in, ldin, 1, W, 1, ldw, mb, nb, K);
+    PHASE_MARK(11);  // (sub) hidden-layer GEMM only, as seen by warp 0
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
       const int r = mb + g8, j = nb + nt * 8 + 2 * t4;
@@ -359,9 +363,6 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   float step_loss = 0.f;        // thread 0: loss numerator of the current step (sum over its tiles)
   float step_aux0 = 0.f, step_aux1 = 0.f;  // FOCOPS: sum(ratio*adv), sum(mask)
   int64_t step_idx = 0;
-#ifdef SPO_PHASE_TIMERS
-  long long phase_t__ = clock64();
-#endif
 
   for (int64_t q = 0; q < n_tiles; ++q) {
     const int cur = static_cast<int>(q & 1);
@@ -536,17 +537,20 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       PHASE_MARK(4);   // small grads + dz2
       // (c) dW2[j][k] += sum_r dz2[r][j] * h1[r][k];  db2[j] += sum_r dz2[r][j]
       spo_warp_mma_3xtf32<1>(reinterpret_cast<float (&)[1][2][4]>(gW2), dz2, 1, SPO_LDH, h1, SPO_LDH, 1, mb, nb, SPO_ROWS);
+      PHASE_MARK(12);  // (sub) dW2 GEMM
       if (tid < SPO_HID) {
         float s = 0.f;
 #pragma unroll 8
         for (int r = 0; r < SPO_ROWS; ++r) s += dz2[r * SPO_LDH + tid];
         gsmall[SPO_HID + tid] += s;
       }
+      PHASE_MARK(13);  // (sub) db2 column sums
       // (d) dz1[r][k] = (sum_j dz2[r][j] * W2[j][k]) * (1 - h1[r][k]^2)   -> overwrites h2
       {
         float acc[1][2][4];
         spo_mma_zero<1>(acc);
         spo_warp_mma_3xtf32<1>(acc, dz2, SPO_LDH, 1, w2, SPO_LDH, 1, mb, nb, SPO_HID);
+        PHASE_MARK(14);  // (sub) dh1 GEMM
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
           const int r = mb + g8, k = nb + nt * 8 + 2 * t4;

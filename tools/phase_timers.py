@@ -34,7 +34,7 @@ upd.run(data, perms=[perm])
 torch.cuda.synchronize()
 lib.spo_debug_phase_cycles(buf, 1)
 names = ["gather wait/issue", "fwd L1", "fwd L2", "out+loss", "small grads+dz2", "dW2+dh1", "dW1", "dp exchange", "reg+sumsq", "cluster sync",
-         "adam"]
+         "adam", "(hidden GEMMs x2)", "(dW2 GEMM)", "(db2 sums)", "(dh1 GEMM)"]
 for rank, net in enumerate(("actor", "reward critic", "cost critic")):
-    row = [buf[rank * 16 + i] / steps for i in range(11)]
+    row = [buf[rank * 16 + i] / steps for i in range(15)]
     print(f"{net:14s} total {sum(row):8.0f} cyc/step | " + " ".join(f"{n}={v:.0f}" for n, v in zip(names, row)))

@@ -31,6 +31,27 @@ __global__ void k_mma(float* out, long long* cyc, int iters) {
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// the access pattern of spo_warp_mma_3xtf32<1>: per k-step 6 mma on NCH independent accumulator chains
+template <int NCH>
+__global__ void k_mma_chain(float* out, long long* cyc, int iters) {
+  float d[NCH][4];
+  unsigned a[4] = {threadIdx.x, threadIdx.x + 1, 3, 4}, b[2] = {5, threadIdx.x};
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.f;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) mma_tf32(d[j % NCH], a, b);
+  }
+  long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) s += d[i][0] + d[i][1] + d[i][2] + d[i][3];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 template <int NACC>
 __global__ void k_ffma(float* out, long long* cyc, int iters, float x, float y) {
   float d[NACC];
@@ -104,6 +125,14 @@ int main() {
   printf("mma 2 indep per warp, 1 warp: %.1f cyc per pair\n", (double)h[0] / iters);
   k_mma<4><<<1, 128>>>(out, cyc, iters); cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost);
   printf("mma 4 indep, 4 warps (1/SMSP): %.2f cyc/mma/warp\n", (double)h[0] / iters / 4);
+  for (int t : {256, 512}) {
+    k_mma_chain<2><<<1, t>>>(out, cyc, iters); cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("6 mma/k-step on 2 chains (3 deep), threads=%d: %.1f cyc per k-step -> 64^3 GEMM (8 k-steps) %.0f cyc\n", t, (double)h[0] / iters, 8.0 * h[0] / iters);
+    k_mma_chain<6><<<1, t>>>(out, cyc, iters); cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("6 mma/k-step on 6 chains (independent), threads=%d: %.1f cyc per k-step\n", t, (double)h[0] / iters);
+    k_mma_chain<3><<<1, t>>>(out, cyc, iters); cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("6 mma/k-step on 3 chains, threads=%d: %.1f cyc per k-step\n", t, (double)h[0] / iters);
+  }
   for (int t : threads) {
     k_ffma<16><<<1, t>>>(out, cyc, iters, 1.0001f, 0.5f); cudaMemcpy(h, cyc, 8, cudaMemcpyDeviceToHost);
     double per = (double)h[0] / iters / 16;
