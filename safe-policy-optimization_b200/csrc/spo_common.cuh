@@ -200,6 +200,20 @@ __device__ __forceinline__ void spo_zero(float (&acc)[4][4]) {
 // <= 1-2 ulp.  (Never tanh.approx here: parity bar is 1e-5 relative on losses.)
 __device__ __forceinline__ float spo_tanh(float x) { return tanhf(x); }
 
+// tanh for the epilogues: 1 - 2/(exp(2|x|)+1) on the SFU (ex2 + rcp) for |x| >= 0.04 and
+// the odd Taylor polynomial below that (absolute error < 3e-7 overall, relative < 2e-7 near
+// 0); tanhf costs ~25 dependent instructions per element, which made the v1 epilogue
+// the bottleneck of this kernel.
+__device__ __forceinline__ float spo_tanh_fast(float x) {
+  const float ax = fabsf(x);
+  const float x2 = x * x;
+  const float poly = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.053968254f, 0.13333334f), -0.33333334f), 1.f);
+  const float e = __expf(2.f * ax);
+  const float big = copysignf(1.f - __fdividef(2.f, e + 1.f), x);
+  return ax < 0.04f ? poly : big;
+}
+
+
 // Hidden layer forward for a 64-row tile:  out[r][j] = tanh(b[j] + sum_k in[r][k] * wt[k][j]).
 // in: sample-major [64][ldin] with K (multiple of 4) valid columns; out: [64][LDH].
 // Thread tile: units j = m0..m0+3, rows r = ns, ns+4, ns+8, ns+12.

@@ -52,18 +52,7 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 
-// tanh for the epilogues: 1 - 2/(exp(2|x|)+1) on the SFU (ex2 + rcp) for |x| >= 0.04 and
-// the odd Taylor polynomial below that (absolute error < 3e-7 overall, relative < 2e-7 near
-// 0); tanhf costs ~25 dependent instructions per element, which made the v1 epilogue
-// the bottleneck of this kernel.
-__device__ __forceinline__ float tanh_fast(float x) {
-  const float ax = fabsf(x);
-  const float x2 = x * x;
-  const float poly = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.053968254f, 0.13333334f), -0.33333334f), 1.f);
-  const float e = __expf(2.f * ax);
-  const float big = copysignf(1.f - __fdividef(2.f, e + 1.f), x);
-  return ax < 0.04f ? poly : big;
-}
+__device__ __forceinline__ float tanh_fast(float x) { return spo_tanh_fast(x); }
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo) {
   uint64_t d = 0;

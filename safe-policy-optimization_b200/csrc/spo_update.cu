@@ -33,16 +33,23 @@ namespace cg = cooperative_groups;
 // clock64() deltas per phase of the step; read back with spo_debug_phase_cycles().
 #ifdef SPO_PHASE_TIMERS
 __device__ unsigned long long g_phase_cycles[4][16];
+__device__ long long g_trace[4][16][24];   // arrival time of every warp at every mark during step 50
+#define TRACE_MARK(idx)                                                   \
+  do {                                                                    \
+    if (lane == 0 && step_idx == 50) g_trace[rank & 3][wid][idx] = clock64(); \
+  } while (0)
 #define PHASE_MARK(idx)                                                   \
   do {                                                                    \
+    TRACE_MARK(idx);                                                      \
     if (tid == 0) {                                                       \
       const long long now__ = clock64();                                  \
-      atomicAdd(&g_phase_cycles[rank & 3][idx], static_cast<unsigned long long>(now__ - phase_t__)); \
+      sm_phase__[idx] += static_cast<unsigned long long>(now__ - phase_t__); /* no global traffic inside the step */ \
       phase_t__ = now__;                                                  \
     }                                                                     \
   } while (0)
 #else
 #define PHASE_MARK(idx) do { } while (0)
+#define TRACE_MARK(idx) do { } while (0)
 #endif
 
 namespace {
@@ -89,17 +96,20 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // One Adam step on a scalar in torch's _multi_tensor_adam op order:
 //   m = lerp(m, g, 1-b1) (fused mul-add);  v = v*b2 + ((1-b2)*g)*g;
 //   denom = sqrt(v)/sqrt(bc2) + eps;  p = p + (step_size*m)/denom,  step_size = -lr/bc1.
-// sqrt and the two divisions use the SFU approximations (sqrt.approx / div.approx,
-// <= 2 ulp): IEEE-exact versions cost ~60 issue slots per parameter (profiles/r01) for
+// sqrt and the division use the SFU approximations (sqrt.approx / div.approx,
+// <= 2 ulp), 1/sqrt(bc2) is a precomputed factor: IEEE-exact versions cost ~60 issue slots per parameter (profiles/r01) for
 // differences far below the 1e-5 parity bar.
 struct AdamK {
-  float w1, b2, w2, bc2s, eps, ss;  // w1 = 1-b1, w2 = 1-b2
+  float w1, b2, w2, ibc2s, eps, ss;  // w1 = 1-b1, w2 = 1-b2, ibc2s = 1/sqrt(1-b2^t)
 };
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
@@ -109,7 +119,7 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 __device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, const AdamK& k) {
   m = fmaf(k.w1, __fsub_rn(g, m), m);
   v = __fadd_rn(__fmul_rn(v, k.b2), __fmul_rn(__fmul_rn(k.w2, g), g));
-  const float denom = __fadd_rn(__fdividef(sqrt_approx(v), k.bc2s), k.eps);
+  const float denom = fmaf(sqrt_approx(v), k.ibc2s, k.eps);
   return __fadd_rn(p, __fdividef(__fmul_rn(k.ss, m), denom));
 }
 
@@ -134,9 +144,13 @@ constexpr int UT = 512;   // threads per CTA: 16 warps, 4 per scheduler -- every
                           // chain, so latency hiding (not issue width) sets the pace (profiles/r01_update_phase_cycles.md)
 constexpr int FE = 8;     // accumulator-fragment elements per thread per 64x64 product (16 x 16 patch per warp)
 
-// leading dimension of the observation tile / W1 image: K padded to a multiple of 8, +4 floats
-// (== 4 mod 8: rows g = 0..7 of an mma fragment fall in 8 different bank groups)
-__host__ __device__ inline int upd_ldx(int D) { return ((D + 7) & ~7) + 4; }
+// Every shared-memory extent is a compile-time constant: the observation tile / W1 image are padded to
+// KX = 64 * NT1 input columns (zeros beyond obs_dim), leading dimension KX + 4 (== 4 mod 8: rows g = 0..7 of
+// an mma fragment fall in 8 different bank groups), the output layer and the small-parameter slots are
+// sized for SPO_MAX_ACT.  Addresses are then immediates off one base -- with runtime extents the
+// compiler rematerialised pointer arithmetic inside the step (18 % of the issued instructions, profiles/r01).
+__host__ __device__ constexpr int upd_ldx(int nt1) { return 64 * nt1 + 4; }
+constexpr int SPN = (2 * SPO_HID + SPO_MAX_ACT * SPO_HID + 2 * SPO_MAX_ACT + 3) & ~3;   // small-parameter slots
 
 // element e = nt*4 + c of the 16 x 16 warp patch of a 64-wide output owned by thread tid
 __device__ __forceinline__ void frag_rc(int tid, int e8, int col_base, int& row, int& col) {
@@ -157,7 +171,8 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   spo_update_ctrl* ctrl = a.ctrl;
   if (*reinterpret_cast<volatile int*>(&ctrl->stop)) return;  // whole cluster takes this branch together
 
-  const int D = a.D, A = a.A, K8 = (D + 7) & ~7, ldx = upd_ldx(D);
+  const int D = a.D, A = a.A;
+  constexpr int KX = 64 * NT1, ldx = upd_ldx(NT1);
   const bool idle = rank >= 3;
   const int net = idle ? 2 : static_cast<int>(rank);
   const bool is_actor = (net == 0) && !idle;
@@ -171,26 +186,25 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
 
   // ---- shared memory carve-up (weights in nn.Linear orientation [out][in]) ----
   float* p = smem;
+  // minibatch row indices of tile q in slot q & 1: requested a step ahead of the rows they address, so the
+  // gather never waits on a dependent global load
+  int64_t* idxbuf = reinterpret_cast<int64_t*>(p); p += 2 * 2 * SPO_ROWS;   // [2][64] int64
+  float* lsc = p; p += 4 * SPO_MAX_ACT;           // per action dim: std, 1/var, log(std), spare (refreshed every step)
+  float* adk = p; p += 8;                         // Adam scalars of the current step (one thread does the fp64 math)
   float* w1 = p;  p += SPO_HID * ldx;
   float* b1 = p;  p += SPO_HID;
   float* w2 = p;  p += SPO_HID * SPO_LDH;
   float* b2 = p;  p += SPO_HID;
   // every CTA of the cluster carves the SAME layout (actor-sized output layer): the peers read
   // xchg through distributed shared memory at their own offset of it
-  const int Oc = A > 1 ? A : 1;
-  float* w3 = p;  p += spo_pad4(Oc * SPO_HID);
-  float* b3 = p;  p += spo_pad4(Oc);
+  float* w3 = p;  p += SPO_MAX_ACT * SPO_HID;
+  float* b3 = p;  p += SPO_MAX_ACT;
   float* log_std = p; p += 8;
-  const int spn = spo_pad4(2 * SPO_HID + A * SPO_HID + 2 * A);   // small-parameter slots (actor-sized for all nets)
-  float* msmall = p;  p += spn;
-  float* vsmall = p;  p += spn;
-  float* gsmall = p;  p += spn;
-  float* xbuf[2];
-  xbuf[0] = p; p += SPO_ROWS * ldx;
-  xbuf[1] = p; p += SPO_ROWS * ldx;
-  float* auxbuf[2];
-  auxbuf[0] = p; p += SPO_ROWS * AUXW;
-  auxbuf[1] = p; p += SPO_ROWS * AUXW;
+  float* msmall = p;  p += SPN;
+  float* vsmall = p;  p += SPN;
+  float* gsmall = p;  p += SPN;
+  float* x = p;   p += SPO_ROWS * ldx;      // observation tile (the next one is staged in registers)
+  float* aux = p; p += SPO_ROWS * AUXW;     // per-row side data
   float* h1 = p;  p += SPO_ROWS * SPO_LDH;
   float* h2 = p;  p += SPO_ROWS * SPO_LDH;   // becomes dz1 during backward
   float* dz2 = p; p += SPO_ROWS * SPO_LDH;
@@ -225,8 +239,8 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       vsmall[i] = a.adam_v[sm.goff(off, i)];
     }
     if (is_actor && tid < A) log_std[tid] = a.params[off.log_std + tid];
-    for (int i = tid; i < 2 * SPO_ROWS * ldx; i += UT) xbuf[0][i] = 0.f;       // xbuf[0],[1] contiguous
-    for (int i = tid; i < 2 * SPO_ROWS * AUXW; i += UT) auxbuf[0][i] = 0.f;
+    for (int i = tid; i < SPO_ROWS * ldx; i += UT) x[i] = 0.f;
+    for (int i = tid; i < SPO_ROWS * AUXW; i += UT) aux[i] = 0.f;
   }
   // Adam moments of this thread's fragment elements: W2 and the first 64 input columns of W1 in registers
   float mW2[FE], vW2[FE], mW1[FE], vW1[FE];
@@ -255,100 +269,169 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   const float vcoef = (net == 1) ? a.hp.value_coef : 1.f;
   const float reg = is_actor ? 0.f : __fmul_rn(vcoef, __fmul_rn(a.hp.critic_l2, 2.f));
 
-  // copies of one observation tile owned by this thread: item i = tid + 256*it covers
-  // (row, chunk) = (i / per_row, i % per_row); decoded once
+  // The next tile is staged in registers: its rows are requested with plain loads at the end of the current
+  // step (between the arrive and the wait of the cluster barrier) and stored to shared memory at the top of the
+  // next one, Adam in between hides the latency.  (cp.async gathers cost 1.5 k cycles of issue per tile for
+  // the rows plus 1.7 k for the side data -- LDGSTS issues at ~50 cycles per warp instruction here,
+  // profiles/r01_update_phase_cycles.md.)
+  // Item it of this thread: obs_dim % 4 == 0: float4 chunk i = tid + it*UT -> (row, chunk) = (i / (D/4), i % (D/4)),
+  // decoded once; otherwise scalar element i -> (i / D, i % D).
   constexpr int PF_MAX = (NT1 == 1) ? 2 : 4;
+  const bool vec_rows = (D & 3) == 0;
   int pf_rc[PF_MAX];
   int pf_n = 0;
-  const int per_row = ((D & 3) == 0) ? (D >> 2) : D;
-  const bool pf_fast = SPO_ROWS * per_row <= PF_MAX * UT;
 #pragma unroll
   for (int it = 0; it < PF_MAX; ++it) {
-    const int i = tid + it * UT;
+    const int i = tid + it * UT, per_row = D >> 2;
     pf_rc[it] = 0xFF;
-    if (pf_fast && i < SPO_ROWS * per_row) { pf_rc[it] = (i / per_row) | ((i % per_row) << 8); pf_n = it + 1; }
+    if (vec_rows && i < SPO_ROWS * per_row) { pf_rc[it] = (i / per_row) | ((i % per_row) << 8); pf_n = it + 1; }
   }
+  float xr[4 * PF_MAX];   // staged observation values
+  float auxr[4];          // staged side data: column c = q8s + 8*i of row r8s
+#pragma unroll
+  for (int i = 0; i < 4 * PF_MAX; ++i) xr[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) auxr[i] = 0.f;
+  const int r8s = tid >> 3, q8s = tid & 7;
+  const int aux_per = !is_actor ? 1 : A + 2 + (a.kind == SPO_LOSS_FOCOPS ? 2 * A : 0);   // <= 26 columns
+  // shared-memory slot of side-data column c
+  auto aux_slot = [&](int c) {
+    if (!is_actor) return AUX_TGT;
+    if (c < A) return c;
+    if (c == A) return AUX_LOGP;
+    if (c == A + 1) return AUX_ADV;
+    if (c < 2 * A + 2) return AUX_OMEAN + (c - A - 2);
+    return AUX_OSTD + (c - 2 * A - 2);
+  };
 
-  // gather + async copy of one tile (64 rows) into buffer b
-  auto prefetch = [&](int64_t q, int b) {
+  int64_t step_idx = 0;
+#ifdef SPO_PHASE_TIMERS
+  __shared__ unsigned long long sm_phase__[16];
+  if (tid < 16) sm_phase__[tid] = 0ull;
+#endif
+  // tile (step, sub) after n more tiles -- no 64-bit division on the per-step path
+  auto tile_after = [&](int64_t step, int sub, int n, int64_t& step_o, int& sub_o) {
+    step_o = step; sub_o = sub;
+    for (int i = 0; i < n; ++i)
+      if (++sub_o == tps) { sub_o = 0; ++step_o; }
+  };
+  // request the rows of tile q = (step, sub): global -> registers (rows beyond the valid range stage zeros)
+  auto load_next = [&](int64_t q, int64_t step, int sub) {
     if (!active || q >= n_tiles) return;
-    const int64_t step = q / tps;
-    const int sub = static_cast<int>(q - step * tps);
-    const int64_t first = step * a.batch + sub * SPO_ROWS;
     int64_t rs = a.perm_len - step * a.batch;
     if (rs > a.batch) rs = a.batch;
     int rows = static_cast<int>(rs) - sub * SPO_ROWS;
     rows = rows < 0 ? 0 : (rows > SPO_ROWS ? SPO_ROWS : rows);
-    float* x = xbuf[b];
-    float* aux = auxbuf[b];
-    if (pf_fast) {
+    const int64_t* ridx = idxbuf + (q & 1) * SPO_ROWS;
+    if (vec_rows) {
 #pragma unroll
       for (int it = 0; it < PF_MAX; ++it) {
         const int r = pf_rc[it] & 0xFF, c = pf_rc[it] >> 8;
-        if (it < pf_n && r < rows) {
-          const int64_t g = a.perm[first + r];
-          if ((D & 3) == 0) cp_async16(x + r * ldx + 4 * c, a.data.obs + g * D + 4 * c);
-          else cp_async4(x + r * ldx + c, a.data.obs + g * D + c);
-        }
-      }
-    } else if ((D & 3) == 0) {
-      const int c4 = D >> 2;
-      for (int i = tid; i < rows * c4; i += UT) {
-        const int r = i / c4, c = i - r * c4;
-        const int64_t g = a.perm[first + r];
-        cp_async16(x + r * ldx + 4 * c, a.data.obs + g * D + 4 * c);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (it < pf_n && r < rows) v = __ldg(reinterpret_cast<const float4*>(a.data.obs + ridx[r] * D + 4 * c));
+        xr[4 * it] = v.x; xr[4 * it + 1] = v.y; xr[4 * it + 2] = v.z; xr[4 * it + 3] = v.w;
       }
     } else {
-      for (int i = tid; i < rows * D; i += UT) {
-        const int r = i / D, c = i - r * D;
-        const int64_t g = a.perm[first + r];
-        cp_async4(x + r * ldx + c, a.data.obs + g * D + c);
+#pragma unroll
+      for (int it = 0; it < 4 * PF_MAX; ++it) {
+        const int i = tid + it * UT, r = i / D, c = i - r * D;
+        xr[it] = (r < rows) ? __ldg(a.data.obs + ridx[r] * D + c) : 0.f;
       }
     }
-    if (is_actor) {
-      const int per = A + 2 + (a.kind == SPO_LOSS_FOCOPS ? 2 * A : 0);
-      for (int i = tid; i < rows * per; i += UT) {
-        const int r = i / per, c = i - r * per;
-        const int64_t g = a.perm[first + r];
-        float* dst = aux + r * AUXW;
-        if (c < A) cp_async4(dst + c, a.data.act + g * A + c);
-        else if (c == A) cp_async4(dst + AUX_LOGP, a.data.logp + g);
-        else if (c == A + 1) cp_async4(dst + AUX_ADV, a.data.adv + g);
-        else if (c < 2 * A + 2) cp_async4(dst + AUX_OMEAN + (c - A - 2), a.data.old_mean + g * A + (c - A - 2));
-        else cp_async4(dst + AUX_OSTD + (c - 2 * A - 2), a.data.old_std + g * A + (c - 2 * A - 2));
+    const bool rv = r8s < rows;
+    const int64_t g = rv ? ridx[r8s] : 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = q8s + 8 * i;
+      float v = 0.f;
+      if (rv && c < aux_per) {
+        const float* src;
+        if (!is_actor) src = ((net == 1) ? a.data.target_r : a.data.target_c) + g;
+        else if (c < A) src = a.data.act + g * A + c;
+        else if (c == A) src = a.data.logp + g;
+        else if (c == A + 1) src = a.data.adv + g;
+        else if (c < 2 * A + 2) src = a.data.old_mean + g * A + (c - A - 2);
+        else src = a.data.old_std + g * A + (c - 2 * A - 2);
+        v = __ldg(src);
+      }
+      auxr[i] = v;
+    }
+  };
+  // registers -> the tile buffers
+  auto store_next = [&]() {
+    if (!active) return;
+    if (vec_rows) {
+#pragma unroll
+      for (int it = 0; it < PF_MAX; ++it) {
+        const int r = pf_rc[it] & 0xFF, c = pf_rc[it] >> 8;
+        if (it < pf_n) *reinterpret_cast<float4*>(x + r * ldx + 4 * c) = make_float4(xr[4 * it], xr[4 * it + 1], xr[4 * it + 2], xr[4 * it + 3]);
       }
     } else {
-      const float* tg = (net == 1) ? a.data.target_r : a.data.target_c;
-      for (int r = tid; r < rows; r += UT) cp_async4(aux + r * AUXW + AUX_TGT, tg + a.perm[first + r]);
+#pragma unroll
+      for (int it = 0; it < 4 * PF_MAX; ++it) {
+        const int i = tid + it * UT, r = i / D, c = i - r * D;
+        if (r < SPO_ROWS) x[r * ldx + c] = xr[it];
+      }
     }
-    // rows beyond the valid range must read as zeros (only the final, short step has any)
-    if (rows < SPO_ROWS) {
-      for (int i = tid; i < (SPO_ROWS - rows) * ldx; i += UT) x[rows * ldx + i] = 0.f;
-      for (int i = tid; i < (SPO_ROWS - rows) * AUXW; i += UT) aux[rows * AUXW + i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = q8s + 8 * i;
+      if (c < aux_per) aux[r8s * AUXW + aux_slot(c)] = auxr[i];
     }
+  };
+  // row indices of tile q -> idxbuf slot q & 1 (lands with the cp.async group it is committed in)
+  auto fetch_idx = [&](int64_t q, int64_t step, int sub) {
+    if (!active || q >= n_tiles) return;
+    const int64_t first = step * a.batch + sub * SPO_ROWS;
+    int64_t rs = a.perm_len - first;
+    if (rs > a.batch - sub * SPO_ROWS) rs = a.batch - sub * SPO_ROWS;
+    if (tid < SPO_ROWS && tid < rs) cp_async8(idxbuf + (q & 1) * SPO_ROWS + tid, a.perm + first + tid);
   };
 
 #ifdef SPO_PHASE_TIMERS
   long long phase_t__ = clock64();
 #endif
-  // hidden layer: out[r][j] = tanh(b[j] + sum_k in[r][k] * W[j][k]) on the tensor pipe
+  // hidden layer: out[r][j] = tanh(b[j] + sum_k in[r][k] * W[j][k]) on the tensor pipe.  The 64-wide case
+  // (second layer always; first layer when obs_dim pads to 64) gets compile-time strides: immediate
+  // offsets instead of per-load address arithmetic (2.7 k -> 1.7 k cycles per product)
   auto hidden = [&](const float* in, int ldin, int K, const float* W, int ldw, const float* bias, float* out) {
     float acc[1][2][4];
     spo_mma_zero<1>(acc);
-    spo_warp_mma_3xtf32<1>(acc, in, ldin, 1, W, 1, ldw, mb, nb, K);
+    spo_warp_mma_3xtf32<1>(acc, in, ldin, 1, W, 1, ldw, mb, nb, K);   // all extents are constants after inlining
     PHASE_MARK(11);  // (sub) hidden-layer GEMM only, as seen by warp 0
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
       const int r = mb + g8, j = nb + nt * 8 + 2 * t4;
       const float2 bb = *reinterpret_cast<const float2*>(bias + j);
-      *reinterpret_cast<float2*>(out + r * SPO_LDH + j) = make_float2(spo_tanh(acc[0][nt][0] + bb.x), spo_tanh(acc[0][nt][1] + bb.y));
-      *reinterpret_cast<float2*>(out + (r + 8) * SPO_LDH + j) = make_float2(spo_tanh(acc[0][nt][2] + bb.x), spo_tanh(acc[0][nt][3] + bb.y));
+      *reinterpret_cast<float2*>(out + r * SPO_LDH + j) = make_float2(spo_tanh_fast(acc[0][nt][0] + bb.x), spo_tanh_fast(acc[0][nt][1] + bb.y));
+      *reinterpret_cast<float2*>(out + (r + 8) * SPO_LDH + j) = make_float2(spo_tanh_fast(acc[0][nt][2] + bb.x), spo_tanh_fast(acc[0][nt][3] + bb.y));
     }
+  };
+  // column sums over the 64 rows of a [64][SPO_LDH] tile, all 512 threads: thread (c = tid >> 3, q = tid & 7)
+  // adds rows q, q+8, ... (bank = 4q + c: conflict-free), three shuffles finish the sum
+  auto colsum_into = [&](const float* buf, float* dst) {
+    const int c = tid >> 3, q8 = tid & 7;
+    float s = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < SPO_ROWS / 8; ++rr) s += buf[(rr * 8 + q8) * SPO_LDH + c];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (q8 == 0) dst[c] += s;
   };
 
   __syncthreads();
-  prefetch(0, 0);
-  cp_async_commit();
+  {
+    int64_t st; int sb;
+    fetch_idx(0, 0, 0);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    load_next(0, 0, 0);
+    tile_after(0, 0, 1, st, sb);
+    fetch_idx(1, st, sb);
+    cp_async_commit();
+  }
 
   // gradient accumulators = accumulator fragments of the dW products (persist across the tiles of a step)
   float gW2[FE], gW1[NT1][FE];
@@ -362,12 +445,11 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   double acc_loss = 0.0;        // thread 0: sum over steps of this net's logged loss
   float step_loss = 0.f;        // thread 0: loss numerator of the current step (sum over its tiles)
   float step_aux0 = 0.f, step_aux1 = 0.f;  // FOCOPS: sum(ratio*adv), sum(mask)
-  int64_t step_idx = 0;
 
-  for (int64_t q = 0; q < n_tiles; ++q) {
-    const int cur = static_cast<int>(q & 1);
-    const int64_t step = q / tps;
-    const int sub = static_cast<int>(q - step * tps);
+  int64_t step = 0;   // tile q = (step, sub)
+  int sub = 0;
+  auto next_tile = [&]() { if (++sub == tps) { sub = 0; ++step; } };
+  for (int64_t q = 0; q < n_tiles; ++q, next_tile()) {
     int64_t rs64 = a.perm_len - step * a.batch;
     if (rs64 > a.batch) rs64 = a.batch;
     const int rows_step = static_cast<int>(rs64);
@@ -375,147 +457,216 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     rows = rows < 0 ? 0 : (rows > SPO_ROWS ? SPO_ROWS : rows);
     const bool last_tile = (sub == tps - 1);
     const float inv_b = __fdiv_rn(1.f, static_cast<float>(rows_step));
+    // stage tile q+1 (its indices landed a step ago) and request the indices of tile q+2
+    auto stage_next = [&]() {
+      int64_t st; int sb;
+      tile_after(step, sub, 1, st, sb);
+      load_next(q + 1, st, sb);
+      tile_after(st, sb, 1, st, sb);
+      fetch_idx(q + 2, st, sb);
+      cp_async_commit();
+    };
 
-    cp_async_wait_all();
-    __syncthreads();                       // tile q landed; buffers of tile q-1 are free
-    prefetch(q + 1, cur ^ 1);
-    cp_async_commit();
-
-    const float* x = xbuf[cur];
-    const float* aux = auxbuf[cur];
-    PHASE_MARK(0);   // wait for the gather + issue the next one
+    store_next();      // tile q: registers -> shared memory (every warp left tile q-1 barriers ago)
+    TRACE_MARK(22);
+    __syncthreads();   // tile q in place; Adam's weight writes visible
+    TRACE_MARK(15);
+    if (is_actor && tid >= UT - 32 && tid - (UT - 32) < A) {
+      // row-independent pieces of the Gaussian log-density (log_std changed in the last Adam step)
+      const int j = tid - (UT - 32);
+      const float sd = expf(log_std[j]);
+      lsc[4 * j + 0] = sd;
+      lsc[4 * j + 1] = __fdiv_rn(1.f, __fmul_rn(sd, sd));
+      lsc[4 * j + 2] = logf(sd);
+    }
+    PHASE_MARK(0);   // top of the step: stage-in + barrier
 
     if (active) {
       // ---------------- forward ----------------
-      hidden(x, ldx, K8, w1, ldx, b1, h1);
+      hidden(x, ldx, KX, w1, ldx, b1, h1);
       __syncthreads();
       PHASE_MARK(1);
       hidden(h1, SPO_LDH, SPO_HID, w2, SPO_LDH, b2, h2);
       __syncthreads();
       PHASE_MARK(2);
-      spo_out_fwd(h2, w3, b3, O, y, SPO_MAX_ACT, tid, UT);
+      // output layer: thread (row r = tid >> 3, eighth q8 of k): h2 chunks q8 and q8+8 stay in registers for all
+      // outputs (the tile is read from shared memory once); three shuffles finish each dot product
+      const int r8 = tid >> 3, q8 = tid & 7;
+      {
+        const float4 ha = *reinterpret_cast<const float4*>(h2 + r8 * SPO_LDH + 4 * q8);
+        const float4 hb = *reinterpret_cast<const float4*>(h2 + r8 * SPO_LDH + 32 + 4 * q8);
+        for (int o = 0; o < O; ++o) {
+          const float4 wa = *reinterpret_cast<const float4*>(w3 + o * SPO_HID + 4 * q8);
+          const float4 wb = *reinterpret_cast<const float4*>(w3 + o * SPO_HID + 32 + 4 * q8);
+          float sacc = (fmaf(ha.x, wa.x, ha.y * wa.y) + fmaf(ha.z, wa.z, ha.w * wa.w)) +
+                       (fmaf(hb.x, wb.x, hb.y * wb.y) + fmaf(hb.z, wb.z, hb.w * wb.w));
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+          if (q8 == 0) y[r8 * SPO_MAX_ACT + o] = sacc + b3[o];
+        }
+      }
+      TRACE_MARK(17);
       __syncthreads();
+      if (tid == UT - 32 && last_tile) {
+        // Adam scalars of this step, computed once per CTA by a thread that has no loss row; only this
+        // thread tracks the beta powers (fp64, like torch's Python floats)
+        b1pow *= static_cast<double>(a.hp.beta1);
+        b2pow *= static_cast<double>(a.hp.beta2);
+        adk[0] = static_cast<float>(1.0 - static_cast<double>(a.hp.beta1));
+        adk[1] = a.hp.beta2;
+        adk[2] = static_cast<float>(1.0 - static_cast<double>(a.hp.beta2));
+        // the root and the quotients in fp32 (<= 1 ulp from torch's fp64-then-round)
+        adk[3] = __fdiv_rn(1.f, sqrtf(static_cast<float>(1.0 - b2pow)));
+        adk[4] = a.hp.adam_eps;
+        adk[5] = -__fdiv_rn(lr, static_cast<float>(1.0 - b1pow));
+      }
 
-      // ---------------- loss and d loss / d output, one thread per row ----------------
+      // ---------------- loss and d loss / d output: thread (row r8, action dim j = q8) ----------------
       float part0 = 0.f, part1 = 0.f, part2 = 0.f;
-      if (tid < SPO_ROWS) {
-        const int r = tid;
+      {
+        const int r = r8, j = q8;
         const bool valid = r < rows;
         const float* ax = aux + r * AUXW;
         if (!is_actor) {
-          const float dv = __fsub_rn(y[r * SPO_MAX_ACT], ax[AUX_TGT]);
-          part0 = valid ? __fmul_rn(dv, dv) : 0.f;
-          dy[r * SPO_MAX_ACT] = valid ? __fmul_rn(__fmul_rn(__fmul_rn(2.f, dv), inv_b), vcoef) : 0.f;
+          if (j == 0) {
+            const float dv = __fsub_rn(y[r * SPO_MAX_ACT], ax[AUX_TGT]);
+            part0 = valid ? __fmul_rn(dv, dv) : 0.f;
+            dy[r * SPO_MAX_ACT] = valid ? __fmul_rn(__fmul_rn(__fmul_rn(2.f, dv), inv_b), vcoef) : 0.f;
+          }
         } else {
-          float lp = 0.f, kl = 0.f;
-          float dmu_lp[SPO_MAX_ACT], dls_lp[SPO_MAX_ACT], dmu_kl[SPO_MAX_ACT], dls_kl[SPO_MAX_ACT];
-#pragma unroll
-          for (int j = 0; j < SPO_MAX_ACT; ++j) {
-            dmu_lp[j] = dls_lp[j] = dmu_kl[j] = dls_kl[j] = 0.f;
-            if (j < A) {
-              const float mean = y[r * SPO_MAX_ACT + j];
-              const float std = expf(log_std[j]);
-              const float var = __fmul_rn(std, std);
-              const float diff = __fsub_rn(ax[j], mean);
-              const float d2 = __fmul_rn(diff, diff);
-              const float term = __fsub_rn(__fsub_rn(__fdiv_rn(-d2, __fmul_rn(2.f, var)), logf(std)), kLogSqrt2Pi);
-              lp = (j == 0) ? term : __fadd_rn(lp, term);
-              dmu_lp[j] = __fdiv_rn(diff, var);
-              dls_lp[j] = __fsub_rn(__fdiv_rn(d2, var), 1.f);
-              if (a.kind == SPO_LOSS_FOCOPS) {
-                // KL(new || old), torch _kl_normal_normal(p=new, q=old)
-                // padded rows carry zeros: keep their (discarded) arithmetic finite
-                const float os = valid ? ax[AUX_OSTD + j] : 1.f, om = ax[AUX_OMEAN + j];
-                const float sr = __fdiv_rn(std, os);
-                const float vr = __fmul_rn(sr, sr);
-                const float dm = __fdiv_rn(__fsub_rn(mean, om), os);
-                const float t1 = __fmul_rn(dm, dm);
-                const float klj = __fmul_rn(0.5f, __fsub_rn(__fsub_rn(__fadd_rn(vr, t1), 1.f), logf(vr)));
-                kl = (j == 0) ? klj : __fadd_rn(kl, klj);
-                dmu_kl[j] = __fdiv_rn(dm, os);
-                dls_kl[j] = __fsub_rn(vr, 1.f);
-              }
+          const bool jv = j < A;
+          float term = 0.f, klj = 0.f, dmu_lp = 0.f, dls_lp = 0.f, dmu_kl = 0.f, dls_kl = 0.f;
+          if (jv) {
+            const float mean = y[r * SPO_MAX_ACT + j];
+            const float std = lsc[4 * j], inv_var = lsc[4 * j + 1];
+            const float diff = __fsub_rn(ax[j], mean);
+            const float d2 = __fmul_rn(diff, diff);
+            const float q2 = __fmul_rn(d2, inv_var);           // (a - mu)^2 / var
+            term = __fsub_rn(__fsub_rn(__fmul_rn(-0.5f, q2), lsc[4 * j + 2]), kLogSqrt2Pi);
+            dmu_lp = __fmul_rn(diff, inv_var);
+            dls_lp = __fsub_rn(q2, 1.f);
+            if (a.kind == SPO_LOSS_FOCOPS) {
+              // KL(new || old), torch _kl_normal_normal(p=new, q=old)
+              // padded rows carry zeros: keep their (discarded) arithmetic finite
+              const float os = valid ? ax[AUX_OSTD + j] : 1.f, om = ax[AUX_OMEAN + j];
+              const float ios = __fdiv_rn(1.f, os);
+              const float sr = __fmul_rn(std, ios);
+              const float vr = __fmul_rn(sr, sr);
+              const float dm = __fmul_rn(__fsub_rn(mean, om), ios);
+              const float t1 = __fmul_rn(dm, dm);
+              klj = __fmul_rn(0.5f, __fsub_rn(__fsub_rn(__fadd_rn(vr, t1), 1.f), logf(vr)));
+              dmu_kl = __fmul_rn(dm, ios);
+              dls_kl = __fsub_rn(vr, 1.f);
             }
+          }
+          // sums over the action dims: the 8 lanes of a row (lanes j >= A hold zeros)
+          float lp = term, kl = klj;
+          lp += __shfl_xor_sync(0xffffffffu, lp, 1);
+          lp += __shfl_xor_sync(0xffffffffu, lp, 2);
+          lp += __shfl_xor_sync(0xffffffffu, lp, 4);
+          if (a.kind == SPO_LOSS_FOCOPS) {
+            kl += __shfl_xor_sync(0xffffffffu, kl, 1);
+            kl += __shfl_xor_sync(0xffffffffu, kl, 2);
+            kl += __shfl_xor_sync(0xffffffffu, kl, 4);
           }
           const float ratio = expf(__fsub_rn(lp, ax[AUX_LOGP]));
           const float adv = ax[AUX_ADV];
           if (a.kind == SPO_LOSS_PPO_CLIP) {
             const float s1 = __fmul_rn(ratio, adv);
             const float s2 = __fmul_rn(fminf(fmaxf(ratio, a.hp.clip_lo), a.hp.clip_hi), adv);
-            part0 = valid ? -fminf(s1, s2) : 0.f;
+            if (j == 0) part0 = valid ? -fminf(s1, s2) : 0.f;
             // d(-mean(min))/d logp = -(1/B) * adv * ratio where the unclipped branch is active
             const float gl = (valid && s1 <= s2) ? -__fmul_rn(__fmul_rn(adv, ratio), inv_b) : 0.f;
-#pragma unroll
-            for (int j = 0; j < SPO_MAX_ACT; ++j) {
-              dy[r * SPO_MAX_ACT + j] = __fmul_rn(gl, dmu_lp[j]);
-              dls[r * SPO_MAX_ACT + j] = __fmul_rn(gl, dls_lp[j]);
+            if (jv) {
+              dy[r * SPO_MAX_ACT + j] = __fmul_rn(gl, dmu_lp);
+              dls[r * SPO_MAX_ACT + j] = __fmul_rn(gl, dls_lp);
             }
           } else {
             // FOCOPS needs mean(mask) over the minibatch before gradients can be formed:
             // stash per-row pieces, finish after the block reduction below.
             const float mask = (valid && kl <= a.hp.focops_kl) ? 1.f : 0.f;
-            part0 = valid ? __fmul_rn(kl, mask) : 0.f;
-            part1 = valid ? __fmul_rn(ratio, adv) : 0.f;
-            part2 = mask;
-#pragma unroll
-            for (int j = 0; j < SPO_MAX_ACT; ++j) {
-              // first term: (1/B) * mask * d kl ; second term scaled later by mean(mask)
-              dy[r * SPO_MAX_ACT + j] = __fmul_rn(__fmul_rn(mask, inv_b), dmu_kl[j]);
-              dls[r * SPO_MAX_ACT + j] = __fmul_rn(__fmul_rn(mask, inv_b), dls_kl[j]);
-              y[r * SPO_MAX_ACT + j] = valid ? __fmul_rn(__fmul_rn(__fmul_rn(adv, ratio), inv_b), dmu_lp[j]) : 0.f;
+            if (j == 0) {
+              part0 = valid ? __fmul_rn(kl, mask) : 0.f;
+              part1 = valid ? __fmul_rn(ratio, adv) : 0.f;
+              part2 = mask;
             }
-            // keep d logp / d log_std pieces in the (now free) aux row of the *current* buffer
-            float* axw = const_cast<float*>(ax);
-#pragma unroll
-            for (int j = 0; j < SPO_MAX_ACT; ++j)
-              if (j < A) axw[AUX_OMEAN + j] = valid ? __fmul_rn(__fmul_rn(__fmul_rn(adv, ratio), inv_b), dls_lp[j]) : 0.f;
+            if (jv) {
+              // first term: (1/B) * mask * d kl ; second term scaled later by mean(mask)
+              const float gl = valid ? __fmul_rn(__fmul_rn(adv, ratio), inv_b) : 0.f;
+              dy[r * SPO_MAX_ACT + j] = __fmul_rn(__fmul_rn(mask, inv_b), dmu_kl);
+              dls[r * SPO_MAX_ACT + j] = __fmul_rn(__fmul_rn(mask, inv_b), dls_kl);
+              y[r * SPO_MAX_ACT + j] = __fmul_rn(gl, dmu_lp);
+              // d logp / d log_std piece: into the (now free) old-mean slot of the current aux row
+              const_cast<float*>(ax)[AUX_OMEAN + j] = __fmul_rn(gl, dls_lp);
+            }
           }
         }
-        part0 = spo_warp_sum(part0); part1 = spo_warp_sum(part1); part2 = spo_warp_sum(part2);
+        part0 = spo_warp_sum(part0);
+        if (is_actor && a.kind == SPO_LOSS_FOCOPS) { part1 = spo_warp_sum(part1); part2 = spo_warp_sum(part2); }
         if (lane == 0) { red[wid * 4 + 0] = part0; red[wid * 4 + 1] = part1; red[wid * 4 + 2] = part2; }
       }
+      TRACE_MARK(18);
       __syncthreads();
       if (tid == 0) {
-        step_loss += red[0] + red[4];
-        step_aux0 += red[1] + red[5];
-        step_aux1 += red[2] + red[6];
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < UT / 32; ++w) { l0 += red[w * 4]; l1 += red[w * 4 + 1]; l2 += red[w * 4 + 2]; }
+        step_loss += l0;
+        step_aux0 += l1;
+        step_aux1 += l2;
       }
       if (is_actor && a.kind == SPO_LOSS_FOCOPS) {
         // This formulation needs the whole minibatch in one tile (batch <= 64): mean(mask)
         // and the per-row pieces are combined here.  (focops.py uses batch 64.)
-        const float mbar = __fmul_rn(__fadd_rn(red[2], red[6]), inv_b);
-        const float c2 = -__fmul_rn(__fdiv_rn(1.f, a.hp.focops_lam), mbar);
-        if (tid < SPO_ROWS) {
-          const int r = tid;
-          float* axw = const_cast<float*>(aux) + r * AUXW;
+        float msum = 0.f;
 #pragma unroll
-          for (int j = 0; j < SPO_MAX_ACT; ++j)
-            if (j < A) {
-              dy[r * SPO_MAX_ACT + j] = __fadd_rn(dy[r * SPO_MAX_ACT + j], __fmul_rn(c2, y[r * SPO_MAX_ACT + j]));
-              dls[r * SPO_MAX_ACT + j] = __fadd_rn(dls[r * SPO_MAX_ACT + j], __fmul_rn(c2, axw[AUX_OMEAN + j]));
-            }
+        for (int w = 0; w < UT / 32; ++w) msum += red[w * 4 + 2];
+        const float mbar = __fmul_rn(msum, inv_b);
+        const float c2 = -__fmul_rn(__fdiv_rn(1.f, a.hp.focops_lam), mbar);
+        if (q8 < A) {
+          const float* ax = aux + r8 * AUXW;
+          dy[r8 * SPO_MAX_ACT + q8] = __fadd_rn(dy[r8 * SPO_MAX_ACT + q8], __fmul_rn(c2, y[r8 * SPO_MAX_ACT + q8]));
+          dls[r8 * SPO_MAX_ACT + q8] = __fadd_rn(dls[r8 * SPO_MAX_ACT + q8], __fmul_rn(c2, ax[AUX_OMEAN + q8]));
         }
         __syncthreads();
       }
 
       PHASE_MARK(3);   // output layer + loss rows
       // ---------------- backward ----------------
-      // (a) small grads of the output layer: dW3[o][k], db3[o], dlog_std[j]
-      for (int i = tid; i < O * SPO_HID + O + sm.A_ls; i += UT) {
-        float s = 0.f;
-        if (i < O * SPO_HID) {
-          const int o = i >> 6, k = i & 63;
-#pragma unroll 8
-          for (int r = 0; r < SPO_ROWS; ++r) s = fmaf(dy[r * SPO_MAX_ACT + o], h2[r * SPO_LDH + k], s);
-        } else if (i < O * SPO_HID + O) {
-          const int o = i - O * SPO_HID;
-          for (int r = 0; r < SPO_ROWS; ++r) s += dy[r * SPO_MAX_ACT + o];
-        } else {
-          const int j = i - O * SPO_HID - O;
-          for (int r = 0; r < SPO_ROWS; ++r) s += dls[r * SPO_MAX_ACT + j];
+      // (a) small grads of the output layer: dW3[o][k] = sum_r dy[r][o] h2[r][k], thread (k = tid >> 3, q8): rows
+      //     q8, q8+8, ... with the h2 column in registers for all outputs; three shuffles finish each sum.
+      //     db3[o] / dlog_std[j] (column sums of dy / dls): the first four warps, same row split.
+      {
+        const int k = r8;
+        float hv[SPO_ROWS / 8];
+#pragma unroll
+        for (int rr = 0; rr < SPO_ROWS / 8; ++rr) hv[rr] = h2[(rr * 8 + q8) * SPO_LDH + k];
+        for (int o = 0; o < O; ++o) {
+          float sa = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < SPO_ROWS / 8; ++rr) sa = fmaf(dy[(rr * 8 + q8) * SPO_MAX_ACT + o], hv[rr], sa);
+          sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+          sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+          sa += __shfl_xor_sync(0xffffffffu, sa, 4);
+          if (q8 == 0) gsmall[2 * SPO_HID + o * SPO_HID + k] += sa;
         }
-        gsmall[2 * SPO_HID + i] += s;
+        if (tid < 128) {
+          const int c = tid >> 3, col = c & 7;          // c < 8: dy column (db3), else dls column (dlog_std)
+          const bool need = (c < 8) ? (col < O) : (col < sm.A_ls);
+          const float* src = (c < 8) ? dy : dls;
+          float sa = 0.f;
+          if (need) {
+#pragma unroll
+            for (int rr = 0; rr < SPO_ROWS / 8; ++rr) sa += src[(rr * 8 + q8) * SPO_MAX_ACT + col];
+          }
+          sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+          sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+          sa += __shfl_xor_sync(0xffffffffu, sa, 4);
+          if (need && q8 == 0) gsmall[2 * SPO_HID + O * SPO_HID + ((c < 8) ? col : O + col)] += sa;
+        }
       }
+      TRACE_MARK(19);
       // (b) dz2[r][k] = (sum_o dy[r][o] * w3[o][k]) * (1 - h2[r][k]^2)
       {
         const int r0 = (tid >> 4) * 2, kk = (tid & 15) * 4;
@@ -538,12 +689,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       // (c) dW2[j][k] += sum_r dz2[r][j] * h1[r][k];  db2[j] += sum_r dz2[r][j]
       spo_warp_mma_3xtf32<1>(reinterpret_cast<float (&)[1][2][4]>(gW2), dz2, 1, SPO_LDH, h1, SPO_LDH, 1, mb, nb, SPO_ROWS);
       PHASE_MARK(12);  // (sub) dW2 GEMM
-      if (tid < SPO_HID) {
-        float s = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < SPO_ROWS; ++r) s += dz2[r * SPO_LDH + tid];
-        gsmall[SPO_HID + tid] += s;
-      }
+      colsum_into(dz2, gsmall + SPO_HID);
       PHASE_MARK(13);  // (sub) db2 column sums
       // (d) dz1[r][k] = (sum_j dz2[r][j] * W2[j][k]) * (1 - h1[r][k]^2)   -> overwrites h2
       {
@@ -567,18 +713,17 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       // (e) dW1[j][k] += sum_r dz1[r][j] * x[r][k];  db1[j] += sum_r dz1[r][j]
 #pragma unroll
       for (int i = 0; i < NT1; ++i)
-        if (i * 64 + nb < K8)
-          spo_warp_mma_3xtf32<1>(reinterpret_cast<float (&)[1][2][4]>(gW1[i]), dz1, 1, SPO_LDH, x, ldx, 1, mb, i * 64 + nb, SPO_ROWS);
-      if (tid < SPO_HID) {
-        float s = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < SPO_ROWS; ++r) s += dz1[r * SPO_LDH + tid];
-        gsmall[tid] += s;
-      }
+        spo_warp_mma_3xtf32<1>(reinterpret_cast<float (&)[1][2][4]>(gW1[i]), dz1, 1, SPO_LDH, x, ldx, 1, mb, i * 64 + nb, SPO_ROWS);
+      colsum_into(dz1, gsmall);
     }  // active
 
     PHASE_MARK(6);   // dW1
-    if (!last_tile) continue;   // next tile of the same step accumulates into the same gradients
+    cp_async_wait_all();   // indices of tile q+1 (requested a step ago); the barrier below publishes them
+    if (!last_tile) {      // next tile of the same step accumulates into the same gradients
+      __syncthreads();
+      stage_next();
+      continue;
+    }
 
     // ---------------- cross-GPU gradient sum (data-parallel ranks), in rank order ----------------
     // Push protocol: every rank stores its gradient straight into each peer's staging slot
@@ -591,7 +736,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       constexpr int Q = FE / 4;   // float4s per tile per thread
       const int world = a.comm.world, me = a.comm.rank;
       const unsigned seq = static_cast<unsigned>(a.comm.seq_base + static_cast<unsigned long long>(step_idx) + 1ull);
-      const size_t slot = static_cast<size_t>(UT) * FE * (1 + NT1) + spn;
+      const size_t slot = static_cast<size_t>(UT) * FE * (1 + NT1) + spo_pad4(2 * SPO_HID + A * SPO_HID + 2 * A);
       const size_t par_off = static_cast<size_t>(seq & 1u) * world * 3 * slot;
       for (int r = 0; r < world; ++r) {
         if (r == me) continue;
@@ -675,6 +820,20 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     float ss = 0.f, th2 = 0.f;
     if (active) {
       __syncthreads();  // gsmall complete
+      if (is_actor) {   // no regulariser, no logged L2 term: nothing to read back
+#pragma unroll
+        for (int e = 0; e < FE; ++e) {
+          ss = fmaf(gW2[e], gW2[e], ss);
+#pragma unroll
+          for (int i = 0; i < NT1; ++i) {
+            int j, k;
+            frag_rc(tid, e, 64 * i, j, k);
+            if (k >= D) gW1[i][e] = 0.f;
+            ss = fmaf(gW1[i][e], gW1[i][e], ss);
+          }
+        }
+        for (int i = tid; i < SP; i += UT) ss = fmaf(gsmall[i], gsmall[i], ss);
+      } else {
 #pragma unroll
       for (int e = 0; e < FE; ++e) {
         int j, k;
@@ -710,17 +869,24 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         ss = fmaf(g, g, ss);
         th2 = fmaf(th, th, th2);
       }
+      }
       ss = spo_warp_sum(ss);
-      th2 = spo_warp_sum(th2);
+      if (!is_actor) th2 = spo_warp_sum(th2);
       if (lane == 0) { red[16 + wid] = ss; red[32 + wid] = th2; }
+      TRACE_MARK(20);
       __syncthreads();
     }
     const int par = static_cast<int>(step_idx & 1);
-    if (tid == 0) {
-      float s = extra_sumsq, t2 = 0.f;
-      if (active) {
-        for (int i = 0; i < UT / 32; ++i) { s += red[16 + i]; t2 += red[32 + i]; }
+    if (wid == 0) {
+      float s = 0.f, t2 = 0.f;
+      if (active && lane < UT / 32) { s = red[16 + lane]; t2 = red[32 + lane]; }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
       }
+      s += extra_sumsq;
+      if (tid == 0) {
       xchg[par] = idle ? 0.f : s;
       // logged loss of this step (ppo_lag.py:330-336): critics include the L2 term
       if (active) {
@@ -732,9 +898,17 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         acc_loss += static_cast<double>(L);
       }
       step_loss = 0.f; step_aux0 = 0.f; step_aux1 = 0.f;
+      }
     }
     PHASE_MARK(8);   // regulariser + sum of squares + block reduction
-    cluster.sync();
+    // cluster barrier, split: the rows of the next tile are requested while the arrivals propagate
+    // (only thread 0 has something to publish -- xchg; a release arrive makes all 512 threads execute a
+    //  gpu-scope MEMBAR, 1.1 k cycles per step in the r01 source profile)
+    if (tid == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    stage_next();
+    TRACE_MARK(16);
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     PHASE_MARK(9);   // cluster barrier (includes waiting for the slowest net)
     float total = 0.f;
     {
@@ -744,38 +918,38 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     const float clip = fminf(__fdiv_rn(a.hp.max_grad_norm, __fadd_rn(sqrtf(total), 1e-6f)), 1.f);
 
     if (active) {
-      b1pow *= static_cast<double>(a.hp.beta1);
-      b2pow *= static_cast<double>(a.hp.beta2);
       AdamK k;
-      k.w1 = static_cast<float>(1.0 - static_cast<double>(a.hp.beta1));
-      k.b2 = a.hp.beta2;
-      k.w2 = static_cast<float>(1.0 - static_cast<double>(a.hp.beta2));
-      k.bc2s = static_cast<float>(sqrt(1.0 - b2pow));
-      k.eps = a.hp.adam_eps;
-      k.ss = static_cast<float>(-(static_cast<double>(lr) / (1.0 - b1pow)));
+      k.w1 = adk[0]; k.b2 = adk[1]; k.w2 = adk[2]; k.ibc2s = adk[3]; k.eps = adk[4]; k.ss = adk[5];
 #pragma unroll
-      for (int e = 0; e < FE; ++e) {
+      for (int e = 0; e < FE; e += 2) {   // elements e, e+1 are neighbours in a weight row
         int j, kc;
         frag_rc(tid, e, 0, j, kc);
-        float* pw = w2 + j * SPO_LDH + kc;
-        *pw = adam_update(*pw, __fmul_rn(gW2[e], clip), mW2[e], vW2[e], k);
-        gW2[e] = 0.f;
-        if (kc < D) {
+        float2* pw = reinterpret_cast<float2*>(w2 + j * SPO_LDH + kc);
+        float2 wv = *pw;
+        wv.x = adam_update(wv.x, __fmul_rn(gW2[e], clip), mW2[e], vW2[e], k);
+        wv.y = adam_update(wv.y, __fmul_rn(gW2[e + 1], clip), mW2[e + 1], vW2[e + 1], k);
+        *pw = wv;
+        gW2[e] = 0.f; gW2[e + 1] = 0.f;
+        if (kc < D) {   // D and kc even or the pair straddles D: handle the second element on its own
           float* p1 = w1 + j * ldx + kc;
-          *p1 = adam_update(*p1, __fmul_rn(gW1[0][e], clip), mW1[e], vW1[e], k);
+          p1[0] = adam_update(p1[0], __fmul_rn(gW1[0][e], clip), mW1[e], vW1[e], k);
+          if (kc + 1 < D) p1[1] = adam_update(p1[1], __fmul_rn(gW1[0][e + 1], clip), mW1[e + 1], vW1[e + 1], k);
         }
-        gW1[0][e] = 0.f;
+        gW1[0][e] = 0.f; gW1[0][e + 1] = 0.f;
         if (NT1 > 1) {
-          if (kc + 64 < D) {
-            float* p1 = w1 + j * ldx + kc + 64;
-            float m = mv1b[e * UT + tid], v = mv1b[(FE + e) * UT + tid];
-            *p1 = adam_update(*p1, __fmul_rn(gW1[NT1 - 1][e], clip), m, v, k);
-            mv1b[e * UT + tid] = m;
-            mv1b[(FE + e) * UT + tid] = v;
-          }
-          gW1[NT1 - 1][e] = 0.f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (kc + h + 64 < D) {
+              float* p1 = w1 + j * ldx + kc + h + 64;
+              float m = mv1b[(e + h) * UT + tid], v = mv1b[(FE + e + h) * UT + tid];
+              *p1 = adam_update(*p1, __fmul_rn(gW1[NT1 - 1][e + h], clip), m, v, k);
+              mv1b[(e + h) * UT + tid] = m;
+              mv1b[(FE + e + h) * UT + tid] = v;
+            }
+          gW1[NT1 - 1][e] = 0.f; gW1[NT1 - 1][e + 1] = 0.f;
         }
       }
+      TRACE_MARK(21);
       for (int i = tid; i < SP; i += UT) {
         float* th;
         if (i < SPO_HID) th = b1 + i;
@@ -838,22 +1012,23 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       atomicAdd(&ctrl->loss_sum[slot], acc_loss);
     }
   }
+#ifdef SPO_PHASE_TIMERS
+  if (tid < 16) atomicAdd(&g_phase_cycles[rank & 3][tid], sm_phase__[tid]);
+#endif
   if (rank == 1 && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->steps), static_cast<unsigned long long>(n_steps));
   cluster.sync();  // no CTA may exit while a peer can still read its shared memory
 }
 
-size_t update_smem_bytes(int D, int A, int nt1) {
-  const int O = A > 1 ? A : 1;
-  const int ldx = upd_ldx(D);
-  size_t f = SPO_HID * ldx + SPO_HID + SPO_HID * SPO_LDH + SPO_HID + spo_pad4(O * SPO_HID) + spo_pad4(O) + 8 +
-             3 * spo_pad4(2 * SPO_HID + A * SPO_HID + 2 * A) + 2 * SPO_ROWS * ldx + 2 * SPO_ROWS * AUXW + 3 * SPO_ROWS * SPO_LDH +
-             3 * SPO_ROWS * SPO_MAX_ACT + 64 + 4 + (nt1 > 1 ? 2 * FE * UT : 0);
+size_t update_smem_bytes(int nt1) {
+  const int ldx = upd_ldx(nt1);
+  size_t f = 4 * SPO_ROWS + 4 * SPO_MAX_ACT + 8 + SPO_HID * ldx + SPO_HID + SPO_HID * SPO_LDH + SPO_HID + SPO_MAX_ACT * SPO_HID + SPO_MAX_ACT + 8 +
+             3 * SPN + SPO_ROWS * ldx + SPO_ROWS * AUXW + 3 * SPO_ROWS * SPO_LDH + 3 * SPO_ROWS * SPO_MAX_ACT + 64 + 4 + (nt1 > 1 ? 2 * FE * UT : 0);
   return f * sizeof(float);
 }
 
 template <int NT1>
 int launch_update(const UpdArgs& a, cudaStream_t stream) {
-  const size_t smem = update_smem_bytes(a.D, a.A, NT1);
+  const size_t smem = update_smem_bytes(NT1);
   SPO_REQUIRE(smem <= 227 * 1024, SPO_ERR_UNSUPPORTED, "spo_pg_update: obs_dim=%d needs %zu B of shared memory (> 227 KB)", a.D, smem);
   static int cluster_size = 0;   // 4 preferred (barrier measured faster than for 3, profiles/r01_ubench.txt); 3 as fallback
   SPO_CUDA_TRY(cudaFuncSetAttribute(spo_update_kernel<NT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -895,6 +1070,10 @@ extern "C" int spo_debug_phase_cycles(unsigned long long* out64, int reset) {
     unsigned long long z[64] = {0};
     SPO_CUDA_TRY(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)));
   }
+  return SPO_OK;
+}
+extern "C" int spo_debug_trace(long long* out_4x16x24) {
+  SPO_CUDA_TRY(cudaMemcpyFromSymbol(out_4x16x24, g_trace, sizeof(long long) * 4 * 16 * 24));
   return SPO_OK;
 }
 #endif

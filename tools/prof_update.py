@@ -24,3 +24,13 @@ for _ in range(3):
     res = upd.run(data, perms=[perm])
 torch.cuda.synchronize()
 print(res)
+if os.environ.get("TIME"):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e9
+    for _ in range(5):
+        e0.record()
+        upd.run(data, perms=[perm])
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    print(f"update kernel: {best * 1e3 / steps:.2f} us per minibatch step ({steps} steps, best of 5)")
