@@ -47,7 +47,7 @@ __device__ __forceinline__ void spo_warp_mma_3xtf32(float (&acc)[MT][2][4], cons
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const float* a_ptr = A + (m_base + g) * a_sm + t * a_sk;
   const float* b_ptr = B + t * b_sk + (n_base + g) * b_sn;
-#pragma unroll 2
+#pragma unroll 4
   for (int k0 = 0; k0 < K; k0 += 8) {
     uint32_t ah[MT][4], al[MT][4], bh[2][2], bl[2][2];
 #pragma unroll
@@ -64,13 +64,16 @@ __device__ __forceinline__ void spo_warp_mma_3xtf32(float (&acc)[MT][2][4], cons
       spo_split_tf32(p[0], bh[nt][0], bl[nt][0]);
       spo_split_tf32(p[4 * b_sk], bh[nt][1], bl[nt][1]);
     }
+    // small terms first; the two column tiles alternate so that an mma never directly follows the one
+    // it depends on
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        spo_mma_tf32(acc[mt][nt], al[mt], bh[nt]);
-        spo_mma_tf32(acc[mt][nt], ah[mt], bl[nt]);
-        spo_mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
-      }
+    for (int mt = 0; mt < MT; ++mt) {
+      spo_mma_tf32(acc[mt][0], al[mt], bh[0]);
+      spo_mma_tf32(acc[mt][1], al[mt], bh[1]);
+      spo_mma_tf32(acc[mt][0], ah[mt], bl[0]);
+      spo_mma_tf32(acc[mt][1], ah[mt], bl[1]);
+      spo_mma_tf32(acc[mt][0], ah[mt], bh[0]);
+      spo_mma_tf32(acc[mt][1], ah[mt], bh[1]);
+    }
   }
 }

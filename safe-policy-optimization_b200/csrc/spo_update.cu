@@ -13,15 +13,18 @@
 //
 // Mapping: a thread-block cluster of 4 CTAs (the 4th only joins the barriers: a cluster of
 // 4 synchronises faster than one of 3 on B200), one net per CTA -- actor / reward critic / cost
-// critic.  Each CTA keeps its net's weights (both orientations), the Adam moments and
-// all activations of the 64-row tile in shared memory / registers for the whole pass;
-// the only traffic per step is the gather of the minibatch rows (cp.async, prefetched one
-// tile ahead) and one float per CTA exchanged through distributed shared memory for the
-// joint gradient norm.  Weights and moments touch HBM once per launch.
+// critic, 512 threads each.  A CTA keeps its net's weights, the Adam moments and all
+// activations of the 64-row tile in shared memory / registers for the whole pass; per step it
+// reads the 64 minibatch rows (staged in registers a step ahead, their indices two steps
+// ahead) and exchanges one float through distributed shared memory for the joint gradient
+// norm.  Weights and moments touch HBM once per launch.
 //
 // The chain of steps is strictly sequential (each step needs the weights of the previous
 // one), so this kernel is latency-bound by construction: what is optimised is
-// microseconds per step, not bandwidth.
+// microseconds per step, not bandwidth.  Every phase between two barriers is spread over all
+// 16 warps (loss rows as (row, action dim), reductions as 8-way row splits + shuffles):
+// with 4 warps per scheduler an instruction executed by every thread costs 4 issue cycles,
+// and a phase run by one warp stalls the other 15 (profiles/r01_update_phase_cycles.md).
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include "spo_common.cuh"
@@ -90,12 +93,6 @@ __device__ __forceinline__ float ld_relaxed_sys_f(const float* p) {
   return v;
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
-}
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
 }
@@ -304,6 +301,20 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     return AUX_OSTD + (c - 2 * A - 2);
   };
 
+  // global source of side-data column c (row g at src + g * (A or 1))
+  auto aux_by_row = [&](int c) { return is_actor && (c < A || c >= A + 2); };
+  auto aux_src = [&](int c) -> const float* {
+    if (!is_actor) return (net == 1) ? a.data.target_r : a.data.target_c;
+    if (c < A) return a.data.act + c;
+    if (c == A) return a.data.logp;
+    if (c == A + 1) return a.data.adv;
+    if (c < 2 * A + 2) return a.data.old_mean + (c - A - 2);
+    return a.data.old_std + (c - 2 * A - 2);
+  };
+  const float* aux_src0 = aux_src(q8s < aux_per ? q8s : 0);   // column q8s: decoded once
+  const int aux_mul0 = aux_by_row(q8s) ? A : 1;
+  const int aux_slot0 = aux_slot(q8s < aux_per ? q8s : 0);
+
   int64_t step_idx = 0;
 #ifdef SPO_PHASE_TIMERS
   __shared__ unsigned long long sm_phase__[16];
@@ -340,21 +351,15 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     }
     const bool rv = r8s < rows;
     const int64_t g = rv ? ridx[r8s] : 0;
+    auxr[0] = (rv && q8s < aux_per) ? __ldg(aux_src0 + g * aux_mul0) : 0.f;
+    if (aux_per > 8) {   // wide action spaces only
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = q8s + 8 * i;
-      float v = 0.f;
-      if (rv && c < aux_per) {
-        const float* src;
-        if (!is_actor) src = ((net == 1) ? a.data.target_r : a.data.target_c) + g;
-        else if (c < A) src = a.data.act + g * A + c;
-        else if (c == A) src = a.data.logp + g;
-        else if (c == A + 1) src = a.data.adv + g;
-        else if (c < 2 * A + 2) src = a.data.old_mean + g * A + (c - A - 2);
-        else src = a.data.old_std + g * A + (c - 2 * A - 2);
-        v = __ldg(src);
+      for (int i = 1; i < 4; ++i) {
+        const int c = q8s + 8 * i;
+        float v = 0.f;
+        if (rv && c < aux_per) v = __ldg(aux_src(c) + g * (aux_by_row(c) ? A : 1));
+        auxr[i] = v;
       }
-      auxr[i] = v;
     }
   };
   // registers -> the tile buffers
@@ -373,10 +378,13 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         if (r < SPO_ROWS) x[r * ldx + c] = xr[it];
       }
     }
+    if (q8s < aux_per) aux[r8s * AUXW + aux_slot0] = auxr[0];
+    if (aux_per > 8) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = q8s + 8 * i;
-      if (c < aux_per) aux[r8s * AUXW + aux_slot(c)] = auxr[i];
+      for (int i = 1; i < 4; ++i) {
+        const int c = q8s + 8 * i;
+        if (c < aux_per) aux[r8s * AUXW + aux_slot(c)] = auxr[i];
+      }
     }
   };
   // row indices of tile q -> idxbuf slot q & 1 (lands with the cp.async group it is committed in)
@@ -821,16 +829,12 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     if (active) {
       __syncthreads();  // gsmall complete
       if (is_actor) {   // no regulariser, no logged L2 term: nothing to read back
+        // (dW1 columns >= obs_dim are exact zeros: the padded observation columns are)
 #pragma unroll
         for (int e = 0; e < FE; ++e) {
           ss = fmaf(gW2[e], gW2[e], ss);
 #pragma unroll
-          for (int i = 0; i < NT1; ++i) {
-            int j, k;
-            frag_rc(tid, e, 64 * i, j, k);
-            if (k >= D) gW1[i][e] = 0.f;
-            ss = fmaf(gW1[i][e], gW1[i][e], ss);
-          }
+          for (int i = 0; i < NT1; ++i) ss = fmaf(gW1[i][e], gW1[i][e], ss);
         }
         for (int i = tid; i < SP; i += UT) ss = fmaf(gsmall[i], gsmall[i], ss);
       } else {
@@ -915,7 +919,9 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       const unsigned nblk = cluster.num_blocks();
       for (unsigned b = 0; b < nblk; ++b) total += *cluster.map_shared_rank(xchg + par, b);
     }
-    const float clip = fminf(__fdiv_rn(a.hp.max_grad_norm, __fadd_rn(sqrtf(total), 1e-6f)), 1.f);
+    // clip coefficient max_norm / (norm + 1e-6), capped at 1 (SFU sqrt and division: <= 2 ulp, and exactly 1 whenever
+    // the norm is below the limit)
+    const float clip = fminf(__fdividef(a.hp.max_grad_norm, __fadd_rn(sqrt_approx(total), 1e-6f)), 1.f);
 
     if (active) {
       AdamK k;
