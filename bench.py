@@ -345,7 +345,9 @@ def run_spo(args):
         "gpu_launches": val["launches"],
         "roofline": {"kernel": "spo_update_kernel (one PPO-Lag pass = 16000 serial minibatch steps)", "bound": "hbm",
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": 387.2e6, "peak_source": how,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture in profiles/r01_update_ncu.md:
+                     # 16.87 MB for a 300-step launch = 56.2 KB per minibatch step, scaled to this launch's step count
+                     "traffic": 16.8704e6 / 300 * kern_steps, "peak_source": how,
                      "note": "serial-latency-bound chain of 64-row Adam steps (SURVEY H3): us_per_minibatch_step is the figure of merit"},
     }
     if e2e is not None:
@@ -363,11 +365,42 @@ def run_spo(args):
 # reference arm: the reference's CPU implementation of the path (oracle port), all host threads
 # ---------------------------------------------------------------------------------------
 
+def pick_reference_threads():
+    """The thread count the reference's path actually profits from on this host.  The reference pins
+    torch.set_num_threads(4) (ppo_lag.py:73); its 64-row minibatch steps get slower, not faster, with more
+    intra-op threads (128 threads on the GPU box: 1015 ms per minibatch step vs 2.3 ms with 4,
+    profiles/r01_bench_reference_128threads.json).  A short probe of the dominant op picks the fastest of
+    1..16 threads, so the arm is timed at the reference's best, not at an oversubscribed setting."""
+    from oracle import spo_oracle as O
+    torch.manual_seed(0)
+    pol = O.OraclePolicy(D_OBS, D_ACT)
+    opt = O.OracleOptim(pol)
+    b = {"obs": torch.randn(64, D_OBS), "act": torch.randn(64, D_ACT), "log_prob": torch.full((64,), -2.5),
+         "target_value_r": torch.randn(64), "target_value_c": torch.randn(64), "adv": torch.randn(64)}
+    best, best_t = None, 1e9
+    ncpu = os.cpu_count() or 4
+    for t in (1, 2, 4, 8, 16):
+        if t > ncpu:
+            break
+        torch.set_num_threads(t)
+        for _ in range(5):
+            O.minibatch_step(pol, opt, b, "ppo")
+        t0 = time.time()
+        n = 0
+        while time.time() - t0 < 0.5:
+            O.minibatch_step(pol, opt, b, "ppo")
+            n += 1
+        dt = (time.time() - t0) / n
+        if dt < best_t:
+            best, best_t = t, dt
+    return best
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 4
+    threads = pick_reference_threads()
     K, W = args.steps, max(args.warmup, 0)
     per = max(args.cpu_seconds / max(K + W, 1), 4.0)
     vals = []
