@@ -353,6 +353,63 @@ def test_full_batch_kl_vs_reference(golden):
     from safepo.single_agent._engine import PolicyGradientUpdate
 
 
+@pytest.mark.parametrize("kind,D,A,batch", [
+    ("ppo", 17, 6, 64),       # obs_dim % 4 != 0: scalar stage-in path; 6 action dims
+    ("focops", 27, 8, 64),    # widest action space: 26 side-data columns per row
+    ("ppo", 104, 3, 64),      # obs_dim > 64: two W1 column blocks (moments of the second in shared memory)
+    ("ppo", 60, 2, 128),      # two 64-row tiles per minibatch step
+    ("ppo", 60, 2, 100),      # ragged second tile in every step
+    ("focops", 60, 2, 48),    # minibatch smaller than the tile
+    ("ppo", 1, 1, 64),        # smallest supported shapes
+])
+def test_update_other_shapes_vs_oracle(kind, D, A, batch):
+    """One pass of minibatch steps at shapes the golden fixtures do not cover, against the oracle's
+    loop (oracle/spo_oracle.py minibatch_step, pinned to the reference by tests/test_oracle_golden.py):
+    pass-mean losses and the weights after the pass.  The last step of the pass is short (13 rows)."""
+    from safepo import _lib as L
+    from safepo.common.model import ActorVCritic
+    from safepo.single_agent._engine import PolicyGradientUpdate
+    dev = _cuda()
+    torch.manual_seed(1000 * D + 10 * A + batch)
+    pol = ActorVCritic(D, A, [64, 64]).to(dev)
+    state = policy_state(pol)
+    opol = oracle_policy(state, D, A)
+    S = 5 * batch + 13
+    g = torch.Generator().manual_seed(S)
+    obs = torch.randn(S, D, generator=g)
+    with torch.no_grad():
+        mean, std = O.actor_mean_std(opol, obs)
+        act = mean + std * torch.randn(S, A, generator=g)
+        logp = O.normal_log_prob(act, mean, std).sum(-1) + 0.05 * torch.randn(S, generator=g)
+        old_mean, old_std = mean.clone(), std.expand_as(mean).clone()
+    data_cpu = {"obs": obs, "act": act, "log_prob": logp, "target_value_r": torch.randn(S, generator=g),
+                "target_value_c": torch.randn(S, generator=g).abs(), "adv": torch.randn(S, generator=g)}
+    perm = torch.randperm(S, generator=g)
+    cfg = dict(hidden_sizes=[64, 64], gamma=0.99, target_kl=1e9, batch_size=batch, learning_iters=1, max_grad_norm=40.0)
+    upd = PolicyGradientUpdate(pol, cfg, L.LOSS_PPO_CLIP if kind == "ppo" else L.LOSS_FOCOPS, epochs=10**9, host_rng=False, device=dev)
+    upd.hp.focops_kl = 0.02
+    data = {k: v.to(dev).contiguous() for k, v in data_cpu.items()}
+    res = upd.run(data, perms=[perm], refresh_old=True)
+    opt = O.OracleOptim(opol)
+    losses = []
+    for s0 in range(0, S, batch):
+        idx = perm[s0:s0 + batch]
+        b = {k: v[idx] for k, v in data_cpu.items()}
+        b["old_mean"], b["old_std"] = old_mean[idx], old_std[idx]
+        losses.append(O.minibatch_step(opol, opt, b, kind))
+    want = torch.tensor(losses, dtype=torch.float64).mean(0)
+    n_steps = (S + batch - 1) // batch
+    assert res["steps"] == n_steps
+    for name, got, w in (("loss_r", res["loss_r"], want[0]), ("loss_c", res["loss_c"], want[1]), ("loss_pi", res["loss_pi"], want[2])):
+        ok, ea, er = close(got, w, rtol=5e-5, atol=5e-6)
+        assert ok, (kind, D, A, batch, name, got, float(w), ea, er)
+    final, ofinal = policy_state(pol), opol.state()
+    for net in O.NET_ORDER:
+        for k, v in ofinal[net].items():
+            err = float((final[net][k] - v).abs().max())
+            assert err < 5e-5, (kind, D, A, batch, net, k, err)    # 6 Adam steps of lr 3e-4
+
+
 # ---------------------------------------------------------------------------------------
 # end to end
 # ---------------------------------------------------------------------------------------
