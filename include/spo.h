@@ -103,6 +103,23 @@ int spo_store_transition(const spo_rollout* r, int t, const float* reward, const
                          const float* next_v_r, const float* next_v_c,
                          const float* final_v_r, const float* final_v_c, void* stream);
 
+/* ---- env I/O transforms around the forward ----
+ * spo_obs_normalize: SafeNormalizeObservation (safepo/common/wrappers.py:42-49; gymnasium
+ * NormalizeObservation + RunningMeanStd): with update != 0 folds the n rows into the running
+ * statistics (mean/var: device float64 [obs_dim], updated in place; `count` is passed by value
+ * and *count_out -- device, may be NULL -- receives count + n), then writes
+ * out = (obs - mean) / sqrt(var + eps) as fp32 [n][obs_dim] (out may be NULL to update only, or
+ * equal to obs for an in-place transform).
+ * The caller owns the count bookkeeping (RunningMeanStd starts at mean 0, var 1, count 1e-4). */
+int spo_obs_normalize(const float* obs, int n, int obs_dim, double* mean, double* var, double count,
+                      double* count_out, int update, double eps, float* out, void* stream);
+
+/* spo_action_rescale: SafeRescaleAction(env, min_action, max_action) (safepo/common/env.py:62,76;
+ * gymnasium RescaleAction): clip to [min_action, max_action], map affinely onto [low, high]
+ * (device fp32 [act_dim]), clip to [low, high].  act/out: device fp32 [n][act_dim]. */
+int spo_action_rescale(const float* act, int n, int act_dim, const float* low, const float* high,
+                       float min_action, float max_action, float* out, void* stream);
+
 /* ---- G1: finish_path -> calculate_adv_and_value_targets -> discount_cumsum
  * (safepo/common/buffer.py:97-140,167-201) for every path of every env in one launch.
  * delta in fp32 ((r + gamma*v') - v, unfused), carry in fp64, outputs rounded to fp32.

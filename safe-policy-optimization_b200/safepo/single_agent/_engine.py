@@ -114,8 +114,16 @@ class Rollout:
         self.obs_d = torch.empty(N, D, dtype=torch.float32, device=device)
         self.bytes_h2d = 0
         self.bytes_d2h = 0
+        # SafeNormalizeObservation (env.py:66,77) on the device: statistics updated and observations
+        # normalised right after the H2D of every env step (reset included, like gymnasium's wrapper)
+        self.obs_norm = None
+        if getattr(args, "normalize_obs", False):
+            from safepo.common.normalizer import SafeNormalizeObservation
+            self.obs_norm = SafeNormalizeObservation(D, device)
         obs, _ = env.reset()
         self.obs_d.copy_(torch.as_tensor(np.asarray(obs), dtype=torch.float32))
+        if self.obs_norm is not None:
+            self.obs_norm.normalize(self.obs_d, out=self.obs_d)
 
     def _burn_bootstrap_draws(self, terminated, truncated, epoch_end):
         """The reference obtains bootstrap values with policy.step(..., deterministic=False)
@@ -159,6 +167,8 @@ class Rollout:
             stage_d.copy_(stage_h, non_blocking=True)
             self.flags_d.copy_(self.flags_h, non_blocking=True)
             self.bytes_h2d += stage_h.numel() * 4 + 2 * N
+            if self.obs_norm is not None:
+                self.obs_norm.normalize(obs_view, out=obs_view)   # in place; final_observation stays raw
             epoch_end = t >= T - 1
             any_trunc = bool(truncated.any())
             final_v = None

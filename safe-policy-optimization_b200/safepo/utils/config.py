@@ -38,6 +38,8 @@ def build_parser():
     p.add_argument("--gae", choices=("scan", "exact"), default="scan", help="GAE kernel variant")
     p.add_argument("--env", choices=("synthetic", "mujoco"), default="synthetic", help="environment backend")
     p.add_argument("--episode-len", type=int, default=1000, help="time limit of the synthetic env")
+    p.add_argument("--normalize-obs", action="store_true",
+                   help="SafeNormalizeObservation on the device (the reference's env factory applies it on the host for MuJoCo tasks)")
     return p
 
 

@@ -125,3 +125,34 @@ def test_no_cpu_fallback():
     pol = ActorVCritic(4, 2)
     with pytest.raises(L.SpoError):
         pol.step(torch.zeros(3, 4))
+
+
+def test_oracle_running_mean_std_matches_pooled_moments():
+    """oracle/envio.py (restated gymnasium RunningMeanStd, parity unpinned): after any sequence of batch
+    updates the statistics equal the pooled moments of all rows plus the prior pseudo-observations
+    (count 1e-4 at mean 0, var 1) -- the defining property of the parallel-variance update."""
+    import numpy as np
+    from oracle import envio
+    rng = np.random.default_rng(0)
+    norm = envio.NormalizeObservation(5)
+    xs = [rng.normal(2.0, 3.0, size=(n, 5)) for n in (7, 1, 64)]
+    for x in xs:
+        out = norm.normalize(x)
+        np.testing.assert_allclose(out, (x - norm.obs_rms.mean) / np.sqrt(norm.obs_rms.var + 1e-8), rtol=0, atol=0)
+    allx = np.concatenate(xs)
+    c0, n = 1e-4, allx.shape[0]
+    mean = allx.sum(0) / (n + c0)                      # prior mean 0
+    ex2 = ((allx ** 2).sum(0) + c0 * 1.0) / (n + c0)   # prior E[x^2] = var + mean^2 = 1
+    np.testing.assert_allclose(norm.obs_rms.mean, mean, rtol=1e-12)
+    np.testing.assert_allclose(norm.obs_rms.var, ex2 - mean ** 2, rtol=1e-10)
+    assert abs(norm.obs_rms.count - (n + c0)) < 1e-9
+    frozen = norm.normalize(xs[0], update=False)
+    assert abs(norm.obs_rms.count - (n + c0)) < 1e-9 and frozen.shape == xs[0].shape
+
+
+def test_oracle_rescale_action_known_answers():
+    import numpy as np
+    from oracle import envio
+    low, high = np.array([-2.0, 0.0]), np.array([2.0, 10.0])
+    got = envio.rescale_action(np.array([[-1.0, -1.0], [0.0, 0.5], [1.0, 1.0], [3.0, -7.0]]), low, high)
+    np.testing.assert_allclose(got, [[-2.0, 0.0], [0.0, 7.5], [2.0, 10.0], [2.0, 0.0]])

@@ -411,6 +411,89 @@ def test_update_other_shapes_vs_oracle(kind, D, A, batch):
 
 
 # ---------------------------------------------------------------------------------------
+# env I/O transforms (oracle/envio.py restates third-party gymnasium: parity unpinned)
+# ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("N,D", [(1024, 60), (7, 33), (1, 1), (300, 128)])
+def test_obs_normalize_vs_oracle(N, D):
+    """Running statistics (fp64) to 1e-12 relative over 6 env steps, normalised observations to 1 fp32 ulp
+    (the oracle's float64 output rounded to fp32, as torch.as_tensor(..., dtype=float32) does)."""
+    from oracle import envio
+    from safepo.common.normalizer import SafeNormalizeObservation
+    dev = _cuda()
+    rng = np.random.default_rng(N * 1000 + D)
+    norm = SafeNormalizeObservation(D, dev)
+    onorm = envio.NormalizeObservation(D)
+    for step in range(6):
+        x = (rng.normal(1.5, 4.0, size=(N, D)) * (1 + np.arange(D)) * 0.1).astype(np.float32)
+        got = norm.normalize(torch.from_numpy(x).to(dev))
+        want = onorm.normalize(x.astype(np.float64))
+        np.testing.assert_allclose(norm.obs_rms.mean.cpu().numpy(), onorm.obs_rms.mean, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(norm.obs_rms.var.cpu().numpy(), onorm.obs_rms.var, rtol=1e-12, atol=1e-300)
+        assert abs(norm.obs_rms.count - onorm.obs_rms.count) < 1e-9
+        w32 = want.astype(np.float32)
+        err = np.abs(got.cpu().numpy() - w32)
+        assert (err <= np.spacing(np.abs(w32)) + 1e-30).all(), (N, D, step, float(err.max()))
+    x = rng.normal(size=(N, D)).astype(np.float32)
+    got = norm.normalize(torch.from_numpy(x).to(dev), update=False)           # evaluation mode: statistics frozen
+    want = onorm.normalize(x.astype(np.float64), update=False).astype(np.float32)
+    assert (np.abs(got.cpu().numpy() - want) <= np.spacing(np.abs(want)) + 1e-30).all()
+    assert abs(norm.obs_rms.count - onorm.obs_rms.count) < 1e-9
+
+
+def test_action_rescale_vs_oracle():
+    from oracle import envio
+    from safepo.common.normalizer import SafeRescaleAction
+    dev = _cuda()
+    rng = np.random.default_rng(5)
+    low, high = np.array([-2.0, 0.0, -0.3], np.float32), np.array([2.0, 10.0, 0.4], np.float32)
+    act = (rng.normal(size=(1024, 3)) * 1.2).astype(np.float32)
+    got = SafeRescaleAction(low, high, dev).action(torch.from_numpy(act).to(dev)).cpu().numpy()
+    want = envio.rescale_action(act.astype(np.float64), low.astype(np.float64), high.astype(np.float64))
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
+    assert (got >= low).all() and (got <= high).all()
+
+
+def test_trainer_with_device_obs_normalisation(tmp_path):
+    """--normalize-obs end to end: the rollout normalises every observation batch on the device (reset
+    included); after one epoch the running statistics equal the oracle's over the same raw stream, and the
+    buffer holds the oracle's normalised observations."""
+    from oracle import envio
+    from safepo.common import synthetic_env as senv
+    from safepo.common.buffer import VectorizedOnPolicyBuffer
+    from safepo.common.logger import EpochLogger
+    from safepo.common.model import ActorVCritic
+    from safepo.single_agent._engine import Rollout
+    from safepo.utils.config import single_agent_args
+    dev = _cuda()
+    N, T = 5, 37
+    args, _ = single_agent_args(["--num-envs", str(N), "--normalize-obs", "--rng", "host", "--log-dir", str(tmp_path)])
+    D, A = senv.TASK_DIMS[args.task]
+    env = senv.SyntheticVecEnv(N, D, A, episode_len=20, seed=9, stagger=True)
+    torch.manual_seed(0)
+    pol = ActorVCritic(D, A).to(dev)
+    buf = VectorizedOnPolicyBuffer(Sp(D), Sp(A), size=T, device=dev, num_envs=N)
+    logger = EpochLogger(log_dir=str(tmp_path / "run"), seed="0")
+    ro = Rollout(env, pol, buf, logger, args, dev)
+    ro.run(T)
+    # replay the raw observation stream through the oracle: same env, same actions (stored in the buffer)
+    env2 = senv.SyntheticVecEnv(N, D, A, episode_len=20, seed=9, stagger=True)
+    onorm = envio.NormalizeObservation(D)
+    obs, _ = env2.reset()
+    cur = onorm.normalize(np.asarray(obs, dtype=np.float32).astype(np.float64))
+    acts = buf.data["act"].cpu().numpy().reshape(N, T, A)
+    stored = buf.data["obs"].cpu().numpy().reshape(N, T, D)
+    for t in range(T):
+        w32 = cur.astype(np.float32)
+        assert (np.abs(stored[:, t] - w32) <= np.spacing(np.abs(w32)) + 1e-30).all(), t
+        nxt = env2.step(acts[:, t])[0]
+        cur = onorm.normalize(np.asarray(nxt, dtype=np.float32).astype(np.float64))
+    np.testing.assert_allclose(ro.obs_norm.obs_rms.mean.cpu().numpy(), onorm.obs_rms.mean, rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(ro.obs_norm.obs_rms.var.cpu().numpy(), onorm.obs_rms.var, rtol=1e-12, atol=1e-300)
+    assert abs(ro.obs_norm.obs_rms.count - onorm.obs_rms.count) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------
 # end to end
 # ---------------------------------------------------------------------------------------
 
