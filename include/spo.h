@@ -152,7 +152,8 @@ int spo_adv_apply(float* adv_r, float* adv_c, int64_t count, const double* stats
 typedef enum spo_loss_kind {
   SPO_LOSS_PPO_CLIP = 0,   /* ppo_lag.py:315-319 */
   SPO_LOSS_FOCOPS = 1,     /* focops.py:323-337 ([B,1]x[B] broadcast semantics) */
-  SPO_LOSS_CRITIC_ONLY = 2 /* cpo.py:543-571, trpo_lag.py:466-494 */
+  SPO_LOSS_CRITIC_ONLY = 2,/* cpo.py:543-571, trpo_lag.py:466-494 */
+  SPO_LOSS_PG = 3          /* pg.py:303-309: -(ratio * adv).mean(), the surrogate without the clip */
 } spo_loss_kind;
 
 typedef struct spo_batch {

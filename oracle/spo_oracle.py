@@ -238,6 +238,34 @@ class OracleLagrange:
 # minibatch order  (torch DataLoader(shuffle=True) as used at ppo_lag.py:283-294)
 # --------------------------------------------------------------------------------------
 
+class OraclePIDLagrange:
+    """PIDLagrangian (safepo/common/lagrange.py:108-200) with its default gains: plain Python-float
+    arithmetic, restated in the reference's operation order (sum_norm=True, diff_norm=False)."""
+
+    def __init__(self, cost_limit, init=0.005, kp=0.1, ki=0.01, kd=0.01, d_delay=10, p_ema=0.95, d_ema=0.95):
+        from collections import deque
+        self.kp, self.ki, self.kd, self.p_ema, self.d_ema = kp, ki, kd, p_ema, d_ema
+        self.pid_i = init
+        self.cost_ds = deque(maxlen=d_delay)
+        self.cost_ds.append(0.0)
+        self.delta_p = 0.0
+        self.cost_d = 0.0
+        self.cost_limit = cost_limit
+        self.lagrangian_multiplier = 0.0
+
+    def update_lagrange_multiplier(self, ep_cost_avg):
+        delta = float(ep_cost_avg - self.cost_limit)
+        self.pid_i = max(0.0, self.pid_i + delta * self.ki)
+        self.delta_p *= self.p_ema
+        self.delta_p += (1 - self.p_ema) * delta
+        self.cost_d *= self.d_ema
+        self.cost_d += (1 - self.d_ema) * float(ep_cost_avg)
+        pid_d = max(0.0, self.cost_d - self.cost_ds[0])
+        pid_o = self.kp * self.delta_p + self.pid_i + self.kd * pid_d
+        self.lagrangian_multiplier = max(0.0, pid_o)
+        self.cost_ds.append(self.cost_d)
+
+
 def dataloader_perm(S):
     """One ``for ... in dataloader`` consumes two int64 draws from the global generator
     (base seed, then the sampler seed); the order is randperm(S) under the second."""
@@ -298,6 +326,14 @@ def ppo_actor_loss(pol, obs_b, act_b, logp_b, adv_b):
     return -torch.min(ratio * adv_b, ratio_c * adv_b).mean()
 
 
+def pg_actor_loss(pol, obs_b, act_b, logp_b, adv_b):
+    """pg.py:303-309: the importance-weighted surrogate without the clip."""
+    mean, std = actor_mean_std(pol, obs_b)
+    log_prob = normal_log_prob(act_b, mean, std).sum(-1)
+    ratio = torch.exp(log_prob - logp_b)
+    return -(ratio * adv_b).mean()
+
+
 def focops_actor_loss(pol, obs_b, act_b, logp_b, adv_b, old_mean_b, old_std_b, target_kl, focops_lam=1.5):
     """focops.py:323-337, including the [B,1]x[B] broadcast."""
     mean, std = actor_mean_std(pol, obs_b)
@@ -316,6 +352,8 @@ def minibatch_step(pol, opt, batch, kind="ppo", max_grad_norm=40.0, target_kl=0.
     loss_r, loss_c = critic_losses(pol, batch["obs"], batch["target_value_r"], batch["target_value_c"])
     if kind == "ppo":
         loss_pi = ppo_actor_loss(pol, batch["obs"], batch["act"], batch["log_prob"], batch["adv"])
+    elif kind == "pg":
+        loss_pi = pg_actor_loss(pol, batch["obs"], batch["act"], batch["log_prob"], batch["adv"])
     elif kind == "focops":
         loss_pi = focops_actor_loss(pol, batch["obs"], batch["act"], batch["log_prob"], batch["adv"],
                                     batch["old_mean"], batch["old_std"], target_kl)

@@ -25,6 +25,13 @@ ALGO_CFG = {
     "cpo": dict(hidden_sizes=[64, 64], gamma=0.99, target_kl=0.01, batch_size=128, learning_iters=10, max_grad_norm=40.0),
     "trpo_lag": dict(hidden_sizes=[64, 64], gamma=0.99, target_kl=0.01, batch_size=128, learning_iters=10, max_grad_norm=40.0),
 }
+# siblings built from the same templates: ppo.py / pg.py / cppo_pid.py are ppo_lag.py with the
+# Lagrange lines removed / the clip removed / PIDLagrangian swapped in; trpo.py is trpo_lag.py without Lagrange
+for _a, _base in (("ppo", "ppo_lag"), ("pg", "ppo_lag"), ("cppo_pid", "ppo_lag"), ("trpo", "trpo_lag")):
+    ALGO_CFG[_a] = dict(ALGO_CFG[_base])
+PG_FAMILY = ("ppo_lag", "focops", "ppo", "pg", "cppo_pid")   # minibatch policy-gradient updates with KL early stop
+PG_KIND = {"ppo_lag": "ppo", "ppo": "ppo", "cppo_pid": "ppo", "pg": "pg", "focops": "focops"}
+NO_LAGRANGE = ("cpo", "ppo", "pg", "trpo")
 
 
 def default_args(**kw):
@@ -178,11 +185,13 @@ def train(algo, args, env, max_epochs=None, hooks=None):
     else:
         epochs_run = epochs
     pol = O.OraclePolicy(D, A, cfg["hidden_sizes"])
-    trust = algo in ("cpo", "trpo_lag")
+    trust = algo in ("cpo", "trpo_lag", "trpo")
     opt = O.OracleOptim(pol, lr=3e-4, critic_lr=1e-3 if trust else 3e-4, epochs=epochs)
     buf = PathBuffer(N, T, D, A, cfg["gamma"])
     lagrange = None
-    if algo != "cpo":
+    if algo == "cppo_pid":
+        lagrange = O.OraclePIDLagrange(args.cost_limit, args.lagrangian_multiplier_init)      # cppo_pid.py:128-131
+    elif algo not in NO_LAGRANGE:
         lagrange = O.OracleLagrange(args.cost_limit, args.lagrangian_multiplier_init, args.lagrangian_multiplier_lr,
                                     upper_bound=2.0 if algo == "focops" else None)
     log = StatLog()
@@ -196,14 +205,22 @@ def train(algo, args, env, max_epochs=None, hooks=None):
         obs = rollout(pol, env, buf, obs, ep, deques, log, T)
         t1 = time.time()
         extra = {}
-        if algo != "cpo":
-            lagrange.update_lagrange_multiplier(log.get_stats("Metrics/EpCost"))
+        ep_costs_stat = log.get_stats("Metrics/EpCost")      # read in every script (ppo_lag.py:272), used or not
+        if lagrange is not None:
+            lagrange.update_lagrange_multiplier(ep_costs_stat)
         data = buf.get()
-        if algo in ("ppo_lag", "focops"):
+
+        def mixed_advantage():
+            if lagrange is None:
+                return data["adv_r"]                          # ppo.py:272, trpo.py:361
             lam = lagrange.lagrangian_multiplier
-            advantage = data["adv_r"] - lam * data["adv_c"]
-            advantage /= (lam + 1)
-            res = O.pg_update(pol, opt, data, advantage, kind="ppo" if algo == "ppo_lag" else "focops",
+            adv = data["adv_r"] - lam * data["adv_c"]
+            adv /= (lam + 1)
+            return adv
+
+        if algo in PG_FAMILY:
+            advantage = mixed_advantage()
+            res = O.pg_update(pol, opt, data, advantage, kind=PG_KIND[algo],
                               batch_size=cfg["batch_size"], learning_iters=cfg["learning_iters"],
                               target_kl=cfg["target_kl"], max_grad_norm=cfg["max_grad_norm"])
             for lr_, lc_, lp_ in res["losses"]:
@@ -214,10 +231,7 @@ def train(algo, args, env, max_epochs=None, hooks=None):
                 ep_costs = log.get_stats("Metrics/EpCost") - args.cost_limit
                 res = O.cpo_policy_update(pol, data, ep_costs, target_kl=cfg["target_kl"])
             else:
-                lam = lagrange.lagrangian_multiplier
-                advantage = data["adv_r"] - lam * data["adv_c"]
-                advantage /= (lam + 1)
-                res = O.trpo_policy_update(pol, data, advantage, target_kl=cfg["target_kl"])
+                res = O.trpo_policy_update(pol, data, mixed_advantage(), target_kl=cfg["target_kl"])
             log.store(**{"Misc/Alpha": res["alpha"].item(), "Misc/FinalStepNorm": torch.norm(res["step_dir"]).mean().item(),
                          "Misc/xHx": res["xHx"].item(), "Misc/gradient_norm": torch.norm(res["g"]).mean().item(),
                          "Misc/H_inv_g": res["x"].norm().item(), "Misc/AcceptanceStep": res["acceptance"],
@@ -229,7 +243,7 @@ def train(algo, args, env, max_epochs=None, hooks=None):
         t2 = time.time()
         if hooks and "after_update" in hooks:
             hooks["after_update"](epoch, pol, data, extra)
-        if algo in ("ppo_lag", "focops"):
+        if algo in PG_FAMILY:
             opt.scheduler_step()
         times["rollout"].append(t1 - t0); times["update"].append(t2 - t1)
         if not log.logged:
@@ -237,10 +251,11 @@ def train(algo, args, env, max_epochs=None, hooks=None):
                 log.log_tabular(k)
             log.log_tabular("Train/Epoch", epoch + 1)
             log.log_tabular("Train/TotalSteps", (epoch + 1) * args.steps_per_epoch)
-            if algo in ("ppo_lag", "focops"):
+            if algo in PG_FAMILY:
                 log.log_tabular("Train/StopIter", extra["Train/StopIter"])
                 log.log_tabular("Train/KL", extra["Train/KL"])
-                log.log_tabular("Train/LagragianMultiplier", lagrange.lagrangian_multiplier)
+                if lagrange is not None:
+                    log.log_tabular("Train/LagragianMultiplier", lagrange.lagrangian_multiplier)
                 log.log_tabular("Train/LR", opt.actor_lr())
             else:
                 if algo == "trpo_lag":

@@ -1108,7 +1108,7 @@ extern "C" int spo_pg_update_dp(const spo_dims* d, float* params, float* adam_m,
   SPO_REQUIRE(params && adam_m && adam_v && adam_t && data && perm && hp && ctrl, SPO_ERR_INVALID_ARG, "spo_pg_update: null argument");
   SPO_REQUIRE(batch > 0 && perm_len > 0 && perm_len <= data->count, SPO_ERR_INVALID_ARG,
               "spo_pg_update: batch=%d perm_len=%lld count=%lld", batch, (long long)perm_len, (long long)data->count);
-  SPO_REQUIRE(kind >= SPO_LOSS_PPO_CLIP && kind <= SPO_LOSS_CRITIC_ONLY, SPO_ERR_INVALID_ARG, "spo_pg_update: kind=%d", (int)kind);
+  SPO_REQUIRE(kind >= SPO_LOSS_PPO_CLIP && kind <= SPO_LOSS_PG, SPO_ERR_INVALID_ARG, "spo_pg_update: kind=%d", (int)kind);
   SPO_REQUIRE(data->obs && data->target_r && data->target_c, SPO_ERR_INVALID_ARG, "spo_pg_update: batch obs/targets null");
   if (kind != SPO_LOSS_CRITIC_ONLY)
     SPO_REQUIRE(data->act && data->logp && data->adv, SPO_ERR_INVALID_ARG, "spo_pg_update: actor loss needs act/logp/adv");
@@ -1120,6 +1120,13 @@ extern "C" int spo_pg_update_dp(const spo_dims* d, float* params, float* adam_m,
   a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.adam_t = adam_t;
   a.data = *data; a.perm = perm; a.perm_len = perm_len; a.batch = batch; a.kind = kind;
   a.D = d->obs_dim; a.A = d->act_dim; a.hp = *hp; a.ctrl = ctrl;
+  if (kind == SPO_LOSS_PG) {
+    // the unclipped surrogate is the clipped one with an unbounded clip range: clamp(ratio) == ratio, the
+    // min() keeps the first branch, value and gradient are those of pg.py:309 bit for bit
+    a.kind = SPO_LOSS_PPO_CLIP;
+    a.hp.clip_lo = -INFINITY;
+    a.hp.clip_hi = INFINITY;
+  }
   if (comm && comm->world > 1) {
     SPO_REQUIRE(comm->rank >= 0 && comm->rank < comm->world && comm->world <= 32 && comm->grad_bufs && comm->flags,
                 SPO_ERR_INVALID_ARG, "spo_pg_update_dp: bad spo_comm (world=%d rank=%d)", comm->world, comm->rank);

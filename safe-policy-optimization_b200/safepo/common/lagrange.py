@@ -57,3 +57,49 @@ class Lagrange:
                 if self.lagrangian_upper_bound is not None:
                     lam = min(lam, _F(self.lagrangian_upper_bound))
             self._lagrangian_multiplier = _F(lam)
+
+
+class PIDLagrangian:
+    """PID-controlled multiplier of CPPO-PID (Stooke, Achiam, Abbeel 2020), interface and defaults of the
+    reference's ``PIDLagrangian`` (safepo/common/lagrange.py:108-200, used by cppo_pid.py:39,128-131).
+
+    State: integral term I (clamped at 0), EMA of the constraint violation (proportional term), EMA of the
+    episode cost with a ``pid_d_delay``-step delay line (derivative term, only rises count).  The penalty is
+    max(0, Kp * ema(delta) + I + Kd * max(0, ema(cost) - ema(cost)[t - delay])).  Python floats on the host,
+    evaluated in the reference's order, so the sequence is bit-identical (tests/golden/siblings.pt)."""
+
+    def __init__(self, cost_limit, lagrangian_multiplier_init=0.005, pid_kp=0.1, pid_ki=0.01, pid_kd=0.01, pid_d_delay=10,
+                 pid_delta_p_ema_alpha=0.95, pid_delta_d_ema_alpha=0.95, sum_norm=True, diff_norm=False, penalty_max=100.0):
+        from collections import deque
+        self.cost_limit = cost_limit
+        self._gains = (pid_kp, pid_ki, pid_kd)
+        self._ema = (pid_delta_p_ema_alpha, pid_delta_d_ema_alpha)
+        self._sum_norm, self._diff_norm, self._penalty_max = sum_norm, diff_norm, penalty_max
+        self._integral = lagrangian_multiplier_init
+        self._violation_ema = 0.0
+        self._cost_ema = 0.0
+        self._delay_line = deque([0.0], maxlen=pid_d_delay)
+        self._penalty = 0.0
+
+    @property
+    def lagrangian_multiplier(self):
+        return self._penalty
+
+    def update_lagrange_multiplier(self, ep_cost_avg):
+        kp, ki, kd = self._gains
+        alpha_p, alpha_d = self._ema
+        violation = float(ep_cost_avg - self.cost_limit)
+        self._integral = max(0.0, self._integral + violation * ki)
+        if self._diff_norm:
+            self._integral = max(0.0, min(1.0, self._integral))
+        self._violation_ema *= alpha_p
+        self._violation_ema += (1 - alpha_p) * violation
+        self._cost_ema *= alpha_d
+        self._cost_ema += (1 - alpha_d) * float(ep_cost_avg)
+        rise = max(0.0, self._cost_ema - self._delay_line[0])
+        self._penalty = max(0.0, kp * self._violation_ema + self._integral + kd * rise)
+        if self._diff_norm:
+            self._penalty = min(1.0, self._penalty)
+        if not (self._diff_norm or self._sum_norm):
+            self._penalty = min(self._penalty, self._penalty_max)
+        self._delay_line.append(self._cost_ema)

@@ -31,7 +31,7 @@ import torch
 
 from safepo import _lib as L
 from safepo.common.buffer import VectorizedOnPolicyBuffer
-from safepo.common.lagrange import Lagrange
+from safepo.common.lagrange import Lagrange, PIDLagrangian
 from safepo.common.logger import EpochLogger
 from safepo.common.model import ActorVCritic
 
@@ -614,6 +614,9 @@ def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False)
             lagrange.update_lagrange_multiplier(logger.get_stats("Metrics/EpCost"))
             data = buffer.get(lagrange.lagrangian_multiplier)
             res = trust.run_trpo(data, data["adv"])
+        elif algo == "trpo":                       # trpo.py:361: advantage = adv_r
+            data = buffer.get(0.0)
+            res = trust.run_trpo(data, data["adv"])
         else:
             data = buffer.get(0.0)
             ep_costs = logger.get_stats("Metrics/EpCost") - args.cost_limit
@@ -679,8 +682,14 @@ def run_policy_gradient(args, config, algo, env=None, max_epochs=None, quiet=Fal
     policy = ActorVCritic(obs_space.shape[0], act_space.shape[0], config["hidden_sizes"]).to(device)
     buffer = VectorizedOnPolicyBuffer(obs_space, act_space, size=T, device=device, num_envs=args.num_envs,
                                       gamma=config["gamma"], gae_mode=getattr(args, "gae", "scan"))
-    lagrange = Lagrange(args.cost_limit, args.lagrangian_multiplier_init, args.lagrangian_multiplier_lr,
-                        lagrangian_upper_bound=2.0 if algo == "focops" else None)
+    # siblings of ppo_lag.py: ppo.py / pg.py drop the multiplier, cppo_pid.py swaps in the PID one
+    if algo in ("ppo", "pg"):
+        lagrange = None
+    elif algo == "cppo_pid":
+        lagrange = PIDLagrangian(args.cost_limit, args.lagrangian_multiplier_init)
+    else:
+        lagrange = Lagrange(args.cost_limit, args.lagrangian_multiplier_init, args.lagrangian_multiplier_lr,
+                            lagrangian_upper_bound=2.0 if algo == "focops" else None)
     dict_args = dict(vars(args))
     dict_args.update(config)
     logger = EpochLogger(args.log_dir, seed=str(args.seed), verbose=not quiet, use_tensorboard=not quiet)
@@ -690,16 +699,19 @@ def run_policy_gradient(args, config, algo, env=None, max_epochs=None, quiet=Fal
     host_rng = getattr(args, "rng", "device") == "host"
     roll_cls = DeviceTapeRollout if getattr(args, "resident_env", False) else Rollout
     roll = roll_cls(env, policy, buffer, logger, args, device)
-    upd = PolicyGradientUpdate(policy, config, L.LOSS_PPO_CLIP if algo == "ppo_lag" else L.LOSS_FOCOPS, epochs, host_rng, device,
-                               dp=dp)
+    kind = {"ppo_lag": L.LOSS_PPO_CLIP, "ppo": L.LOSS_PPO_CLIP, "cppo_pid": L.LOSS_PPO_CLIP, "pg": L.LOSS_PG, "focops": L.LOSS_FOCOPS}[algo]
+    upd = PolicyGradientUpdate(policy, config, kind, epochs, host_rng, device, dp=dp)
     timings = []
     n_epochs = epochs if max_epochs is None else min(epochs, max_epochs)
     for epoch in range(n_epochs):
         t_roll = roll.run(T)
         t1 = time.time()
         ep_costs = logger.get_stats("Metrics/EpCost") if dp is None else dp.mean_episode_cost(logger, device=device)
-        lagrange.update_lagrange_multiplier(ep_costs)
-        data = buffer.get(lagrange.lagrangian_multiplier, all_reduce=None if dp is None else dp.all_reduce_sum)
+        if lagrange is not None:
+            lagrange.update_lagrange_multiplier(ep_costs)
+        # without a multiplier the advantage is adv_r itself (ppo.py:272): (adv_r - 0 * adv_c) / 1, exactly
+        lam = lagrange.lagrangian_multiplier if lagrange is not None else 0.0
+        data = buffer.get(lam, all_reduce=None if dp is None else dp.all_reduce_sum)
         res = upd.run(data)
         buffer.reset_segments()
         torch.cuda.synchronize()
@@ -714,7 +726,8 @@ def run_policy_gradient(args, config, algo, env=None, max_epochs=None, quiet=Fal
             logger.log_tabular("Train/TotalSteps", (epoch + 1) * args.steps_per_epoch)
             logger.log_tabular("Train/StopIter", res["stop_iter"])
             logger.log_tabular("Train/KL", res["kl"])
-            logger.log_tabular("Train/LagragianMultiplier", lagrange.lagrangian_multiplier)
+            if lagrange is not None:
+                logger.log_tabular("Train/LagragianMultiplier", lagrange.lagrangian_multiplier)
             logger.log_tabular("Train/LR", upd.sched.lr)
             for k in ("Loss/Loss_reward_critic", "Loss/Loss_cost_critic", "Loss/Loss_actor"):
                 logger.log_tabular(k)

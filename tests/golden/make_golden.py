@@ -47,7 +47,7 @@ def import_reference():
     if REF not in sys.path:
         sys.path.insert(0, REF)
     mods = {}
-    for algo in ("ppo_lag", "focops", "cpo", "trpo_lag"):
+    for algo in ("ppo_lag", "focops", "cpo", "trpo_lag", "ppo", "pg", "cppo_pid", "trpo"):
         m = importlib.import_module(f"safepo.single_agent.{algo}")
         if hasattr(m, "LinearLR"):
             real = m.LinearLR
@@ -300,11 +300,39 @@ def gen_main_runs(ref, out):
     out["main_runs"] = runs
 
 
+def gen_siblings(ref, out):
+    """main() of the sibling scripts ppo / pg / cppo_pid / trpo on the synthetic env, and a
+    PIDLagrangian sequence (safepo/common/lagrange.py:108-200)."""
+    runs = {}
+    cfgs = {
+        "ppo": (dict(seed=7, num_envs=3, steps_per_epoch=3 * 70, total_steps=3 * 70 * 2), dict(episode_len=25, stagger=True, p_terminate=0.02)),
+        "pg": (dict(seed=8, num_envs=2, steps_per_epoch=2 * 90, total_steps=2 * 90 * 2), dict(episode_len=30, stagger=True, p_terminate=0.02)),
+        "cppo_pid": (dict(seed=9, num_envs=3, steps_per_epoch=3 * 70, total_steps=3 * 70 * 3, cost_limit=5.0),
+                     dict(episode_len=25, stagger=True, p_terminate=0.02)),
+        "trpo": (dict(seed=10, num_envs=2, steps_per_epoch=2 * 100, total_steps=2 * 100 * 2), dict(episode_len=40, stagger=True, p_terminate=0.02)),
+    }
+    for algo, (akw, ekw) in cfgs.items():
+        rows, actor_sd, files = run_reference_main(ref, algo, akw, ekw)
+        runs[algo] = dict(args=akw, env=ekw, rows=rows, actor=actor_sd, files=files)
+        print(algo, "rows:", len(rows), "files:", files)
+    out["main_runs"] = runs
+    P = ref["lagrange"].PIDLagrangian(25.0, 0.001)
+    jcs = [0.0, 50.0, 50.0, 10.0, 31.5, 2.0, 80.0, 80.0, 80.0, 26.0, 24.0, 3.0, 90.0, 12.5]
+    seq = []
+    for jc in jcs:
+        P.update_lagrange_multiplier(jc)
+        seq.append(P.lagrangian_multiplier)
+    out["pid"] = dict(jc=jcs, lam=seq)
+
+
 def main():
     sys.path.insert(0, ROOT)
     ref = import_reference()
+    only = set(sys.argv[1:])      # e.g. `python make_golden.py siblings` regenerates one fixture
     for name, fn in (("forward", gen_forward), ("gae", gen_gae), ("lagrange", gen_lagrange), ("update", gen_update_chain),
-                     ("dataloader", gen_dataloader), ("trust", gen_trust), ("main_runs", gen_main_runs)):
+                     ("dataloader", gen_dataloader), ("trust", gen_trust), ("main_runs", gen_main_runs), ("siblings", gen_siblings)):
+        if only and name not in only:
+            continue
         out = {}
         fn(ref, out)
         path = os.path.join(HERE, f"{name}.pt")

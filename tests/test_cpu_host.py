@@ -156,3 +156,20 @@ def test_oracle_rescale_action_known_answers():
     low, high = np.array([-2.0, 0.0]), np.array([2.0, 10.0])
     got = envio.rescale_action(np.array([[-1.0, -1.0], [0.0, 0.5], [1.0, 1.0], [3.0, -7.0]]), low, high)
     np.testing.assert_allclose(got, [[-2.0, 0.0], [0.0, 7.5], [2.0, 10.0], [2.0, 0.0]])
+
+
+def test_pid_lagrangian_host_class_matches_reference(golden):
+    """safepo.common.lagrange.PIDLagrangian (cppo_pid) against the sequence the reference's class produced."""
+    from safepo.common.lagrange import PIDLagrangian
+    c = golden("siblings")["pid"]
+    P = PIDLagrangian(25.0, 0.001)
+    for jc, want in zip(c["jc"], c["lam"]):
+        P.update_lagrange_multiplier(jc)
+        assert P.lagrangian_multiplier == want, (jc, P.lagrangian_multiplier, want)
+
+
+def test_sibling_cli_modules_expose_reference_entry_points():
+    import importlib
+    for name in ("ppo", "pg", "cppo_pid", "trpo", "ppo_lag", "focops", "cpo", "trpo_lag"):
+        m = importlib.import_module(f"safepo.single_agent.{name}")
+        assert callable(m.main) and isinstance(m.default_cfg, dict) and m.default_cfg["hidden_sizes"] == [64, 64]

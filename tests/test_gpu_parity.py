@@ -361,6 +361,8 @@ def test_full_batch_kl_vs_reference(golden):
     ("ppo", 60, 2, 100),      # ragged second tile in every step
     ("focops", 60, 2, 48),    # minibatch smaller than the tile
     ("ppo", 1, 1, 64),        # smallest supported shapes
+    ("pg", 60, 2, 64),        # SPO_LOSS_PG: the surrogate without the clip (pg.py:309)
+    ("pg", 17, 6, 100),
 ])
 def test_update_other_shapes_vs_oracle(kind, D, A, batch):
     """One pass of minibatch steps at shapes the golden fixtures do not cover, against the oracle's
@@ -386,7 +388,8 @@ def test_update_other_shapes_vs_oracle(kind, D, A, batch):
                 "target_value_c": torch.randn(S, generator=g).abs(), "adv": torch.randn(S, generator=g)}
     perm = torch.randperm(S, generator=g)
     cfg = dict(hidden_sizes=[64, 64], gamma=0.99, target_kl=1e9, batch_size=batch, learning_iters=1, max_grad_norm=40.0)
-    upd = PolicyGradientUpdate(pol, cfg, L.LOSS_PPO_CLIP if kind == "ppo" else L.LOSS_FOCOPS, epochs=10**9, host_rng=False, device=dev)
+    upd = PolicyGradientUpdate(pol, cfg, {"ppo": L.LOSS_PPO_CLIP, "pg": L.LOSS_PG, "focops": L.LOSS_FOCOPS}[kind], epochs=10**9,
+                               host_rng=False, device=dev)
     upd.hp.focops_kl = 0.02
     data = {k: v.to(dev).contiguous() for k, v in data_cpu.items()}
     res = upd.run(data, perms=[perm], refresh_old=True)
@@ -497,7 +500,7 @@ def test_trainer_with_device_obs_normalisation(tmp_path):
 # end to end
 # ---------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("algo", ["ppo_lag", "focops"])
+@pytest.mark.parametrize("algo", ["ppo_lag", "focops", "ppo", "pg", "cppo_pid"])
 def test_trainer_tracks_oracle_trainer(tmp_path, algo):
     """The drop-in CLI entry (main) on the synthetic env in host-RNG (parity) mode follows
     oracle.trainers.train -- i.e. the reference's main() -- through two epochs."""
@@ -506,14 +509,15 @@ def test_trainer_tracks_oracle_trainer(tmp_path, algo):
     from safepo.utils.config import single_agent_args
     mod = importlib.import_module(f"safepo.single_agent.{algo}")
     N, T, L_ep = 6, 120, 40
+    extra = ["--cost-limit", "5.0"] if algo == "cppo_pid" else []      # a limit the synthetic costs exceed: the PID terms move
     argv = ["--seed", "3", "--num-envs", str(N), "--steps-per-epoch", str(N * T), "--total-steps", str(2 * N * T),
-            "--rng", "host", "--gae", "exact", "--log-dir", str(tmp_path)]
+            "--rng", "host", "--gae", "exact", "--log-dir", str(tmp_path)] + extra
     args, _ = single_agent_args(argv)
     args.log_dir = str(tmp_path / "exp" / args.task / algo / "run")
     D, A = senv.TASK_DIMS[args.task]
     env = senv.SyntheticVecEnv(N, D, A, episode_len=L_ep, seed=3, stagger=True, p_terminate=0.01)
     pol, logger, timings, _ = mod.main(args, env=env, quiet=True)
-    oargs = TR.default_args(seed=3, num_envs=N, steps_per_epoch=N * T, total_steps=2 * N * T)
+    oargs = TR.default_args(seed=3, num_envs=N, steps_per_epoch=N * T, total_steps=2 * N * T, cost_limit=args.cost_limit)
     oenv = senv.SyntheticVecEnv(N, D, A, episode_len=L_ep, seed=3, stagger=True, p_terminate=0.01)
     opol, olog, _ = TR.train(algo, oargs, oenv)
     import csv
@@ -522,7 +526,9 @@ def test_trainer_tracks_oracle_trainer(tmp_path, algo):
     for got, want in zip(rows, olog.rows):
         for k in ("Metrics/EpRet", "Metrics/EpCost", "Metrics/EpLen", "Train/Epoch", "Train/TotalSteps", "Train/LR"):
             assert float(got[k]) == pytest.approx(float(want[k]), rel=1e-6, abs=1e-9), k
-        assert float(got["Train/LagragianMultiplier"]) == pytest.approx(float(want["Train/LagragianMultiplier"]), rel=1e-5, abs=1e-8)
+        assert ("Train/LagragianMultiplier" in got) == ("Train/LagragianMultiplier" in want) == (algo not in ("ppo", "pg"))
+        if "Train/LagragianMultiplier" in want:
+            assert float(got["Train/LagragianMultiplier"]) == pytest.approx(float(want["Train/LagragianMultiplier"]), rel=1e-5, abs=1e-8)
         assert int(float(got["Train/StopIter"])) == int(want["Train/StopIter"])
         for k in ("Loss/Loss_reward_critic", "Loss/Loss_cost_critic", "Loss/Loss_actor", "Train/KL"):
             assert float(got[k]) == pytest.approx(float(want[k]), rel=2e-3, abs=2e-5), (k, got[k], want[k])
@@ -602,7 +608,7 @@ def test_linesearch_eval_vs_oracle(golden):
         assert close(got, want, rtol=2e-5, atol=1e-7)[0], (float(got), float(want))
 
 
-@pytest.mark.parametrize("algo", ["cpo", "trpo_lag"])
+@pytest.mark.parametrize("algo", ["cpo", "trpo_lag", "trpo"])
 def test_trust_region_trainer_tracks_oracle(tmp_path, algo):
     import csv
     import importlib

@@ -164,3 +164,33 @@ def test_full_main_matches_reference(golden, algo):
             assert g == w or np.float32(g) == np.float32(w) or (np.isnan(g) and np.isnan(w)), (algo, k, g, w)
     # the checkpoint the reference wrote is from epoch 0 (logger.torch_save at epoch==0)
     assert set(run["actor"].keys()) == set(pol.nets["actor"].keys())
+
+
+@pytest.mark.parametrize("algo", ["ppo", "pg", "cppo_pid", "trpo"])
+def test_sibling_main_matches_reference(golden, algo):
+    """the sibling scripts (ppo_lag / trpo_lag minus Lagrange, minus the clip, with the PID
+    multiplier) -- oracle.trainers.train against the reference's own main(), every logged number bit for bit."""
+    run = golden("siblings")["main_runs"][algo]
+    senv = _load_env_mod()
+    args = TR.default_args(**run["args"])
+    D, A = senv.TASK_DIMS[args.task]
+    env = senv.SyntheticVecEnv(args.num_envs, D, A, seed=args.seed, **run["env"])
+    pol, log, _ = TR.train(algo, args, env)
+    assert len(log.rows) == len(run["rows"])
+    for got, want in zip(log.rows, run["rows"]):
+        assert set(k for k in want if not k.startswith("Time/")) <= set(got.keys()), (algo, sorted(set(want) - set(got)))
+        for k, v in want.items():
+            if k.startswith("Time/"):
+                continue
+            w = float(v.replace("tensor(", "").rstrip(")")) if isinstance(v, str) else float(v)
+            g = float(got[k])
+            assert g == w or np.float32(g) == np.float32(w) or (np.isnan(g) and np.isnan(w)), (algo, k, g, w)
+        assert ("Train/LagragianMultiplier" in got) == ("Train/LagragianMultiplier" in want), algo
+
+
+def test_pid_lagrange_matches_reference(golden):
+    c = golden("siblings")["pid"]
+    P = O.OraclePIDLagrange(25.0, 0.001)
+    for jc, want in zip(c["jc"], c["lam"]):
+        P.update_lagrange_multiplier(jc)
+        assert P.lagrangian_multiplier == want, (jc, P.lagrangian_multiplier, want)
