@@ -675,6 +675,31 @@ def trpo_policy_update(pol, data, advantage, target_kl=0.01, cg_iters=15, search
             "acceptance": acceptance, "kl": final_kl, "loss_actor": loss_pi.item()}
 
 
+def npg_policy_update(pol, data, advantage, target_kl=0.01, cg_iters=15):
+    """natural_pg.py:355-387 / rcpo.py: the TRPO direction x * sqrt(2 delta / xHx) taken at full length, no
+    line search; Train/KL is KL(old || new).mean() after the step, Loss/Loss_actor the surrogate before it."""
+    obs, act, logp_old = data["obs"], data["act"], data["log_prob"]
+    for p_ in pol.params("actor"):
+        p_.grad = None
+    theta_old = flat_params(pol)
+    loss_pi = -surrogate_loss(pol, obs, act, logp_old, advantage)
+    with torch.no_grad():
+        old_mean, old_std = actor_mean_std(pol, obs)
+        old_mean, old_std = old_mean.clone(), old_std.clone()
+    loss_pi.backward()
+    g = -flat_grads(pol)
+    Avp = lambda v: fvp_autograd(pol, obs, v)
+    x = conjugate_gradients(Avp, g, cg_iters)
+    xHx = torch.dot(x, Avp(x))
+    alpha = torch.sqrt(2 * target_kl / (xHx + 1e-8))
+    step_dir = x * alpha
+    set_flat_params(pol, theta_old + step_dir)
+    with torch.no_grad():
+        mean, std = actor_mean_std(pol, obs)
+        kl = normal_kl(old_mean, old_std, mean, std).mean().item()
+    return {"g": g, "x": x, "xHx": xHx, "alpha": alpha, "step_dir": step_dir, "kl": kl, "loss_actor": loss_pi.mean().item()}
+
+
 # --------------------------------------------------------------------------------------
 # vectorised-over-envs restatement of gae_dual for full-size checks (same sequential
 # arithmetic per env: separate fp32 mul/add/sub for delta, separate fp64 mul/add for the

@@ -27,11 +27,13 @@ ALGO_CFG = {
 }
 # siblings built from the same templates: ppo.py / pg.py / cppo_pid.py are ppo_lag.py with the
 # Lagrange lines removed / the clip removed / PIDLagrangian swapped in; trpo.py is trpo_lag.py without Lagrange
-for _a, _base in (("ppo", "ppo_lag"), ("pg", "ppo_lag"), ("cppo_pid", "ppo_lag"), ("trpo", "trpo_lag")):
+for _a, _base in (("ppo", "ppo_lag"), ("pg", "ppo_lag"), ("cppo_pid", "ppo_lag"), ("trpo", "trpo_lag"), ("natural_pg", "trpo_lag"),
+                  ("rcpo", "trpo_lag")):
     ALGO_CFG[_a] = dict(ALGO_CFG[_base])
 PG_FAMILY = ("ppo_lag", "focops", "ppo", "pg", "cppo_pid")   # minibatch policy-gradient updates with KL early stop
 PG_KIND = {"ppo_lag": "ppo", "ppo": "ppo", "cppo_pid": "ppo", "pg": "pg", "focops": "focops"}
-NO_LAGRANGE = ("cpo", "ppo", "pg", "trpo")
+NO_LAGRANGE = ("cpo", "ppo", "pg", "trpo", "natural_pg")
+NPG_FAMILY = ("natural_pg", "rcpo")        # trpo.py / trpo_lag.py without the line search
 
 
 def default_args(**kw):
@@ -185,7 +187,7 @@ def train(algo, args, env, max_epochs=None, hooks=None):
     else:
         epochs_run = epochs
     pol = O.OraclePolicy(D, A, cfg["hidden_sizes"])
-    trust = algo in ("cpo", "trpo_lag", "trpo")
+    trust = algo in ("cpo", "trpo_lag", "trpo") + NPG_FAMILY
     opt = O.OracleOptim(pol, lr=3e-4, critic_lr=1e-3 if trust else 3e-4, epochs=epochs)
     buf = PathBuffer(N, T, D, A, cfg["gamma"])
     lagrange = None
@@ -230,12 +232,15 @@ def train(algo, args, env, max_epochs=None, hooks=None):
             if algo == "cpo":
                 ep_costs = log.get_stats("Metrics/EpCost") - args.cost_limit
                 res = O.cpo_policy_update(pol, data, ep_costs, target_kl=cfg["target_kl"])
+            elif algo in NPG_FAMILY:
+                res = O.npg_policy_update(pol, data, mixed_advantage(), target_kl=cfg["target_kl"])
             else:
                 res = O.trpo_policy_update(pol, data, mixed_advantage(), target_kl=cfg["target_kl"])
             log.store(**{"Misc/Alpha": res["alpha"].item(), "Misc/FinalStepNorm": torch.norm(res["step_dir"]).mean().item(),
                          "Misc/xHx": res["xHx"].item(), "Misc/gradient_norm": torch.norm(res["g"]).mean().item(),
-                         "Misc/H_inv_g": res["x"].norm().item(), "Misc/AcceptanceStep": res["acceptance"],
-                         "Loss/Loss_actor": res["loss_actor"], "Train/KL": res["kl"]})
+                         "Misc/H_inv_g": res["x"].norm().item(), "Loss/Loss_actor": res["loss_actor"], "Train/KL": res["kl"]})
+            if algo not in NPG_FAMILY:
+                log.store(**{"Misc/AcceptanceStep": res["acceptance"]})
             for lr_, lc_ in O.critic_regression(pol, opt, data, batch_size=cfg["batch_size"],
                                                 learning_iters=cfg["learning_iters"], max_grad_norm=cfg["max_grad_norm"]):
                 log.store(**{"Loss/Loss_reward_critic": lr_, "Loss/Loss_cost_critic": lc_})
@@ -258,7 +263,7 @@ def train(algo, args, env, max_epochs=None, hooks=None):
                     log.log_tabular("Train/LagragianMultiplier", lagrange.lagrangian_multiplier)
                 log.log_tabular("Train/LR", opt.actor_lr())
             else:
-                if algo == "trpo_lag":
+                if algo in ("trpo_lag", "rcpo"):
                     log.log_tabular("Train/LagragianMultiplier", lagrange.lagrangian_multiplier)
                 log.log_tabular("Train/KL")
             for k in ("Loss/Loss_reward_critic", "Loss/Loss_cost_critic", "Loss/Loss_actor"):
@@ -269,8 +274,8 @@ def train(algo, args, env, max_epochs=None, hooks=None):
             log.log_tabular("Value/RewardAdv", data["adv_r"].mean().item())
             log.log_tabular("Value/CostAdv", data["adv_c"].mean().item())
             if trust:
-                for k in ("Misc/Alpha", "Misc/FinalStepNorm", "Misc/xHx", "Misc/gradient_norm", "Misc/H_inv_g",
-                          "Misc/AcceptanceStep"):
+                for k in ("Misc/Alpha", "Misc/FinalStepNorm", "Misc/xHx", "Misc/gradient_norm", "Misc/H_inv_g") + \
+                        (() if algo in NPG_FAMILY else ("Misc/AcceptanceStep",)):
                     log.log_tabular(k)
             log.dump_tabular()
     return pol, log, times

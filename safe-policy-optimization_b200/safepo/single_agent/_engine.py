@@ -575,8 +575,29 @@ class TrustRegionUpdate:
                 "Loss/Loss_actor": loss_pi, "Train/KL": final_kl, "step_frac": step_frac, "stale_sumsq": sc[2].to(self.device)}
 
 
+    def run_npg(self, data, advantage):
+        """natural_pg.py:355-387 / rcpo.py: the TRPO direction at full length, no line search."""
+        pol, kl_target = self.policy, self.cfg["target_kl"]
+        theta_old = pol.actor_flat().clone()
+        loss0 = self._grad(data, advantage, self.g)
+        self._old_dist(data)
+        self._cg(data, self.g, self.x)
+        self._fvp(data, self.x, self.Fx)
+        sc = torch.stack([torch.dot(self.x, self.Fx), loss0[0], torch.dot(self.g, self.g), torch.dot(self.x, self.x)]).cpu()
+        xHx = sc[0]
+        assert torch.isfinite(self.x).all(), "x is not finite"
+        assert xHx.item() >= 0, "xHx is negative"
+        alpha = torch.sqrt(2 * kl_target / (xHx + 1e-8))
+        step = self.x * alpha.item()
+        pol.actor_flat().copy_(theta_old + step)
+        o = self._eval(data, advantage, None)           # KL(old || new).mean() at the new parameters
+        return {"Misc/Alpha": alpha.item(), "Misc/FinalStepNorm": float(torch.norm(step)), "Misc/xHx": xHx.item(),
+                "Misc/gradient_norm": float(sc[2].sqrt()), "Misc/H_inv_g": float(sc[3].sqrt()),
+                "Loss/Loss_actor": -float(sc[1]), "Train/KL": float(o[2]), "stale_sumsq": sc[2].to(self.device)}
+
+
 def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False):
-    """main() of cpo.py / trpo_lag.py."""
+    """main() of cpo.py / trpo_lag.py and their siblings trpo.py / natural_pg.py / rcpo.py."""
     seed_all(args.seed)
     if args.device != "cuda":
         raise L.SpoError("this build has no CPU path: run with --device cuda")
@@ -592,7 +613,7 @@ def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False)
     buffer = VectorizedOnPolicyBuffer(obs_space, act_space, size=T, device=device, num_envs=args.num_envs,
                                       gamma=config["gamma"], gae_mode=getattr(args, "gae", "scan"))
     lagrange = None
-    if algo == "trpo_lag":
+    if algo in ("trpo_lag", "rcpo"):
         lagrange = Lagrange(args.cost_limit, args.lagrangian_multiplier_init, args.lagrangian_multiplier_lr)
     dict_args = dict(vars(args))
     dict_args.update(config)
@@ -610,13 +631,13 @@ def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False)
     for epoch in range(n_epochs):
         t_roll = roll.run(T)
         t1 = time.time()
-        if algo == "trpo_lag":
+        if algo in ("trpo_lag", "rcpo"):
             lagrange.update_lagrange_multiplier(logger.get_stats("Metrics/EpCost"))
             data = buffer.get(lagrange.lagrangian_multiplier)
-            res = trust.run_trpo(data, data["adv"])
-        elif algo == "trpo":                       # trpo.py:361: advantage = adv_r
+            res = trust.run_trpo(data, data["adv"]) if algo == "trpo_lag" else trust.run_npg(data, data["adv"])
+        elif algo in ("trpo", "natural_pg"):       # trpo.py:361: advantage = adv_r
             data = buffer.get(0.0)
-            res = trust.run_trpo(data, data["adv"])
+            res = trust.run_trpo(data, data["adv"]) if algo == "trpo" else trust.run_npg(data, data["adv"])
         else:
             data = buffer.get(0.0)
             ep_costs = logger.get_stats("Metrics/EpCost") - args.cost_limit
@@ -625,7 +646,7 @@ def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False)
         buffer.reset_segments()
         torch.cuda.synchronize()
         t_upd = time.time() - t1
-        timings.append({"rollout": t_roll, "update": t_upd, "steps": cres["steps"], "acceptance": res["Misc/AcceptanceStep"]})
+        timings.append({"rollout": t_roll, "update": t_upd, "steps": cres["steps"], "acceptance": res.get("Misc/AcceptanceStep")})
         logger.store(**{k: v for k, v in res.items() if k.startswith(("Misc/", "Loss/", "Train/"))})
         logger.store(**{"Loss/Loss_reward_critic": cres["loss_r"], "Loss/Loss_cost_critic": cres["loss_c"]})
         if not logger.logged:
@@ -633,7 +654,7 @@ def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False)
                 logger.log_tabular(k)
             logger.log_tabular("Train/Epoch", epoch + 1)
             logger.log_tabular("Train/TotalSteps", (epoch + 1) * args.steps_per_epoch)
-            if algo == "trpo_lag":
+            if lagrange is not None:
                 logger.log_tabular("Train/LagragianMultiplier", lagrange.lagrangian_multiplier)
             logger.log_tabular("Train/KL")
             for k in ("Loss/Loss_reward_critic", "Loss/Loss_cost_critic", "Loss/Loss_actor"):
@@ -643,7 +664,8 @@ def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False)
             logger.log_tabular("Time/Total", t_roll + t_upd)
             logger.log_tabular("Value/RewardAdv", data["adv_r"].mean().item())
             logger.log_tabular("Value/CostAdv", data["adv_c"].mean().item())
-            for k in ("Misc/Alpha", "Misc/FinalStepNorm", "Misc/xHx", "Misc/gradient_norm", "Misc/H_inv_g", "Misc/AcceptanceStep"):
+            for k in ("Misc/Alpha", "Misc/FinalStepNorm", "Misc/xHx", "Misc/gradient_norm", "Misc/H_inv_g") + \
+                    (() if algo in ("natural_pg", "rcpo") else ("Misc/AcceptanceStep",)):
                 logger.log_tabular(k)
             logger.dump_tabular()
             if (epoch + 1) % 100 == 0 or epoch == 0:
