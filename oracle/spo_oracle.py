@@ -570,8 +570,11 @@ def cpo_step_direction(x, p, xHx, g, b, ep_costs, target_kl):
     return step, case, lambda_star, nu_star, alpha
 
 
-def cpo_policy_update(pol, data, ep_costs, target_kl=0.01, cg_iters=15, search_steps=15, step_fraction=0.8):
-    """cpo.py:351-519 (actor part).  Returns a dict of the logged / decided quantities."""
+def cpo_policy_update(pol, data, ep_costs, target_kl=0.01, cg_iters=15, search_steps=15, step_fraction=0.8, variant="cpo"):
+    """cpo.py:351-519 (actor part).  Returns a dict of the logged / decided quantities.
+    variant="pcpo": pcpo.py:371,392-401 -- the case analysis is replaced by the projection step
+    sqrt(2 delta / (q+1e-8)) * F x  -  max(0, (sqrt(2 delta / q) r + c) / s) * p   (F x, not x: the reference's
+    ``H_inv_g = fvp(x)``), optim_case 0, and the line search runs up to 200 steps (pcpo.py:44)."""
     obs, act, logp_old = data["obs"], data["act"], data["log_prob"]
     for p_ in pol.params("actor"):
         p_.grad = None
@@ -592,7 +595,15 @@ def cpo_policy_update(pol, data, ep_costs, target_kl=0.01, cg_iters=15, search_s
     loss_pi_c.backward()
     b = flat_grads(pol)
     p = conjugate_gradients(Avp, b, cg_iters)
-    step_dir, case, lambda_star, nu_star, alpha = cpo_step_direction(x, p, xHx, g, b, ep_costs, target_kl)
+    if variant == "pcpo":
+        Fx = Avp(x)
+        q, r, s_ = xHx, g.dot(p), b.dot(p)
+        alpha = torch.sqrt(2 * target_kl / (xHx + 1e-8))
+        step_dir = (torch.sqrt(2 * target_kl / (q + 1e-8)) * Fx
+                    - torch.clamp_min((torch.sqrt(2 * target_kl / q) * r + ep_costs) / s_, torch.tensor(0.0)) * p)
+        case, lambda_star, nu_star = 0, None, None
+    else:
+        step_dir, case, lambda_star, nu_star, alpha = cpo_step_direction(x, p, xHx, g, b, ep_costs, target_kl)
     step_frac = 1.0
     theta_old = flat_params(pol)
     expected = g.dot(step_dir)

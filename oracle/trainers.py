@@ -28,11 +28,11 @@ ALGO_CFG = {
 # siblings built from the same templates: ppo.py / pg.py / cppo_pid.py are ppo_lag.py with the
 # Lagrange lines removed / the clip removed / PIDLagrangian swapped in; trpo.py is trpo_lag.py without Lagrange
 for _a, _base in (("ppo", "ppo_lag"), ("pg", "ppo_lag"), ("cppo_pid", "ppo_lag"), ("trpo", "trpo_lag"), ("natural_pg", "trpo_lag"),
-                  ("rcpo", "trpo_lag")):
+                  ("rcpo", "trpo_lag"), ("pcpo", "cpo")):
     ALGO_CFG[_a] = dict(ALGO_CFG[_base])
 PG_FAMILY = ("ppo_lag", "focops", "ppo", "pg", "cppo_pid")   # minibatch policy-gradient updates with KL early stop
 PG_KIND = {"ppo_lag": "ppo", "ppo": "ppo", "cppo_pid": "ppo", "pg": "pg", "focops": "focops"}
-NO_LAGRANGE = ("cpo", "ppo", "pg", "trpo", "natural_pg")
+NO_LAGRANGE = ("cpo", "pcpo", "ppo", "pg", "trpo", "natural_pg")
 NPG_FAMILY = ("natural_pg", "rcpo")        # trpo.py / trpo_lag.py without the line search
 
 
@@ -187,7 +187,7 @@ def train(algo, args, env, max_epochs=None, hooks=None):
     else:
         epochs_run = epochs
     pol = O.OraclePolicy(D, A, cfg["hidden_sizes"])
-    trust = algo in ("cpo", "trpo_lag", "trpo") + NPG_FAMILY
+    trust = algo in ("cpo", "pcpo", "trpo_lag", "trpo") + NPG_FAMILY
     opt = O.OracleOptim(pol, lr=3e-4, critic_lr=1e-3 if trust else 3e-4, epochs=epochs)
     buf = PathBuffer(N, T, D, A, cfg["gamma"])
     lagrange = None
@@ -229,9 +229,10 @@ def train(algo, args, env, max_epochs=None, hooks=None):
                 log.store(**{"Loss/Loss_reward_critic": lr_, "Loss/Loss_cost_critic": lc_, "Loss/Loss_actor": lp_})
             extra = {"Train/StopIter": res["stop_iter"], "Train/KL": res["kl"]}
         else:
-            if algo == "cpo":
+            if algo in ("cpo", "pcpo"):
                 ep_costs = log.get_stats("Metrics/EpCost") - args.cost_limit
-                res = O.cpo_policy_update(pol, data, ep_costs, target_kl=cfg["target_kl"])
+                res = O.cpo_policy_update(pol, data, ep_costs, target_kl=cfg["target_kl"], variant=algo,
+                                          search_steps=200 if algo == "pcpo" else 15)
             elif algo in NPG_FAMILY:
                 res = O.npg_policy_update(pol, data, mixed_advantage(), target_kl=cfg["target_kl"])
             else:

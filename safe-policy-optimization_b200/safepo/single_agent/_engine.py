@@ -443,8 +443,10 @@ class TrustRegionUpdate:
         self.old_log_std.copy_(pol.flat[: pol.act_dim])
 
     # -- CPO --
-    def run_cpo(self, data, ep_costs):
-        """cpo.py:351-519.  ep_costs = Jc - cost_limit (python float)."""
+    def run_cpo(self, data, ep_costs, variant="cpo"):
+        """cpo.py:351-519.  ep_costs = Jc - cost_limit (python float).
+        variant="pcpo" (pcpo.py:371,392-401): projection step instead of the case analysis, optim_case 0,
+        up to 200 line-search steps (pcpo.py:44)."""
         pol, kl_target = self.policy, self.cfg["target_kl"]
         theta_old = pol.actor_flat().clone()
         loss_r = self._grad(data, data["adv_r"], self.g)            # g = -grad(loss_pi_r) = grad mean(ratio*adv_r)
@@ -462,7 +464,14 @@ class TrustRegionUpdate:
         assert xHx.item() >= 0, "xHx is negative"
         alpha = torch.sqrt(2 * kl_target / (xHx + 1e-8))
         q = xHx
-        if bb <= 1e-6 and ep_costs < 0:
+        search_steps = self.SEARCH_STEPS
+        if variant == "pcpo":
+            # sqrt(2 delta / (q + 1e-8)) * F x  -  max(0, (sqrt(2 delta / q) r + c) / s) * p   (F x: the reference's fvp(x))
+            case, search_steps = 0, 200
+            c_g = torch.sqrt(2 * kl_target / (q + 1e-8)).item()
+            c_p = torch.clamp_min((torch.sqrt(2 * kl_target / q) * r + ep_costs) / s, torch.tensor(0.0)).item()
+            step = c_g * self.Fx - c_p * self.p
+        elif bb <= 1e-6 and ep_costs < 0:
             A_, B_, case = torch.zeros(1), torch.zeros(1), 4
         else:
             assert torch.isfinite(r).all() and torch.isfinite(s).all(), "r/s not finite"
@@ -478,7 +487,9 @@ class TrustRegionUpdate:
             else:
                 case = 0
                 self._log("Alert! Attempting infeasible recovery!", "red")
-        if case in (3, 4):
+        if variant == "pcpo":
+            pass
+        elif case in (3, 4):
             nu_star, lambda_star = torch.zeros(1), 1 / (alpha + 1e-8)
             step = alpha.item() * self.x
         elif case in (1, 2):
@@ -499,7 +510,7 @@ class TrustRegionUpdate:
             step = -nu_star.item() * self.p
         step_frac, acceptance, accepted, kl = 1.0, 0, False, 0.0
         expected = float(torch.dot(self.g, step))
-        for i in range(self.SEARCH_STEPS):
+        for i in range(search_steps):
             pol.actor_flat().copy_(theta_old + step_frac * step)
             acceptance = i + 1
             o = self._eval(data, data["adv_r"], data["adv_c"])
@@ -641,7 +652,7 @@ def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False)
         else:
             data = buffer.get(0.0)
             ep_costs = logger.get_stats("Metrics/EpCost") - args.cost_limit
-            res = trust.run_cpo(data, ep_costs)
+            res = trust.run_cpo(data, ep_costs, variant="pcpo" if algo == "pcpo" else "cpo")
         cres = critics.run(data, res["stale_sumsq"])
         buffer.reset_segments()
         torch.cuda.synchronize()

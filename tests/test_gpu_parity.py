@@ -608,7 +608,7 @@ def test_linesearch_eval_vs_oracle(golden):
         assert close(got, want, rtol=2e-5, atol=1e-7)[0], (float(got), float(want))
 
 
-@pytest.mark.parametrize("algo", ["cpo", "trpo_lag", "trpo", "natural_pg", "rcpo"])
+@pytest.mark.parametrize("algo", ["cpo", "trpo_lag", "trpo", "natural_pg", "rcpo", "pcpo"])
 def test_trust_region_trainer_tracks_oracle(tmp_path, algo):
     import csv
     import importlib
@@ -616,7 +616,7 @@ def test_trust_region_trainer_tracks_oracle(tmp_path, algo):
     from safepo.utils.config import single_agent_args
     mod = importlib.import_module(f"safepo.single_agent.{algo}")
     N, T, L_ep = 5, 160, 40
-    task = "SafetyCarButton1-v0" if algo == "cpo" else "SafetyPointGoal1-v0"
+    task = "SafetyCarButton1-v0" if algo in ("cpo", "pcpo") else "SafetyPointGoal1-v0"
     argv = ["--seed", "5", "--num-envs", str(N), "--steps-per-epoch", str(N * T), "--total-steps", str(2 * N * T), "--task", task,
             "--rng", "host", "--gae", "exact", "--log-dir", str(tmp_path)]
     args, _ = single_agent_args(argv)
