@@ -153,7 +153,10 @@ typedef enum spo_loss_kind {
   SPO_LOSS_PPO_CLIP = 0,   /* ppo_lag.py:315-319 */
   SPO_LOSS_FOCOPS = 1,     /* focops.py:323-337 ([B,1]x[B] broadcast semantics) */
   SPO_LOSS_CRITIC_ONLY = 2,/* cpo.py:543-571, trpo_lag.py:466-494 */
-  SPO_LOSS_PG = 3          /* pg.py:303-309: -(ratio * adv).mean(), the surrogate without the clip */
+  SPO_LOSS_PG = 3,         /* pg.py:303-309: -(ratio * adv).mean(), the surrogate without the clip */
+  SPO_LOSS_CUP_PROJECTION = 4 /* cup.py:355-404, second stage: ACTOR ONLY (critics untouched, clip norm over the actor),
+                               * loss (c * ratio * adv [B] + KL(new||old) [B,1]).mean() with c passed in hp->focops_lam
+                               * (c = lambda * (1 - gamma*0.95) / (1 - gamma)); needs old_mean/old_std, batch <= 64 */
 } spo_loss_kind;
 
 typedef struct spo_batch {

@@ -408,6 +408,38 @@ def pg_update(pol, opt, data, advantage, kind="ppo", batch_size=64, learning_ite
     return {"stop_iter": update_counts, "kl": final_kl, "losses": losses}
 
 
+def cup_second_stage(pol, opt, data, lam, gamma=0.99, cup_lambda=0.95, batch_size=64, learning_iters=40, target_kl=0.02,
+                     max_grad_norm=40.0, perms=None):
+    """cup.py:355-404: the projection stage.  Actor only (its optimizer, its own grad-norm clip); the loss
+    (lam * coef * ratio * adv_c [B] + KL(new || old) [B,1]).mean() broadcasts to [B,B] like FOCOPS."""
+    S = data["obs"].shape[0]
+    with torch.no_grad():
+        old_mean, old_std = actor_mean_std(pol, data["obs"])
+        old_mean, old_std = old_mean.clone(), old_std.clone()
+    old_std_full = old_std.expand_as(old_mean).clone()
+    advantage = data["adv_c"]
+    coef = (1 - gamma * cup_lambda) / (1 - gamma)
+    update_counts, final_kl = 0, None
+    for it in range(learning_iters):
+        perm = perms[it] if perms is not None else dataloader_perm(S)
+        for s in range(0, S, batch_size):
+            idx = perm[s:s + batch_size]
+            mean, std = actor_mean_std(pol, data["obs"][idx])
+            logp = normal_log_prob(data["act"][idx], mean, std).sum(dim=-1)
+            ratio = torch.exp(logp - data["log_prob"][idx])
+            temp_kl = normal_kl(mean, std, old_mean[idx], old_std_full[idx]).sum(-1, keepdim=True)
+            loss = (lam * coef * ratio * advantage[idx] + temp_kl).mean()
+            opt.actor.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(pol.params("actor"), max_grad_norm)
+            opt.actor.step()
+        final_kl = full_batch_kl(pol, data["obs"], old_mean, old_std)
+        update_counts += 1
+        if final_kl > target_kl:
+            break
+    return {"stop_iter": update_counts, "kl": final_kl}
+
+
 def critic_regression(pol, opt, data, batch_size=128, learning_iters=10, max_grad_norm=40.0, perms=None):
     """cpo.py:534-571 / trpo_lag.py:457-494.  The joint clip runs over *all* parameters,
     so whatever .grad the actor still holds enters the norm (Appendix A6)."""

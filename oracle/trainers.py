@@ -28,10 +28,11 @@ ALGO_CFG = {
 # siblings built from the same templates: ppo.py / pg.py / cppo_pid.py are ppo_lag.py with the
 # Lagrange lines removed / the clip removed / PIDLagrangian swapped in; trpo.py is trpo_lag.py without Lagrange
 for _a, _base in (("ppo", "ppo_lag"), ("pg", "ppo_lag"), ("cppo_pid", "ppo_lag"), ("trpo", "trpo_lag"), ("natural_pg", "trpo_lag"),
-                  ("rcpo", "trpo_lag"), ("pcpo", "cpo")):
+                  ("rcpo", "trpo_lag"), ("pcpo", "cpo"), ("cup", "ppo_lag")):
     ALGO_CFG[_a] = dict(ALGO_CFG[_base])
-PG_FAMILY = ("ppo_lag", "focops", "ppo", "pg", "cppo_pid")   # minibatch policy-gradient updates with KL early stop
-PG_KIND = {"ppo_lag": "ppo", "ppo": "ppo", "cppo_pid": "ppo", "pg": "pg", "focops": "focops"}
+PG_FAMILY = ("ppo_lag", "focops", "ppo", "pg", "cppo_pid", "cup")   # minibatch policy-gradient updates with KL early stop
+PG_KIND = {"ppo_lag": "ppo", "ppo": "ppo", "cppo_pid": "ppo", "pg": "pg", "focops": "focops", "cup": "ppo"}
+CUP_LAMBDA, CUP_NU = 0.95, 0.20            # cup.py:45-46
 NO_LAGRANGE = ("cpo", "pcpo", "ppo", "pg", "trpo", "natural_pg")
 NPG_FAMILY = ("natural_pg", "rcpo")        # trpo.py / trpo_lag.py without the line search
 
@@ -195,7 +196,7 @@ def train(algo, args, env, max_epochs=None, hooks=None):
         lagrange = O.OraclePIDLagrange(args.cost_limit, args.lagrangian_multiplier_init)      # cppo_pid.py:128-131
     elif algo not in NO_LAGRANGE:
         lagrange = O.OracleLagrange(args.cost_limit, args.lagrangian_multiplier_init, args.lagrangian_multiplier_lr,
-                                    upper_bound=2.0 if algo == "focops" else None)
+                                    upper_bound=2.0 if algo == "focops" else (CUP_NU if algo == "cup" else None))
     log = StatLog()
     deques = (deque(maxlen=50), deque(maxlen=50), deque(maxlen=50))
     obs, _ = env.reset()
@@ -221,13 +222,18 @@ def train(algo, args, env, max_epochs=None, hooks=None):
             return adv
 
         if algo in PG_FAMILY:
-            advantage = mixed_advantage()
+            advantage = data["adv_r"] if algo == "cup" else mixed_advantage()      # cup.py:284: first stage = plain PPO
             res = O.pg_update(pol, opt, data, advantage, kind=PG_KIND[algo],
                               batch_size=cfg["batch_size"], learning_iters=cfg["learning_iters"],
                               target_kl=cfg["target_kl"], max_grad_norm=cfg["max_grad_norm"])
             for lr_, lc_, lp_ in res["losses"]:
                 log.store(**{"Loss/Loss_reward_critic": lr_, "Loss/Loss_cost_critic": lc_, "Loss/Loss_actor": lp_})
             extra = {"Train/StopIter": res["stop_iter"], "Train/KL": res["kl"]}
+            if algo == "cup":
+                res2 = O.cup_second_stage(pol, opt, data, lagrange.lagrangian_multiplier, gamma=cfg["gamma"], cup_lambda=CUP_LAMBDA,
+                                          batch_size=cfg["batch_size"], learning_iters=cfg["learning_iters"],
+                                          target_kl=cfg["target_kl"], max_grad_norm=cfg["max_grad_norm"])
+                extra.update({"Train/SeconStageStopIter": res2["stop_iter"], "Train/KL": res2["kl"]})
         else:
             if algo in ("cpo", "pcpo"):
                 ep_costs = log.get_stats("Metrics/EpCost") - args.cost_limit
@@ -259,6 +265,8 @@ def train(algo, args, env, max_epochs=None, hooks=None):
             log.log_tabular("Train/TotalSteps", (epoch + 1) * args.steps_per_epoch)
             if algo in PG_FAMILY:
                 log.log_tabular("Train/StopIter", extra["Train/StopIter"])
+                if algo == "cup":
+                    log.log_tabular("Train/SeconStageStopIter", extra["Train/SeconStageStopIter"])
                 log.log_tabular("Train/KL", extra["Train/KL"])
                 if lagrange is not None:
                     log.log_tabular("Train/LagragianMultiplier", lagrange.lagrangian_multiplier)

@@ -68,6 +68,7 @@ struct UpdArgs {
   const int64_t* perm;
   int64_t perm_len;
   int batch, kind, D, A;
+  int actor_only;   // CUP projection stage: the critic CTAs only join the barriers
   spo_hparams hp;
   spo_update_ctrl* ctrl;
   spo_comm comm;   // world <= 1: single GPU
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   const bool idle = rank >= 3;
   const int net = idle ? 2 : static_cast<int>(rank);
   const bool is_actor = (net == 0) && !idle;
-  const bool active = !idle && !(is_actor && a.kind == SPO_LOSS_CRITIC_ONLY);
+  const bool active = !idle && !(is_actor && a.kind == SPO_LOSS_CRITIC_ONLY) && !(!is_actor && a.actor_only);
   const SpoNetOff off = spo_net_off(D, A, net);
   const int O = off.out;
   const SmallMap sm{O, is_actor ? A : 0};
@@ -1108,11 +1109,11 @@ extern "C" int spo_pg_update_dp(const spo_dims* d, float* params, float* adam_m,
   SPO_REQUIRE(params && adam_m && adam_v && adam_t && data && perm && hp && ctrl, SPO_ERR_INVALID_ARG, "spo_pg_update: null argument");
   SPO_REQUIRE(batch > 0 && perm_len > 0 && perm_len <= data->count, SPO_ERR_INVALID_ARG,
               "spo_pg_update: batch=%d perm_len=%lld count=%lld", batch, (long long)perm_len, (long long)data->count);
-  SPO_REQUIRE(kind >= SPO_LOSS_PPO_CLIP && kind <= SPO_LOSS_PG, SPO_ERR_INVALID_ARG, "spo_pg_update: kind=%d", (int)kind);
+  SPO_REQUIRE(kind >= SPO_LOSS_PPO_CLIP && kind <= SPO_LOSS_CUP_PROJECTION, SPO_ERR_INVALID_ARG, "spo_pg_update: kind=%d", (int)kind);
   SPO_REQUIRE(data->obs && data->target_r && data->target_c, SPO_ERR_INVALID_ARG, "spo_pg_update: batch obs/targets null");
   if (kind != SPO_LOSS_CRITIC_ONLY)
     SPO_REQUIRE(data->act && data->logp && data->adv, SPO_ERR_INVALID_ARG, "spo_pg_update: actor loss needs act/logp/adv");
-  if (kind == SPO_LOSS_FOCOPS) {
+  if (kind == SPO_LOSS_FOCOPS || kind == SPO_LOSS_CUP_PROJECTION) {
     SPO_REQUIRE(data->old_mean && data->old_std, SPO_ERR_INVALID_ARG, "spo_pg_update: FOCOPS needs old_mean/old_std");
     SPO_REQUIRE(batch <= SPO_ROWS, SPO_ERR_UNSUPPORTED, "spo_pg_update: FOCOPS supports batch <= %d (got %d)", SPO_ROWS, batch);
   }
@@ -1120,6 +1121,14 @@ extern "C" int spo_pg_update_dp(const spo_dims* d, float* params, float* adam_m,
   a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.adam_t = adam_t;
   a.data = *data; a.perm = perm; a.perm_len = perm_len; a.batch = batch; a.kind = kind;
   a.D = d->obs_dim; a.A = d->act_dim; a.hp = *hp; a.ctrl = ctrl;
+  if (kind == SPO_LOSS_CUP_PROJECTION) {
+    // (c * ratio * adv [B] + kl [B,1]).mean() = mean(kl) + c * mean(ratio * adv): the FOCOPS loss
+    // (kl - ratio * adv / lam) * 1(kl <= delta) with delta = inf (mask 1) and 1/lam = -c
+    a.kind = SPO_LOSS_FOCOPS;
+    a.actor_only = 1;
+    a.hp.focops_kl = INFINITY;
+    a.hp.focops_lam = -1.f / hp->focops_lam;   // c = 0 -> -inf -> 1/lam = -0
+  }
   if (kind == SPO_LOSS_PG) {
     // the unclipped surrogate is the clipped one with an unbounded clip range: clamp(ratio) == ratio, the
     // min() keeps the first branch, value and gradient are those of pg.py:309 bit for bit

@@ -57,7 +57,7 @@ CTRL_DTYPE = [("loss_sum", "<f8", 3), ("kl_sum", "<f8"), ("steps", "<i8"), ("sto
 CTRL_EXTRA_SUMSQ_F32_INDEX = 14  # byte offset 56
 CTRL_KL_SUM_F64_INDEX = 3        # byte offset 24
 
-LOSS_PPO_CLIP, LOSS_FOCOPS, LOSS_CRITIC_ONLY, LOSS_PG = 0, 1, 2, 3
+LOSS_PPO_CLIP, LOSS_FOCOPS, LOSS_CRITIC_ONLY, LOSS_PG, LOSS_CUP_PROJECTION = 0, 1, 2, 3, 4
 
 _lib = None
 

@@ -278,11 +278,17 @@ class PolicyGradientUpdate:
         self.old_std_full = None
         self.launches = 0
 
-    def run(self, data, perms=None, refresh_old=True):
+    def run(self, data, perms=None, refresh_old=True, kind=None, cup_coef=None, step_sched=True):
         """data: dict from buffer.get(lam).  Returns dict(stop_iter, kl, losses(3)).
         refresh_old=False keeps the old distribution of the previous call (tests drive the
-        loop one minibatch at a time)."""
+        loop one minibatch at a time).  kind / cup_coef: run this call with another loss kind on the same
+        optimizer state (CUP's projection stage, cup.py:355-404); step_sched=False leaves the actor's
+        LinearLR alone (it steps once per epoch, after both stages)."""
         pol, cfg, lib = self.policy, self.cfg, L.lib()
+        kind = self.kind if kind is None else kind
+        focops_lam_saved = self.hp.focops_lam
+        if kind == L.LOSS_CUP_PROJECTION:
+            self.hp.focops_lam = float(cup_coef)
         S = data["obs"].shape[0]
         d = pol.dims
         if self.old_mean is None or self.old_mean.shape[0] != S:
@@ -293,7 +299,7 @@ class PolicyGradientUpdate:
                     "spo_actor_forward")
             self.old_log_std.copy_(pol.flat[: pol.act_dim])
         old_std = None
-        if self.kind == L.LOSS_FOCOPS:
+        if kind in (L.LOSS_FOCOPS, L.LOSS_CUP_PROJECTION):
             old_std = torch.exp(self.old_log_std).expand(S, pol.act_dim).contiguous()
         batch = L.Batch(L.ptr(data["obs"]), L.ptr(data["act"]), L.ptr(data["log_prob"]), L.ptr(data["target_value_r"]),
                         L.ptr(data["target_value_c"]), L.ptr(data["adv"]), L.ptr(self.old_mean), L.ptr(old_std), S)
@@ -309,7 +315,7 @@ class PolicyGradientUpdate:
                 perm = torch.randperm(S, device=self.device)
             if self.dp is None:
                 L.check(lib.spo_pg_update(C.byref(d), L.ptr(pol.flat), L.ptr(self.adam.m), L.ptr(self.adam.v), L.ptr(self.adam.t),
-                                          C.byref(batch), L.ptr(perm), perm.numel(), cfg["batch_size"], self.kind, C.byref(self.hp),
+                                          C.byref(batch), L.ptr(perm), perm.numel(), cfg["batch_size"], kind, C.byref(self.hp),
                                           L.ptr(self.ctrl), L.stream()), "spo_pg_update")
                 L.check(lib.spo_actor_kl(C.byref(d), L.ptr(pol.flat), L.ptr(data["obs"]), L.ptr(self.old_mean),
                                          L.ptr(self.old_log_std), S, 0, cfg["target_kl"], L.ptr(self.ctrl), L.stream()),
@@ -319,7 +325,7 @@ class PolicyGradientUpdate:
                 comm = self.dp.comm_struct()
                 L.check(lib.spo_pg_update_dp(C.byref(d), L.ptr(pol.flat), L.ptr(self.adam.m), L.ptr(self.adam.v),
                                              L.ptr(self.adam.t), C.byref(batch), L.ptr(perm), perm.numel(), cfg["batch_size"],
-                                             self.kind, C.byref(self.hp), L.ptr(self.ctrl), C.byref(comm), L.stream()),
+                                             kind, C.byref(self.hp), L.ptr(self.ctrl), C.byref(comm), L.stream()),
                         "spo_pg_update_dp")
                 self.dp.advance((perm.numel() + cfg["batch_size"] - 1) // cfg["batch_size"])
                 L.check(lib.spo_actor_kl_accumulate(C.byref(d), L.ptr(pol.flat), L.ptr(data["obs"]), L.ptr(self.old_mean),
@@ -336,7 +342,9 @@ class PolicyGradientUpdate:
                     break
         c = read_ctrl(self.ctrl)
         steps = max(int(c["steps"]), 1)
-        self.sched.step()
+        self.hp.focops_lam = focops_lam_saved
+        if step_sched:
+            self.sched.step()
         return {"stop_iter": int(c["passes"]), "kl": float(c["final_kl"]),
                 "loss_r": c["loss_sum"][0] / steps, "loss_c": c["loss_sum"][1] / steps, "loss_pi": c["loss_sum"][2] / steps,
                 "steps": int(c["steps"])}
@@ -716,13 +724,14 @@ def run_policy_gradient(args, config, algo, env=None, max_epochs=None, quiet=Fal
     buffer = VectorizedOnPolicyBuffer(obs_space, act_space, size=T, device=device, num_envs=args.num_envs,
                                       gamma=config["gamma"], gae_mode=getattr(args, "gae", "scan"))
     # siblings of ppo_lag.py: ppo.py / pg.py drop the multiplier, cppo_pid.py swaps in the PID one
+    CUP_LAMBDA, CUP_NU = 0.95, 0.20       # cup.py:45-46
     if algo in ("ppo", "pg"):
         lagrange = None
     elif algo == "cppo_pid":
         lagrange = PIDLagrangian(args.cost_limit, args.lagrangian_multiplier_init)
     else:
         lagrange = Lagrange(args.cost_limit, args.lagrangian_multiplier_init, args.lagrangian_multiplier_lr,
-                            lagrangian_upper_bound=2.0 if algo == "focops" else None)
+                            lagrangian_upper_bound=2.0 if algo == "focops" else (CUP_NU if algo == "cup" else None))
     dict_args = dict(vars(args))
     dict_args.update(config)
     logger = EpochLogger(args.log_dir, seed=str(args.seed), verbose=not quiet, use_tensorboard=not quiet)
@@ -732,7 +741,8 @@ def run_policy_gradient(args, config, algo, env=None, max_epochs=None, quiet=Fal
     host_rng = getattr(args, "rng", "device") == "host"
     roll_cls = DeviceTapeRollout if getattr(args, "resident_env", False) else Rollout
     roll = roll_cls(env, policy, buffer, logger, args, device)
-    kind = {"ppo_lag": L.LOSS_PPO_CLIP, "ppo": L.LOSS_PPO_CLIP, "cppo_pid": L.LOSS_PPO_CLIP, "pg": L.LOSS_PG, "focops": L.LOSS_FOCOPS}[algo]
+    kind = {"ppo_lag": L.LOSS_PPO_CLIP, "ppo": L.LOSS_PPO_CLIP, "cppo_pid": L.LOSS_PPO_CLIP, "cup": L.LOSS_PPO_CLIP, "pg": L.LOSS_PG,
+            "focops": L.LOSS_FOCOPS}[algo]
     upd = PolicyGradientUpdate(policy, config, kind, epochs, host_rng, device, dp=dp)
     timings = []
     n_epochs = epochs if max_epochs is None else min(epochs, max_epochs)
@@ -744,8 +754,17 @@ def run_policy_gradient(args, config, algo, env=None, max_epochs=None, quiet=Fal
             lagrange.update_lagrange_multiplier(ep_costs)
         # without a multiplier the advantage is adv_r itself (ppo.py:272): (adv_r - 0 * adv_c) / 1, exactly
         lam = lagrange.lagrangian_multiplier if lagrange is not None else 0.0
-        data = buffer.get(lam, all_reduce=None if dp is None else dp.all_reduce_sum)
-        res = upd.run(data)
+        # cup.py:284: the first stage is plain PPO on adv_r; the multiplier enters the projection stage only
+        data = buffer.get(0.0 if algo == "cup" else lam, all_reduce=None if dp is None else dp.all_reduce_sum)
+        if algo == "cup":
+            res = upd.run(data, step_sched=False)
+            coef = (1 - config["gamma"] * CUP_LAMBDA) / (1 - config["gamma"])
+            data2 = dict(data)
+            data2["adv"] = data["adv_c"].reshape(-1)
+            res2 = upd.run(data2, kind=L.LOSS_CUP_PROJECTION, cup_coef=lam * coef)
+            res["second_stop_iter"], res["kl"], res["steps"] = res2["stop_iter"], res2["kl"], res["steps"] + res2["steps"]
+        else:
+            res = upd.run(data)
         buffer.reset_segments()
         torch.cuda.synchronize()
         t_upd = time.time() - t1
@@ -758,6 +777,8 @@ def run_policy_gradient(args, config, algo, env=None, max_epochs=None, quiet=Fal
             logger.log_tabular("Train/Epoch", epoch + 1)
             logger.log_tabular("Train/TotalSteps", (epoch + 1) * args.steps_per_epoch)
             logger.log_tabular("Train/StopIter", res["stop_iter"])
+            if algo == "cup":
+                logger.log_tabular("Train/SeconStageStopIter", res["second_stop_iter"])
             logger.log_tabular("Train/KL", res["kl"])
             if lagrange is not None:
                 logger.log_tabular("Train/LagragianMultiplier", lagrange.lagrangian_multiplier)

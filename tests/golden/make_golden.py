@@ -47,7 +47,7 @@ def import_reference():
     if REF not in sys.path:
         sys.path.insert(0, REF)
     mods = {}
-    for algo in ("ppo_lag", "focops", "cpo", "trpo_lag", "ppo", "pg", "cppo_pid", "trpo", "natural_pg", "rcpo", "pcpo"):
+    for algo in ("ppo_lag", "focops", "cpo", "trpo_lag", "ppo", "pg", "cppo_pid", "trpo", "natural_pg", "rcpo", "pcpo", "cup"):
         m = importlib.import_module(f"safepo.single_agent.{algo}")
         if hasattr(m, "LinearLR"):
             real = m.LinearLR
@@ -312,6 +312,8 @@ def gen_siblings(ref, out):
         "trpo": (dict(seed=10, num_envs=2, steps_per_epoch=2 * 100, total_steps=2 * 100 * 2), dict(episode_len=40, stagger=True, p_terminate=0.02)),
         "natural_pg": (dict(seed=11, num_envs=2, steps_per_epoch=2 * 100, total_steps=2 * 100 * 2), dict(episode_len=40, stagger=True, p_terminate=0.02)),
         "rcpo": (dict(seed=12, num_envs=3, steps_per_epoch=3 * 80, total_steps=3 * 80 * 2), dict(episode_len=20, stagger=True, p_terminate=0.02)),
+        "cup": (dict(seed=14, num_envs=3, steps_per_epoch=3 * 70, total_steps=3 * 70 * 3, cost_limit=0.2),
+                dict(episode_len=25, stagger=True, p_terminate=0.02)),
         "pcpo": (dict(seed=13, num_envs=3, steps_per_epoch=3 * 80, total_steps=3 * 80 * 2, task="SafetyCarButton1-v0", cost_limit=8.0),
                  dict(episode_len=20, stagger=True, p_terminate=0.02)),
     }

@@ -170,6 +170,6 @@ def test_pid_lagrangian_host_class_matches_reference(golden):
 
 def test_sibling_cli_modules_expose_reference_entry_points():
     import importlib
-    for name in ("ppo", "pg", "cppo_pid", "trpo", "natural_pg", "rcpo", "pcpo", "ppo_lag", "focops", "cpo", "trpo_lag"):
+    for name in ("ppo", "pg", "cppo_pid", "trpo", "natural_pg", "rcpo", "pcpo", "cup", "ppo_lag", "focops", "cpo", "trpo_lag"):
         m = importlib.import_module(f"safepo.single_agent.{name}")
         assert callable(m.main) and isinstance(m.default_cfg, dict) and m.default_cfg["hidden_sizes"] == [64, 64]

@@ -500,7 +500,7 @@ def test_trainer_with_device_obs_normalisation(tmp_path):
 # end to end
 # ---------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("algo", ["ppo_lag", "focops", "ppo", "pg", "cppo_pid"])
+@pytest.mark.parametrize("algo", ["ppo_lag", "focops", "ppo", "pg", "cppo_pid", "cup"])
 def test_trainer_tracks_oracle_trainer(tmp_path, algo):
     """The drop-in CLI entry (main) on the synthetic env in host-RNG (parity) mode follows
     oracle.trainers.train -- i.e. the reference's main() -- through two epochs."""
@@ -509,7 +509,7 @@ def test_trainer_tracks_oracle_trainer(tmp_path, algo):
     from safepo.utils.config import single_agent_args
     mod = importlib.import_module(f"safepo.single_agent.{algo}")
     N, T, L_ep = 6, 120, 40
-    extra = ["--cost-limit", "5.0"] if algo == "cppo_pid" else []      # a limit the synthetic costs exceed: the PID terms move
+    extra = ["--cost-limit", "5.0"] if algo == "cppo_pid" else (["--cost-limit", "0.2"] if algo == "cup" else [])   # limits the synthetic costs exceed
     argv = ["--seed", "3", "--num-envs", str(N), "--steps-per-epoch", str(N * T), "--total-steps", str(2 * N * T),
             "--rng", "host", "--gae", "exact", "--log-dir", str(tmp_path)] + extra
     args, _ = single_agent_args(argv)
@@ -530,6 +530,8 @@ def test_trainer_tracks_oracle_trainer(tmp_path, algo):
         if "Train/LagragianMultiplier" in want:
             assert float(got["Train/LagragianMultiplier"]) == pytest.approx(float(want["Train/LagragianMultiplier"]), rel=1e-5, abs=1e-8)
         assert int(float(got["Train/StopIter"])) == int(want["Train/StopIter"])
+        if algo == "cup":
+            assert int(float(got["Train/SeconStageStopIter"])) == int(want["Train/SeconStageStopIter"])
         for k in ("Loss/Loss_reward_critic", "Loss/Loss_cost_critic", "Loss/Loss_actor", "Train/KL"):
             assert float(got[k]) == pytest.approx(float(want[k]), rel=2e-3, abs=2e-5), (k, got[k], want[k])
     # first-epoch rollout (before any update) must agree to fp32 rounding: compare actor weights loosely after 2 epochs

@@ -166,7 +166,7 @@ def test_full_main_matches_reference(golden, algo):
     assert set(run["actor"].keys()) == set(pol.nets["actor"].keys())
 
 
-@pytest.mark.parametrize("algo", ["ppo", "pg", "cppo_pid", "trpo", "natural_pg", "rcpo", "pcpo"])
+@pytest.mark.parametrize("algo", ["ppo", "pg", "cppo_pid", "trpo", "natural_pg", "rcpo", "pcpo", "cup"])
 def test_sibling_main_matches_reference(golden, algo):
     """the sibling scripts (ppo_lag / trpo_lag minus Lagrange, minus the clip, with the PID
     multiplier) -- oracle.trainers.train against the reference's own main(), every logged number bit for bit."""
