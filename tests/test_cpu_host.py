@@ -173,3 +173,36 @@ def test_sibling_cli_modules_expose_reference_entry_points():
     for name in ("ppo", "pg", "cppo_pid", "trpo", "natural_pg", "rcpo", "pcpo", "cup", "ppo_lag", "focops", "cpo", "trpo_lag"):
         m = importlib.import_module(f"safepo.single_agent.{name}")
         assert callable(m.main) and isinstance(m.default_cfg, dict) and m.default_cfg["hidden_sizes"] == [64, 64]
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """bench.py --impl reference runs without a GPU and prints ONE JSON line with the keys the driver reads."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-seconds", "3", "--num-envs", "64", "--horizon", "50"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and 1 <= d["cpu_baseline"]["cores"] <= 16
+
+
+def test_bench_spo_arm_refuses_to_run_without_cuda():
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a host without CUDA")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
