@@ -30,6 +30,14 @@ __host__ __device__ inline uint32_t blk_off(int row, int col) {   // byte offset
   return ((row >> 3) * 16 + (col >> 2)) * 128 + (row & 7) * 16 + (col & 3) * 4;
 }
 constexpr uint32_t ROWGRP = 2048, COLCHK = 128;
+// alternative blocked layout for the MN-major experiments: [col/4][row/8][row%8][col%4] (row groups of one column chunk contiguous)
+__host__ __device__ inline uint32_t blk_off_alt(int row, int col) {
+  return ((col >> 2) * 8 + (row >> 3)) * 128 + (row & 7) * 16 + (col & 3) * 4;
+}
+struct MnCfg {   // descriptor parameters tried for an MN-major operand
+  int alt_layout;            // 0: blk_off, 1: blk_off_alt
+  uint32_t lbo, sbo, kstep;  // bytes
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -63,7 +71,7 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
 // X, Y: plain row-major [64][64] in global memory.  variant 0: D[m][n] = sum_k X[m][k] Y[n][k]
 //                                                   variant 1: D[m][n] = sum_k X[k][m] Y[k][n]
 //                                                   variant 2: D[m][n] = sum_k X[m][k] Y[k][n]
-__global__ void __launch_bounds__(128) tc64_kernel(const float* X, const float* Y, float* D, int variant, long long* cycles) {
+__global__ void __launch_bounds__(128) tc64_kernel(const float* X, const float* Y, float* D, int variant, long long* cycles, MnCfg mn) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* x_hi = smem;
   uint8_t* x_lo = smem + 16384;
@@ -77,10 +85,13 @@ __global__ void __launch_bounds__(128) tc64_kernel(const float* X, const float* 
     const int r = i / T, c = i % T;
     const float xv = X[i], yv = Y[i];
     const float xh = __uint_as_float(__float_as_uint(xv) & 0xFFFFE000u), yh = __uint_as_float(__float_as_uint(yv) & 0xFFFFE000u);
-    *reinterpret_cast<float*>(x_hi + blk_off(r, c)) = xv;        // the tensor core reads the top 19 bits
-    *reinterpret_cast<float*>(x_lo + blk_off(r, c)) = xv - xh;
-    *reinterpret_cast<float*>(y_hi + blk_off(r, c)) = yv;
-    *reinterpret_cast<float*>(y_lo + blk_off(r, c)) = yv - yh;
+    const bool x_mn = (variant == 1), y_mn = (variant >= 1);
+    const uint32_t xo = (x_mn && mn.alt_layout) ? blk_off_alt(r, c) : blk_off(r, c);
+    const uint32_t yo = (y_mn && mn.alt_layout) ? blk_off_alt(r, c) : blk_off(r, c);
+    *reinterpret_cast<float*>(x_hi + xo) = xv;        // the tensor core reads the top 19 bits
+    *reinterpret_cast<float*>(x_lo + xo) = xv - xh;
+    *reinterpret_cast<float*>(y_hi + yo) = yv;
+    *reinterpret_cast<float*>(y_lo + yo) = yv - yh;
   }
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
@@ -102,8 +113,8 @@ __global__ void __launch_bounds__(128) tc64_kernel(const float* X, const float* 
     const uint32_t idesc = make_idesc(T, T, a_mn, b_mn);
     // K-major operand (MN = row, K = col): LBO = column-chunk stride, SBO = row-group stride, a k-step of 8 = 2 chunks
     // MN-major operand (MN = col, K = row): LBO = row-group stride, SBO = column-chunk stride, a k-step of 8 = 1 row group
-    const uint32_t a_lbo = a_mn ? ROWGRP : COLCHK, a_sbo = a_mn ? COLCHK : ROWGRP, a_step = a_mn ? ROWGRP : 2 * COLCHK;
-    const uint32_t b_lbo = b_mn ? ROWGRP : COLCHK, b_sbo = b_mn ? COLCHK : ROWGRP, b_step = b_mn ? ROWGRP : 2 * COLCHK;
+    const uint32_t a_lbo = a_mn ? mn.lbo : COLCHK, a_sbo = a_mn ? mn.sbo : ROWGRP, a_step = a_mn ? mn.kstep : 2 * COLCHK;
+    const uint32_t b_lbo = b_mn ? mn.lbo : COLCHK, b_sbo = b_mn ? mn.sbo : ROWGRP, b_step = b_mn ? mn.kstep : 2 * COLCHK;
     uint32_t accum = 0;
     t0 = clock64();
     for (int pass = 2; pass >= 0; --pass) {   // lo*hi, hi*lo, hi*hi
@@ -157,28 +168,36 @@ int main() {
   cudaMalloc(&dX, T * T * 4); cudaMalloc(&dY, T * T * 4); cudaMalloc(&dD, T * T * 4); cudaMalloc(&dC, 3 * sizeof(long long));
   cudaMemcpy(dX, hX, T * T * 4, cudaMemcpyHostToDevice); cudaMemcpy(dY, hY, T * T * 4, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
-  for (int variant = 0; variant < 3; ++variant) {
-    cudaMemset(dD, 0, T * T * 4);
-    for (int rep = 0; rep < 2; ++rep) tc64_kernel<<<1, 128, 66 * 1024>>>(dX, dY, dD, variant, dC);
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) { printf("variant %d CUDA error: %s\n", variant, cudaGetErrorString(e)); return 1; }
-    long long cyc[3];
-    cudaMemcpy(hD, dD, T * T * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(cyc, dC, sizeof(cyc), cudaMemcpyDeviceToHost);
-    double max_abs = 0, max_ref = 0;
-    for (int m = 0; m < T; ++m)
-      for (int n = 0; n < T; ++n) {
-        double s = 0;
-        for (int k = 0; k < T; ++k) {
-          const double a = (variant == 1) ? hX[k * T + m] : hX[m * T + k];
-          const double b = (variant == 0) ? hY[n * T + k] : hY[k * T + n];
-          s += a * b;
+  // candidates for the MN-major descriptors (variant 0 ignores them).  #0 is what cute's make_umma_desc<Major::MN> derives for
+  // the no-swizzle layout ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO)); it returned zeros in the first run, hence the scan.
+  const MnCfg cands[] = {{0, ROWGRP, COLCHK, ROWGRP}, {0, COLCHK, ROWGRP, ROWGRP}, {1, COLCHK, 8 * COLCHK, COLCHK}, {1, 8 * COLCHK, COLCHK, COLCHK},
+                         {0, ROWGRP, COLCHK, 2 * ROWGRP}, {1, COLCHK, 8 * COLCHK, 2 * COLCHK}};
+  const int ncand = sizeof(cands) / sizeof(cands[0]);
+  for (int variant = 0; variant < 3; ++variant)
+    for (int ci = 0; ci < (variant == 0 ? 1 : ncand); ++ci) {
+      const MnCfg mn = cands[ci];
+      cudaMemset(dD, 0, T * T * 4);
+      for (int rep = 0; rep < 2; ++rep) tc64_kernel<<<1, 128, 66 * 1024>>>(dX, dY, dD, variant, dC, mn);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("variant %d cand %d CUDA error: %s\n", variant, ci, cudaGetErrorString(e)); return 1; }
+      long long cyc[3];
+      cudaMemcpy(hD, dD, T * T * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(cyc, dC, sizeof(cyc), cudaMemcpyDeviceToHost);
+      double max_abs = 0, max_ref = 0, sum_abs = 0;
+      for (int m = 0; m < T; ++m)
+        for (int n = 0; n < T; ++n) {
+          double sacc = 0;
+          for (int k = 0; k < T; ++k) {
+            const double a = (variant == 1) ? hX[k * T + m] : hX[m * T + k];
+            const double b = (variant == 0) ? hY[n * T + k] : hY[k * T + n];
+            sacc += a * b;
+          }
+          max_abs = fmax(max_abs, fabs(sacc - hD[m * T + n]));
+          max_ref = fmax(max_ref, fabs(sacc));
+          sum_abs += fabs(hD[m * T + n]);
         }
-        max_abs = fmax(max_abs, fabs(s - hD[m * T + n]));
-        max_ref = fmax(max_ref, fabs(s));
-      }
-    printf("variant %d: max |err| = %.3e (max |ref| = %.3f)   24 tcgen05.mma (M=64,N=64,K=8) issue -> complete: %lld cycles\n", variant, max_abs,
-           max_ref, cyc[variant]);
-  }
+      printf("variant %d cand %d (alt_layout %d lbo %u sbo %u kstep %u): max |err| = %.3e (max |ref| = %.3f, mean |D| = %.3e)   24 mma: %lld cycles\n",
+             variant, ci, mn.alt_layout, mn.lbo, mn.sbo, mn.kstep, max_abs, max_ref, sum_abs / (T * T), cyc[variant]);
+    }
   return 0;
 }
