@@ -331,12 +331,45 @@ def gen_siblings(ref, out):
     out["pid"] = dict(jc=jcs, lam=seq)
 
 
+def gen_ma_gae(ref, out):
+    """SeparatedReplayBuffer.compute_returns / compute_cost_returns (buffer.py:356-384) with a PopArt
+    value normaliser (popart.py).  The buffer methods are called unbound on a bare namespace holding exactly the
+    attributes they touch, so the arithmetic is the reference's own without building gymnasium spaces."""
+    import importlib
+    from types import SimpleNamespace
+    buf_mod = ref["buffer"]
+    popart_mod = importlib.import_module("safepo.common.popart")
+    cases = []
+    for (T, N, seed, gamma, lam) in ((8, 5, 0, 0.96, 0.95), (64, 3, 1, 0.99, 0.95), (1, 4, 2, 0.96, 0.95), (33, 16, 3, 0.96, 0.9)):
+        g = torch.Generator().manual_seed(seed)
+        pop = popart_mod.PopArt(1)
+        trained = []
+        for _ in range(3):                                   # move the running statistics off their initial zeros
+            x = torch.randn(40, 1, generator=g) * 3 + 1.5
+            trained.append((x.clone(), pop(x).clone()))
+        value_preds = torch.randn(T + 1, N, 1, generator=g)
+        cost_preds = torch.randn(T + 1, N, 1, generator=g)
+        rewards = torch.randn(T, N, 1, generator=g)
+        costs = torch.rand(T, N, 1, generator=g)
+        masks = (torch.rand(T + 1, N, 1, generator=g) > 0.15).float()
+        ns = SimpleNamespace(value_preds=value_preds.clone(), cost_preds=cost_preds.clone(), rewards=rewards, costs=costs, masks=masks,
+                             gamma=gamma, gae_lambda=lam, returns=torch.zeros(T + 1, N, 1), cost_returns=torch.zeros(T + 1, N, 1))
+        next_value, next_cost = value_preds[-1].clone(), cost_preds[-1].clone()
+        buf_mod.SeparatedReplayBuffer.compute_returns(ns, next_value, pop)
+        buf_mod.SeparatedReplayBuffer.compute_cost_returns(ns, next_cost, pop)
+        cases.append(dict(T=T, N=N, gamma=gamma, lam=lam, popart_inputs=[t[0] for t in trained], popart_outputs=[t[1] for t in trained],
+                          popart_state=(pop.running_mean.clone(), pop.running_mean_sq.clone(), pop.debiasing_term.clone()),
+                          denorm_probe=pop.denormalize(value_preds[:2]).clone(), value_preds=value_preds, cost_preds=cost_preds,
+                          rewards=rewards, costs=costs, masks=masks, returns=ns.returns.clone(), cost_returns=ns.cost_returns.clone()))
+    out["ma_gae"] = cases
+
+
 def main():
     sys.path.insert(0, ROOT)
     ref = import_reference()
     only = set(sys.argv[1:])      # e.g. `python make_golden.py siblings` regenerates one fixture
     for name, fn in (("forward", gen_forward), ("gae", gen_gae), ("lagrange", gen_lagrange), ("update", gen_update_chain),
-                     ("dataloader", gen_dataloader), ("trust", gen_trust), ("main_runs", gen_main_runs), ("siblings", gen_siblings)):
+                     ("dataloader", gen_dataloader), ("trust", gen_trust), ("main_runs", gen_main_runs), ("siblings", gen_siblings), ("ma_gae", gen_ma_gae)):
         if only and name not in only:
             continue
         out = {}

@@ -194,3 +194,20 @@ def test_pid_lagrange_matches_reference(golden):
     for jc, want in zip(c["jc"], c["lam"]):
         P.update_lagrange_multiplier(jc)
         assert P.lagrangian_multiplier == want, (jc, P.lagrangian_multiplier, want)
+
+
+def test_masked_gae_with_popart_matches_reference(golden):
+    """SURVEY 8 row G2 (MAPPO-Lag, config 5): oracle/ma_oracle.py against the reference's SeparatedReplayBuffer.compute_returns /
+    compute_cost_returns and PopArt, bit for bit: normalised outputs, running statistics, de-normalisation, both return tensors."""
+    from oracle import ma_oracle as MA
+    for c in golden("ma_gae")["ma_gae"]:
+        pop = MA.OraclePopArt(1)
+        for x, want in zip(c["popart_inputs"], c["popart_outputs"]):
+            assert torch.equal(pop.normalize(x), want)
+        for got, want in zip((pop.running_mean, pop.running_mean_sq, pop.debiasing_term), c["popart_state"]):
+            assert torch.equal(got, want)
+        assert torch.equal(pop.denormalize(c["value_preds"][:2]), c["denorm_probe"])
+        ret = MA.masked_gae(c["rewards"], c["value_preds"], c["masks"], pop, c["gamma"], c["lam"])
+        cret = MA.masked_gae(c["costs"], c["cost_preds"], c["masks"], pop, c["gamma"], c["lam"])
+        assert torch.equal(ret, c["returns"][:-1]) and torch.equal(cret, c["cost_returns"][:-1]), (c["T"], c["N"])
+        assert float(c["returns"][-1].abs().max()) == 0.0      # the reference's extra row stays zero
