@@ -34,15 +34,22 @@ constexpr uint32_t ROWGRP = 2048, COLCHK = 128;
 __host__ __device__ inline uint32_t blk_off_alt(int row, int col) {
   return ((col >> 2) * 8 + (row >> 3)) * 128 + (row & 7) * 16 + (col & 3) * 4;
 }
+// 128B-swizzled layout: [col/32][row][col%32] (128-byte rows, 8 KB per 32-column atom), 16-byte chunk index XORed with row % 8.
+// As K-major (MN = row, K = col): SBO = 1024 (8-row groups), a k-step of 8 advances the start address by 32 B inside the atom and
+// by 8192 B to the next atom.  As MN-major (MN = col, K = row): LBO = 8192 (next 32-column atom), SBO = 1024, k-step = 1024.
+__host__ __device__ inline uint32_t sw128_off(int row, int col) {
+  uint32_t b = (col >> 5) * 8192 + row * 128 + (col & 31) * 4;
+  return b ^ (((b >> 7) & 7) << 4);
+}
 struct MnCfg {   // descriptor parameters tried for an MN-major operand
-  int alt_layout;            // 0: blk_off, 1: blk_off_alt
+  int alt_layout;            // 0: blk_off, 1: blk_off_alt, 2: sw128_off (then ALL operands use the swizzled layout, layout_type = 2)
   uint32_t lbo, sbo, kstep;  // bytes
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type = 0) {
+  uint64_t d = static_cast<uint64_t>(layout_type & 7) << 61;   // 0 none, 1 128B_BASE32B, 2 128B, 4 64B, 6 32B
   d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
   d |= static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32;
@@ -86,8 +93,8 @@ __global__ void __launch_bounds__(128) tc64_kernel(const float* X, const float* 
     const float xv = X[i], yv = Y[i];
     const float xh = __uint_as_float(__float_as_uint(xv) & 0xFFFFE000u), yh = __uint_as_float(__float_as_uint(yv) & 0xFFFFE000u);
     const bool x_mn = (variant == 1), y_mn = (variant >= 1);
-    const uint32_t xo = (x_mn && mn.alt_layout) ? blk_off_alt(r, c) : blk_off(r, c);
-    const uint32_t yo = (y_mn && mn.alt_layout) ? blk_off_alt(r, c) : blk_off(r, c);
+    const uint32_t xo = mn.alt_layout == 2 ? sw128_off(r, c) : ((x_mn && mn.alt_layout) ? blk_off_alt(r, c) : blk_off(r, c));
+    const uint32_t yo = mn.alt_layout == 2 ? sw128_off(r, c) : ((y_mn && mn.alt_layout) ? blk_off_alt(r, c) : blk_off(r, c));
     *reinterpret_cast<float*>(x_hi + xo) = xv;        // the tensor core reads the top 19 bits
     *reinterpret_cast<float*>(x_lo + xo) = xv - xh;
     *reinterpret_cast<float*>(y_hi + yo) = yv;
@@ -115,13 +122,24 @@ __global__ void __launch_bounds__(128) tc64_kernel(const float* X, const float* 
     // MN-major operand (MN = col, K = row): LBO = row-group stride, SBO = column-chunk stride, a k-step of 8 = 1 row group
     const uint32_t a_lbo = a_mn ? mn.lbo : COLCHK, a_sbo = a_mn ? mn.sbo : ROWGRP, a_step = a_mn ? mn.kstep : 2 * COLCHK;
     const uint32_t b_lbo = b_mn ? mn.lbo : COLCHK, b_sbo = b_mn ? mn.sbo : ROWGRP, b_step = b_mn ? mn.kstep : 2 * COLCHK;
+    const bool sw = mn.alt_layout == 2;
     uint32_t accum = 0;
     t0 = clock64();
     for (int pass = 2; pass >= 0; --pass) {   // lo*hi, hi*lo, hi*hi
       const uint8_t* ap = (pass == 2) ? x_lo : x_hi;
       const uint8_t* bp = (pass == 1) ? y_lo : y_hi;
       for (int ks = 0; ks < T / 8; ++ks) {
-        mma_tf32(tmem_d, make_desc(smem_u32(ap) + ks * a_step, a_lbo, a_sbo), make_desc(smem_u32(bp) + ks * b_step, b_lbo, b_sbo), idesc, accum);
+        uint64_t da, db;
+        if (!sw) {
+          da = make_desc(smem_u32(ap) + ks * a_step, a_lbo, a_sbo);
+          db = make_desc(smem_u32(bp) + ks * b_step, b_lbo, b_sbo);
+        } else {
+          // swizzled K-major: 32 B per k-step inside a 128 B atom row, next atom after 4 k-steps; LBO unused (1), SBO = 1024
+          const uint32_t koff = (ks & 3) * 32 + (ks >> 2) * 8192;
+          da = a_mn ? make_desc(smem_u32(ap) + ks * mn.kstep, mn.lbo, mn.sbo, 2) : make_desc(smem_u32(ap) + koff, 16, 1024, 2);
+          db = b_mn ? make_desc(smem_u32(bp) + ks * mn.kstep, mn.lbo, mn.sbo, 2) : make_desc(smem_u32(bp) + koff, 16, 1024, 2);
+        }
+        mma_tf32(tmem_d, da, db, idesc, accum);
         accum = 1;
       }
     }
@@ -171,11 +189,16 @@ int main() {
   // candidates for the MN-major descriptors (variant 0 ignores them).  #0 is what cute's make_umma_desc<Major::MN> derives for
   // the no-swizzle layout ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO)); it returned zeros in the first run, hence the scan.
   const MnCfg cands[] = {{0, ROWGRP, COLCHK, ROWGRP}, {0, COLCHK, ROWGRP, ROWGRP}, {1, COLCHK, 8 * COLCHK, COLCHK}, {1, 8 * COLCHK, COLCHK, COLCHK},
-                         {0, ROWGRP, COLCHK, 2 * ROWGRP}, {1, COLCHK, 8 * COLCHK, 2 * COLCHK}};
+                         {0, ROWGRP, COLCHK, 2 * ROWGRP}, {1, COLCHK, 8 * COLCHK, 2 * COLCHK},
+                         // 128B-swizzled tiles (cute: MN-major B128 = ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO))); also run for variant 0 as a check
+                         // of the swizzled K-major path
+                         {2, 8192, 1024, 1024}, {2, 1024, 8192, 1024}};
   const int ncand = sizeof(cands) / sizeof(cands[0]);
   for (int variant = 0; variant < 3; ++variant)
-    for (int ci = 0; ci < (variant == 0 ? 1 : ncand); ++ci) {
+    for (int ci = 0; ci < ncand; ++ci) {
       const MnCfg mn = cands[ci];
+      if (variant == 0 && ci != 0 && mn.alt_layout != 2) continue;   // K-major only: the no-swizzle layout once, the swizzled one once
+      if (variant == 0 && ci == ncand - 1) continue;
       cudaMemset(dD, 0, T * T * 4);
       for (int rep = 0; rep < 2; ++rep) tc64_kernel<<<1, 128, 66 * 1024>>>(dX, dY, dD, variant, dC, mn);
       cudaError_t e = cudaDeviceSynchronize();
