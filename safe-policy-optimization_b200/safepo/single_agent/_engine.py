@@ -82,6 +82,15 @@ class AdamState:
         self.t = torch.zeros(3, dtype=torch.int32, device=dev)
 
 
+def _normalizer_state(roll, env):
+    """What the reference checkpoints as "Normalizer" (ppo_lag.py:381-386: env.obs_rms): the device-side running statistics when
+    --normalize-obs is on (mean / var / count as numpy, like gymnasium's RunningMeanStd fields), else whatever the env carries."""
+    norm = getattr(roll, "obs_norm", None)
+    if norm is not None:
+        return norm.obs_rms.state_dict()
+    return getattr(env, "obs_rms", None)
+
+
 def make_ctrl(device):
     return torch.zeros(L.CTRL_BYTES, dtype=torch.uint8, device=device)
 
@@ -689,7 +698,7 @@ def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False)
             logger.dump_tabular()
             if (epoch + 1) % 100 == 0 or epoch == 0:
                 logger.torch_save(itr=epoch)
-                logger.save_state({"Normalizer": getattr(env, "obs_rms", None)}, itr=epoch)
+                logger.save_state({"Normalizer": _normalizer_state(roll, env)}, itr=epoch)
     logger.close()
     return policy, logger, timings, {"rollout": roll, "trust": trust, "critics": critics, "lagrange": lagrange, "buffer": buffer}
 
@@ -793,6 +802,6 @@ def run_policy_gradient(args, config, algo, env=None, max_epochs=None, quiet=Fal
             logger.dump_tabular()
             if (epoch + 1) % 100 == 0 or epoch == 0:
                 logger.torch_save(itr=epoch)
-                logger.save_state({"Normalizer": getattr(env, "obs_rms", None)}, itr=epoch)
+                logger.save_state({"Normalizer": _normalizer_state(roll, env)}, itr=epoch)
     logger.close()
     return policy, logger, timings, {"rollout": roll, "update": upd, "lagrange": lagrange, "buffer": buffer}
