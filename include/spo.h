@@ -132,6 +132,15 @@ int spo_gae_dual(const float* reward, const float* cost, const float* value_r, c
                  float* adv_r, float* adv_c, float* tgt_r, float* tgt_c,
                  int num_envs, int steps, int mode, void* stream);
 
+/* ---- G2 (multi-agent path, config 5): SeparatedReplayBuffer.compute_returns / compute_cost_returns
+ * (safepo/common/buffer.py:356-384): masked GAE on PopArt-de-normalised predictions, fp32 like the reference.
+ * Time-major device arrays: rewards [T][N], value_preds [T+1][N] (row T = bootstrap), masks [T+1][N],
+ * returns [T][N].  popart_mean / popart_sqrt_var: the de-biased running mean and sqrt(clamped variance) of the
+ * value normaliser (popart.py:64-74); gamma_lambda = gamma * gae_lambda as the double product python forms.
+ * (Round-1 status: compiled, first hardware run pending -- tests/test_zz_pending_gpu.py.) */
+int spo_gae_masked(const float* rewards, const float* value_preds, const float* masks, float popart_mean,
+                   float popart_sqrt_var, float gamma, double gamma_lambda, float* returns, int N, int T, void* stream);
+
 /* ---- G3 + L1: buffer.get() statistics (buffer.py:154-160) and the Lagrange mix
  * (ppo_lag.py:280-281).  stats (device, 4 doubles) = {sum adv_r, sum adv_r^2, sum adv_c,
  * count}; spo_adv_stats overwrites them (all-reduce them across ranks before apply for

@@ -118,3 +118,44 @@ extern "C" int spo_action_rescale(const float* act, int n, int act_dim, const fl
   SPO_CUDA_TRY(cudaGetLastError());
   return SPO_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Row G2 (multi-agent path, BASELINE config 5): SeparatedReplayBuffer.compute_returns / compute_cost_returns
+// (safepo/common/buffer.py:356-384) -- masked GAE on PopArt-de-normalised value predictions, fp32 throughout
+// like the reference, time-major [T(+1)][N] so one thread per env reads coalesced rows:
+//     D(x)  = x * sqrt(var) + mean                                  (popart.py:128)
+//     delta = ((r_t + (gamma * D(v_{t+1})) * m_{t+1}) - D(v_t)
+//     gae   = delta + ((gamma*lambda) * m_{t+1}) * gae
+//     ret_t = gae + D(v_t)
+// every product and sum rounded separately, in the reference's association (torch evaluates the python expression
+// left to right, scalars cast to fp32), so the sequential kernel reproduces it bit for bit.
+// STATUS: written at the end of round 1 after the GPU budget was spent -- compiled, covered by an xfail-tolerant GPU test
+// (tests/test_zz_pending_gpu.py), not yet run on hardware.
+namespace {
+__global__ void spo_gae_masked_kernel(const float* __restrict__ rewards, const float* __restrict__ vpred, const float* __restrict__ masks,
+                                      float mean, float sqrt_var, float gamma, float gamma_lambda, float* __restrict__ returns, int N, int T) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float gae = 0.f;
+  float d_next = __fadd_rn(__fmul_rn(vpred[static_cast<size_t>(T) * N + n], sqrt_var), mean);   // D(v_T): the bootstrap row
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t i = static_cast<size_t>(t) * N + n;
+    const float m = masks[i + N];
+    const float d_cur = __fadd_rn(__fmul_rn(vpred[i], sqrt_var), mean);
+    const float delta = __fsub_rn(__fadd_rn(rewards[i], __fmul_rn(__fmul_rn(gamma, d_next), m)), d_cur);
+    gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lambda, m), gae));
+    returns[i] = __fadd_rn(gae, d_cur);
+    d_next = d_cur;
+  }
+}
+}  // namespace
+
+extern "C" int spo_gae_masked(const float* rewards, const float* value_preds, const float* masks, float popart_mean, float popart_sqrt_var,
+                              float gamma, double gamma_lambda, float* returns, int N, int T, void* stream) {
+  SPO_REQUIRE(rewards && value_preds && masks && returns, SPO_ERR_INVALID_ARG, "spo_gae_masked: null argument");
+  SPO_REQUIRE(N >= 1 && T >= 1, SPO_ERR_INVALID_ARG, "spo_gae_masked: N=%d T=%d", N, T);
+  spo_gae_masked_kernel<<<(N + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(rewards, value_preds, masks, popart_mean, popart_sqrt_var,
+                                                                                     gamma, static_cast<float>(gamma_lambda), returns, N, T);
+  SPO_CUDA_TRY(cudaGetLastError());
+  return SPO_OK;
+}

@@ -129,3 +129,17 @@ class VectorizedOnPolicyBuffer:
 
     def reset_segments(self):
         self.seg_end.zero_()
+
+
+def masked_gae_returns(rewards, value_preds, masks, popart_mean, popart_sqrt_var, gamma, gae_lambda, out=None):
+    """SeparatedReplayBuffer.compute_returns / compute_cost_returns of the multi-agent path
+    (reference safepo/common/buffer.py:356-384) on the device: time-major ``rewards`` [T, N, 1], ``value_preds`` and
+    ``masks`` [T+1, N, 1] (value_preds[-1] = the bootstrap), PopArt statistics as two floats.  Returns [T, N, 1]."""
+    T, N = rewards.shape[0], rewards.shape[1]
+    if value_preds.shape[0] != T + 1 or masks.shape[0] != T + 1:
+        raise L.SpoError("value_preds / masks must have T+1 time steps")
+    if out is None:
+        out = torch.empty_like(rewards)
+    L.check(L.lib().spo_gae_masked(L.ptr(rewards), L.ptr(value_preds), L.ptr(masks), float(popart_mean), float(popart_sqrt_var),
+                                   float(gamma), float(gamma) * float(gae_lambda), L.ptr(out), N, T, L.stream()), "spo_gae_masked")
+    return out
