@@ -206,3 +206,30 @@ def test_bench_spo_arm_refuses_to_run_without_cuda():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
                          timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_the_device():
+    """Error behaviour of the C-ABI (include/spo.h): invalid arguments return a status code and leave a message in
+    spo_last_error() without launching anything -- checked here without a GPU."""
+    import ctypes as C
+    from safepo import _lib as L
+    lib = L.lib()
+    OK = 0
+    d_bad = L.dims(60, 2, hidden=32)
+    a, c, t = C.c_int(), C.c_int(), C.c_int()
+    assert lib.spo_param_count(C.byref(d_bad), C.byref(a), C.byref(c), C.byref(t)) != OK
+    assert b"hidden" in lib.spo_last_error()
+    d_big = L.dims(4096, 2)
+    assert lib.spo_param_count(C.byref(d_big), C.byref(a), C.byref(c), C.byref(t)) != OK and b"obs_dim" in lib.spo_last_error()
+    d = L.dims(60, 2)
+    assert lib.spo_param_count(C.byref(d), C.byref(a), C.byref(c), C.byref(t)) == OK and (a.value, c.value) == (8196, 8129)
+    # null pointers / empty batches
+    assert lib.spo_policy_step(C.byref(d), None, None, None, 0, 0, 0, 0, None, None, None, None, None, 0, None) != OK
+    assert b"spo_policy_step" in lib.spo_last_error()
+    assert lib.spo_gae_dual(None, None, None, None, None, None, None, 0.99, 0.94, 0.94, None, None, None, None, 4, 5, 0, None) != OK
+    assert lib.spo_adv_stats(None, None, 0, None, None) != OK and b"spo_adv_stats" in lib.spo_last_error()
+    assert lib.spo_obs_normalize(None, 4, 3, None, None, 1.0, None, 1, 1e-8, None, None) != OK
+    assert lib.spo_action_rescale(None, 4, 3, None, None, -1.0, 1.0, None, None) != OK
+    assert lib.spo_gae_masked(None, None, None, 0.0, 1.0, 0.96, 0.9, None, 4, 8, None) != OK and b"spo_gae_masked" in lib.spo_last_error()
+    assert lib.spo_actor_forward(C.byref(d), None, None, 0, None, None) != OK
+    assert lib.spo_fvp(C.byref(d), None, None, 0, None, 0.1, None, None) != OK
