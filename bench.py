@@ -18,6 +18,12 @@ One "step" = one epoch of the hot path: T=1000 fused forward/sample/store launch
           step's observations/rewards/costs/flags host->device from pinned memory and reads
           the actions back (bytes counted from the tensors copied).
 
+Both arms run on ONE set of trainer objects (policy, optimizer state, buffer): the `value`
+arm's W warm-up epochs warm every kernel of the `e2e` arm as well, which only swaps the rollout
+front end (one extra warm-up epoch covers its copy path).  A wall-clock budget
+(SPO_BENCH_BUDGET_S, default 780 s -- the driver's per-run limit is 870 s) bounds the e2e
+arm: if K more epochs would not fit, it times fewer and says so in `e2e.steps`.
+
 Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for the roofline and
 cpu_baseline definitions.
 """
@@ -47,6 +53,10 @@ BYTES_PER_SAMPLE_UPDATE = 4 * (D_OBS + D_ACT + 4) + 8
 FLOPS_PER_SAMPLE_UPDATE = 3 * 48128                          # fwd + bwd of the three nets
 
 
+T_START = time.time()
+BUDGET_S = float(os.environ.get("SPO_BENCH_BUDGET_S", "780"))
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -56,10 +66,10 @@ def parse():
     ap.add_argument("--num-envs", type=int, default=1024, help="envs per GPU")
     ap.add_argument("--horizon", type=int, default=1000, help="steps per env per epoch (T)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--ref-horizon", type=int, default=0,
+                    help="steps per env of the reference arm's measured mini-epoch (0 = sized from --cpu-seconds)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--ref-passes", type=int, default=40,
-                    help="update passes per epoch assumed by the reference arm (the GPU arm observes StopIter = 40 on this stream)")
     return ap.parse_args()
 
 
@@ -225,66 +235,65 @@ def time_update_kernel(tr, device):
     return float(np.mean(times)), (S + 63) // 64
 
 
-def cpu_baseline(args, passes, kind="port", threads=4):
-    """The oracle port of the reference's CPU path, timed on this box's host cores on a
-    bounded sample of the same workload: `r` vector env steps at N envs (rollout loop incl.
-    store + bootstraps) and `m` PPO-Lag minibatch steps; extrapolated to the workload with
-    the measured per-step costs and `passes` update passes."""
+def cpu_baseline(args, kind="port", threads=4, horizon=None):
+    """The reference's CPU path (oracle port, bit-identical to the reference's main() -- tests/test_oracle_golden.py)
+    timed on this box's host cores: ONE TRULY EXECUTED PPO-Lag epoch of oracle.trainers.train() -- rollout loop with
+    store / bootstrap forwards / per-path GAE, buffer.get(), Lagrange step, <= 40 passes of batch-64 minibatch steps with
+    the KL early stop -- at the workload's N envs and a reduced horizon T_s, plus 3 mid-epoch vector env steps to
+    separate the per-step rollout cost from the once-per-epoch closing step.  The epoch is then scaled linearly to the
+    workload's horizon T (every component is linear in T at fixed N; the closing step is counted once):
+        epoch_s(T) = (T - 1) * t_step + t_close + t_update(T_s) * T / T_s."""
+    from collections import deque
     from oracle import spo_oracle as O
     from oracle import trainers as TR
     from safepo.common.synthetic_env import SyntheticVecEnv
-    from collections import deque
-    torch.set_num_threads(threads)
     N, T = args.num_envs, args.horizon
+    Ts = horizon or max(1, min(16, int((args.cpu_seconds - 4.0) / 2.5)))
+    torch.set_num_threads(threads)
+    # (a) per-step rollout cost away from the epoch end
     torch.manual_seed(0)
     env = SyntheticVecEnv(N, D_OBS, D_ACT, episode_len=T, seed=0)
     pol = O.OraclePolicy(D_OBS, D_ACT)
-    opt = O.OracleOptim(pol)
-    r = 4
+    r = 3
     buf = TR.PathBuffer(N, r, D_OBS, D_ACT, 0.99)
-    log = TR.StatLog()
     obs, _ = env.reset()
     obs = torch.as_tensor(obs, dtype=torch.float32)
     ep = (np.zeros(N), np.zeros(N), np.zeros(N))
     dq = (deque(maxlen=50), deque(maxlen=50), deque(maxlen=50))
     t0 = time.time()
-    obs = TR.rollout(pol, env, buf, obs, ep, dq, log, r, epoch_T=10 ** 9)      # r mid-epoch steps (no path closes)
-    t_roll = (time.time() - t0) / r                                            # s per vector env step
-    for i in range(N):
-        buf.finish_path(torch.zeros(1), torch.zeros(1), i)
-    data = buf.get()
-    buf1 = TR.PathBuffer(N, 1, D_OBS, D_ACT, 0.99)
-    t0e = time.time()
-    TR.rollout(pol, env, buf1, obs, ep, dq, log, 1)                            # the epoch-end step: N bootstrap forwards + GAE
-    t_end = time.time() - t0e
-    adv = data["adv_r"] - 0.1 * data["adv_c"]
-    S = data["obs"].shape[0]
-    budget = max(args.cpu_seconds - (time.time() - t0), 2.0)
+    TR.rollout(pol, env, buf, obs, ep, dq, TR.StatLog(), r, epoch_T=10 ** 9)
+    t_step = (time.time() - t0) / r
+    # (b) one real epoch at horizon Ts through the trainer
+    env = SyntheticVecEnv(N, D_OBS, D_ACT, episode_len=T, seed=0)
+    a = TR.default_args(num_envs=N, steps_per_epoch=N * Ts, total_steps=N * Ts * 1000, seed=0, torch_threads=threads)
     t1 = time.time()
-    m = 0
-    perm = torch.randperm(S)
-    while time.time() - t1 < budget:
-        for s in range(0, S, 64):
-            idx = perm[s:s + 64]
-            b = {"obs": data["obs"][idx], "act": data["act"][idx], "log_prob": data["log_prob"][idx],
-                 "target_value_r": data["target_value_r"][idx], "target_value_c": data["target_value_c"][idx], "adv": adv[idx]}
-            O.minibatch_step(pol, opt, b, "ppo")
-            m += 1
-            if time.time() - t1 >= budget:
-                break
-    t_mb = (time.time() - t1) / m
-    t2 = time.time()
-    with torch.no_grad():
-        old_mean, old_std = O.actor_mean_std(pol, data["obs"])
-    O.full_batch_kl(pol, data["obs"], old_mean, old_std)
-    t_kl_per_sample = (time.time() - t2) / S
-    S_full = N * T
-    epoch_s = (T - 1) * t_roll + t_end + passes * ((S_full + 63) // 64) * t_mb + passes * S_full * t_kl_per_sample
+    seen = {}
+    _, log, times = TR.train("ppo_lag", a, env, max_epochs=1,
+                             hooks={"after_update": lambda epoch, pol_, data_, extra: seen.update(extra)})
+    t_epoch = time.time() - t1
+    t_roll, t_upd = times["rollout"][0], times["update"][0]
+    passes = int(seen.get("Train/StopIter", -1))
+    t_close = max(t_roll - (Ts - 1) * t_step, 0.0)
+    S_full, S_s = N * T, N * Ts
+    epoch_s = (T - 1) * t_step + t_close + t_upd * T / Ts
+    mb = passes * ((S_s + 63) // 64) if passes > 0 else 0
     return {"value": S_full / epoch_s, "unit": "env-steps/s", "cores": threads, "kind": kind,
-            "sample": (f"{r} vector env steps at {N} envs + {m} PPO-Lag minibatch steps (batch 64) on the oracle port; "
-                       f"extrapolated to S={S_full} with {passes} update pass(es): {t_roll*1e3:.1f} ms/env-step-vector, {t_end*1e3:.0f} ms epoch-end step, "
-                       f"{t_mb*1e3:.2f} ms/minibatch-step"),
-            "ms_per_minibatch_step": t_mb * 1e3, "ms_per_vector_env_step": t_roll * 1e3, "passes": passes}
+            "sample": (f"one executed PPO-Lag epoch of the oracle port at {N} envs x {Ts} steps (S={S_s}: rollout {t_roll:.2f} s, "
+                       f"update {t_upd:.2f} s = {passes} passes / {mb} minibatch steps of 64, total {t_epoch:.2f} s) "
+                       f"+ {r} mid-epoch vector steps ({t_step*1e3:.1f} ms each); scaled linearly to {T} steps/env"),
+            "measured_epoch": {"horizon": Ts, "seconds": t_epoch, "env_steps_per_s": S_s / t_epoch, "passes": passes},
+            "ms_per_minibatch_step": (t_upd / mb * 1e3) if mb else None, "ms_per_vector_env_step": t_step * 1e3, "passes": passes}
+
+
+def update_traffic_per_step():
+    """dram__bytes_read.sum + dram__bytes_write.sum per minibatch step of the update kernel, from the committed
+    `ncu --set full` capture (profiles/r02_update_traffic.json, written by tools/ncu_traffic.py); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r02_update_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        t = json.load(f)
+    return float(t["dram_bytes_per_minibatch_step"]), t.get("source", "profiles/r02_update_traffic.json")
 
 
 def run_spo(args):
@@ -310,11 +319,23 @@ def run_spo(args):
     kern_ms, kern_steps = time_update_kernel(tr, device) if world == 1 else (float("nan"), 1)
     e2e = None
     if not args.no_e2e:
-        if dp is not None:
-            dp.close()
-            dp = DataParallel()
-        tr2 = build_trainer(args, device, rank, resident=False, dp=dp)
-        e2e = timed_epochs(tr2, K, W, world, device)
+        # same policy / optimizer / buffer objects, host-env rollout front end; one warm-up epoch for its copy path
+        from safepo.common.synthetic_env import SyntheticVecEnv
+        from safepo.single_agent._engine import Rollout
+        tr2 = dict(tr)
+        env2 = SyntheticVecEnv(args.num_envs, D_OBS, D_ACT, episode_len=args.horizon, seed=rank)
+        tr2["env"] = env2
+        tr2["roll"] = Rollout(env2, tr["policy"], tr["buffer"], tr["logger"], tr["roll"].args, device)
+        epoch_s = val["ms"] / K / 1e3 * 1.10 + 0.5
+        reserve = 0.0 if (args.no_cpu_baseline or world > 1) else args.cpu_seconds + 10.0
+        left = BUDGET_S - (time.time() - T_START) - reserve
+        k_e = int(min(K, max(1, int(left / epoch_s) - 1)))      # -1: the warm-up epoch
+        if world > 1:
+            t = torch.tensor([k_e], device=device)
+            dist.broadcast(t, src=0)
+            k_e = int(t.item())
+        e2e = timed_epochs(tr2, k_e, 1, world, device)
+        e2e["K"] = k_e
     if dp is not None:
         dp.close()
 
@@ -330,6 +351,7 @@ def run_spo(args):
         kern_ms = val["ms"] / K / max(passes, 1)
     alg_bytes = kern_steps * 64 * BYTES_PER_SAMPLE_UPDATE
     achieved = alg_bytes / (kern_ms / 1e3) / 1e9
+    traffic_step, traffic_src = update_traffic_per_step()
     out = {
         "metric": "env-steps/sec PPO-Lag SafetyPointGoal1 @1024 envs/GPU", "value": value, "unit": "env-steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": val["ms"] / K, "higher_is_better": True,
@@ -345,17 +367,17 @@ def run_spo(args):
         "gpu_launches": val["launches"],
         "roofline": {"kernel": "spo_update_kernel (one PPO-Lag pass = 16000 serial minibatch steps)", "bound": "hbm",
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture in profiles/r01_update_ncu.md:
-                     # 16.87 MB for a 300-step launch = 56.2 KB per minibatch step, scaled to this launch's step count
-                     "traffic": 16.8704e6 / 300 * kern_steps, "peak_source": how,
+                     "traffic": (traffic_step * kern_steps) if traffic_step is not None else None, "traffic_source": traffic_src,
+                     "peak_source": how,
                      "note": "serial-latency-bound chain of 64-row Adam steps (SURVEY H3): us_per_minibatch_step is the figure of merit"},
     }
     if e2e is not None:
-        out["e2e"] = {"value": S * K * world / (e2e["ms"] / 1e3), "unit": "env-steps/s", "h2d_bytes_per_step": e2e["h2d"],
-                      "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["ms"] / K, "stop_iter": e2e["stops"],
-                      "gpu_launches": e2e["launches"]}
+        out["e2e"] = {"value": S * e2e["K"] * world / (e2e["ms"] / 1e3), "unit": "env-steps/s", "h2d_bytes_per_step": e2e["h2d"],
+                      "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["ms"] / e2e["K"], "steps": e2e["K"], "warmup": 1,
+                      "stop_iter": e2e["stops"], "gpu_launches": e2e["launches"],
+                      "note": "same trainer objects as the value arm (already warm); only the rollout front end differs"}
     if not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args, passes)
+        out["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -402,16 +424,12 @@ def run_reference(args):
         return
     threads = pick_reference_threads()
     K, W = args.steps, max(args.warmup, 0)
-    per = max(args.cpu_seconds / max(K + W, 1), 4.0)
+    # every step = one executed mini-epoch of the oracle port (cpu_baseline); horizon sized so K+W of them end in minutes
+    per = max(args.cpu_seconds * 6.0 / max(K + W, 1), 5.0)
+    Ts = args.ref_horizon or max(1, min(16, int((per - 3.0) / 2.5)))
     vals = []
-    a2 = argparse.Namespace(**vars(args))
-    a2.cpu_seconds = per
-    # KL early stop (ppo_lag.py:347): on this synthetic stream (advantages uncorrelated with the
-    # observations) the KL never reaches target_kl, so all 40 passes run -- the GPU arm, which executes the
-    # same rule, logs StopIter = 40 in every epoch (profiles/r01_bench_default.json).
-    passes = args.ref_passes
     for i in range(K + W):
-        r = cpu_baseline(a2, passes, kind="port", threads=threads)
+        r = cpu_baseline(args, kind="port", threads=threads, horizon=Ts)
         if i >= W:
             vals.append(r)
     v = float(np.mean([r["value"] for r in vals]))
@@ -419,8 +437,11 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "env-steps/sec PPO-Lag SafetyPointGoal1 @1024 envs/GPU", "value": v, "unit": "env-steps/s",
            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": S / v * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"PPO-Lag SafetyPointGoal1-v0 shape, {args.num_envs} envs x {args.horizon} steps/epoch (bounded sample per step)",
-                      "passes_assumed": passes},
+           "config": {"workload": "BASELINE.json configs[1]: PPO-Lag SafetyPointGoal1-v0 shape (obs 60, act 2, hidden 64x64), "
+                                  f"{args.num_envs} envs/GPU x {args.horizon} steps/epoch, batch 64, <=40 passes with KL early stop",
+                      "sampling": f"each step executes one full epoch at {Ts} steps/env and scales it linearly to {args.horizon} (ms_per_step is the scaled epoch)",
+                      "passes_observed": [r["passes"] for r in vals],
+                      "measured_env_steps_per_s_at_reduced_horizon": float(np.mean([r["measured_epoch"]["env_steps_per_s"] for r in vals]))},
            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": vals[-1]["sample"]},
            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))

@@ -125,10 +125,15 @@ class VectorizedOnPolicyBuffer:
         out["adv"] = mixed
         self.ptr_list = [0] * self.num_envs
         self.path_start_idx_list = [0] * self.num_envs
+        # the path boundaries / bootstrap values belong to the epoch just consumed (they are not part of the
+        # returned dict): clear them so that a store()/finish_path()/get() loop never sees stale cuts
+        self.reset_segments()
         return out
 
     def reset_segments(self):
         self.seg_end.zero_()
+        self.boot_r.zero_()
+        self.boot_c.zero_()
 
 
 def masked_gae_returns(rewards, value_preds, masks, popart_mean, popart_sqrt_var, gamma, gae_lambda, out=None):

@@ -20,6 +20,13 @@ class RunningMeanStd:
         self.var = torch.ones(shape, dtype=torch.float64, device=device)
         self.count = float(epsilon)
 
+    def host_copy(self):
+        """Picklable host object with gymnasium's RunningMeanStd surface (numpy ``mean`` / ``var``, float ``count``,
+        ``update(x)``): what the trainers store as the checkpoint's "Normalizer" (ppo_lag.py:381-386)."""
+        h = HostRunningMeanStd(tuple(self.mean.shape))
+        h.mean, h.var, h.count = self.mean.cpu().numpy().copy(), self.var.cpu().numpy().copy(), float(self.count)
+        return h
+
     def state_dict(self):
         return {"mean": self.mean.cpu().numpy(), "var": self.var.cpu().numpy(), "count": self.count}
 
@@ -27,6 +34,29 @@ class RunningMeanStd:
         self.mean.copy_(torch.as_tensor(state["mean"], dtype=torch.float64))
         self.var.copy_(torch.as_tensor(state["var"], dtype=torch.float64))
         self.count = float(state["count"])
+
+
+class HostRunningMeanStd:
+    """Host-side (numpy) running statistics with the attribute / method names of
+    gymnasium.wrappers.normalize.RunningMeanStd, which the reference pickles into its checkpoints and
+    evaluate.py:56-57 re-attaches to an env whose wrapper then reads ``.mean`` / ``.var`` and calls
+    ``.update(obs)``.  The merge is the parallel-variance formula gymnasium publishes (restated in oracle/envio.py)."""
+
+    def __init__(self, shape=(), epsilon=1e-4):
+        import numpy as np
+        self.mean = np.zeros(shape, "float64")
+        self.var = np.ones(shape, "float64")
+        self.count = float(epsilon)
+
+    def update(self, x):
+        import numpy as np
+        x = np.asarray(x, dtype=np.float64)
+        b_mean, b_var, b_n = x.mean(axis=0), x.var(axis=0), x.shape[0]
+        delta = b_mean - self.mean
+        tot = self.count + b_n
+        new_mean = self.mean + delta * b_n / tot
+        m2 = self.var * self.count + b_var * b_n + np.square(delta) * self.count * b_n / tot
+        self.mean, self.var, self.count = new_mean, m2 / tot, tot
 
 
 class SafeNormalizeObservation:

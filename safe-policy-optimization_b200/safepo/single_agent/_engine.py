@@ -83,11 +83,13 @@ class AdamState:
 
 
 def _normalizer_state(roll, env):
-    """What the reference checkpoints as "Normalizer" (ppo_lag.py:381-386: env.obs_rms): the device-side running statistics when
-    --normalize-obs is on (mean / var / count as numpy, like gymnasium's RunningMeanStd fields), else whatever the env carries."""
+    """What the reference checkpoints as "Normalizer" (ppo_lag.py:381-386: env.obs_rms): a host object with ``mean`` / ``var`` /
+    ``count`` numpy fields and ``update()`` like gymnasium's RunningMeanStd -- evaluate.py:56-57 assigns the unpickled object
+    straight to ``eval_env.obs_rms`` -- holding the device-side statistics when observations are normalised on the device, else
+    whatever the env carries."""
     norm = getattr(roll, "obs_norm", None)
     if norm is not None:
-        return norm.obs_rms.state_dict()
+        return norm.obs_rms.host_copy()
     return getattr(env, "obs_rms", None)
 
 
@@ -125,10 +127,20 @@ class Rollout:
         self.bytes_d2h = 0
         # SafeNormalizeObservation (env.py:66,77) on the device: statistics updated and observations
         # normalised right after the H2D of every env step (reset included, like gymnasium's wrapper)
+        # A host env built by safepo.common.env.make_sa_mujoco_env is bare: it asks for both wrappers of the
+        # reference's factory (env.py:62-66) through ``device_wrappers``.
+        wants = getattr(env, "device_wrappers", ())
         self.obs_norm = None
-        if getattr(args, "normalize_obs", False):
+        if getattr(args, "normalize_obs", False) or "normalize_obs" in wants:
             from safepo.common.normalizer import SafeNormalizeObservation
             self.obs_norm = SafeNormalizeObservation(D, device)
+            if hasattr(env, "obs_rms"):
+                env.obs_rms = self.obs_norm.obs_rms
+        self.act_rescale = None
+        if "rescale_action" in wants:
+            from safepo.common.normalizer import SafeRescaleAction
+            self.act_rescale = SafeRescaleAction(env.action_space.low, env.action_space.high, device)
+            self.act_env_d = torch.empty(N, self.A, dtype=torch.float32, device=device)
         obs, _ = env.reset()
         self.obs_d.copy_(torch.as_tensor(np.asarray(obs), dtype=torch.float32))
         if self.obs_norm is not None:
@@ -156,6 +168,8 @@ class Rollout:
         for t in range(T):
             eps = torch.empty(N, A).normal_().to(self.device, non_blocking=True) if self.host_rng else None
             act, _, _, _ = pol.step(self.obs_d, eps=eps, store=(buf.struct, t))
+            if self.act_rescale is not None:     # the buffer keeps the policy's action; the env gets the rescaled one
+                act = self.act_rescale.action(act, out=self.act_env_d)
             self.act_h.copy_(act, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             self.bytes_d2h += N * A * 4
@@ -365,7 +379,11 @@ class PolicyGradientUpdate:
 
 class CriticRegression:
     """cpo.py:534-571 / trpo_lag.py:457-494: minibatch regression of the two critics
-    (batch 128, lr 1e-3, 10 passes); the joint clip also sees the actor's stale .grad."""
+    (batch 128, lr 1e-3, 10 passes).  The joint clip (cpo.py:562) runs over policy.parameters(), but
+    every fvp() call starts with policy.actor.zero_grad() (cpo.py:137, trpo_lag.py:139), which sets the
+    actor's .grad to None, and nothing calls backward() on the actor afterwards: only the two critics'
+    gradients enter the norm.  ``stale_actor_grad_sumsq`` stays as an explicit knob (default 0) for a
+    caller whose actor does hold a gradient at this point."""
 
     def __init__(self, policy, cfg, host_rng, device, lr=1e-3):
         self.policy, self.cfg, self.host_rng, self.device = policy, cfg, host_rng, device
@@ -375,7 +393,7 @@ class CriticRegression:
                             0.001 if cfg.get("use_critic_norm", True) else 0.0, 0.8, 1.2, 1.5, 0.0,
                             2.0 if cfg.get("use_value_coefficient", False) else 1.0)
 
-    def run(self, data, stale_actor_grad_sumsq, perms=None):
+    def run(self, data, stale_actor_grad_sumsq=0.0, perms=None):
         pol, cfg, lib = self.policy, self.cfg, L.lib()
         S = data["obs"].shape[0]
         batch = L.Batch(L.ptr(data["obs"]), None, None, L.ptr(data["target_value_r"]), L.ptr(data["target_value_c"]),
@@ -555,8 +573,7 @@ class TrustRegionUpdate:
         pol.actor_flat().copy_(theta_old + step_frac * step)
         return {"Misc/Alpha": alpha.item(), "Misc/FinalStepNorm": float(torch.norm(step)), "Misc/xHx": xHx.item(),
                 "Misc/gradient_norm": float(sc[6].sqrt()), "Misc/H_inv_g": float(sc[7].sqrt()), "Misc/AcceptanceStep": acceptance,
-                "Loss/Loss_actor": -float(sc[4]) + float(sc[5]), "Train/KL": kl, "case": case, "step_frac": step_frac,
-                "stale_sumsq": bb.to(self.device)}
+                "Loss/Loss_actor": -float(sc[4]) + float(sc[5]), "Train/KL": kl, "case": case, "step_frac": step_frac}
 
     # -- TRPO-Lag --
     def run_trpo(self, data, advantage):
@@ -600,7 +617,7 @@ class TrustRegionUpdate:
         pol.actor_flat().copy_(theta_old + step_frac * step)
         return {"Misc/Alpha": alpha.item(), "Misc/FinalStepNorm": float(torch.norm(step)), "Misc/xHx": xHx.item(),
                 "Misc/gradient_norm": float(sc[2].sqrt()), "Misc/H_inv_g": float(sc[3].sqrt()), "Misc/AcceptanceStep": acceptance,
-                "Loss/Loss_actor": loss_pi, "Train/KL": final_kl, "step_frac": step_frac, "stale_sumsq": sc[2].to(self.device)}
+                "Loss/Loss_actor": loss_pi, "Train/KL": final_kl, "step_frac": step_frac}
 
 
     def run_npg(self, data, advantage):
@@ -621,7 +638,7 @@ class TrustRegionUpdate:
         o = self._eval(data, advantage, None)           # KL(old || new).mean() at the new parameters
         return {"Misc/Alpha": alpha.item(), "Misc/FinalStepNorm": float(torch.norm(step)), "Misc/xHx": xHx.item(),
                 "Misc/gradient_norm": float(sc[2].sqrt()), "Misc/H_inv_g": float(sc[3].sqrt()),
-                "Loss/Loss_actor": -float(sc[1]), "Train/KL": float(o[2]), "stale_sumsq": sc[2].to(self.device)}
+                "Loss/Loss_actor": -float(sc[1]), "Train/KL": float(o[2])}
 
 
 def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False):
@@ -670,7 +687,7 @@ def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False)
             data = buffer.get(0.0)
             ep_costs = logger.get_stats("Metrics/EpCost") - args.cost_limit
             res = trust.run_cpo(data, ep_costs, variant="pcpo" if algo == "pcpo" else "cpo")
-        cres = critics.run(data, res["stale_sumsq"])
+        cres = critics.run(data)
         buffer.reset_segments()
         torch.cuda.synchronize()
         t_upd = time.time() - t1

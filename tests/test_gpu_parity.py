@@ -680,3 +680,26 @@ def test_tensor_core_forward_and_kl_large_batch(D, A, S):
         want_kl = O.normal_kl(old_mean, torch.exp(old_ls), m, s).sum(-1, keepdim=True).mean().item()
     assert abs(float(r["final_kl"]) - want_kl) <= 2e-5 * abs(want_kl) + 1e-7, (float(r["final_kl"]), want_kl)
     assert int(r["passes"]) == 1
+
+
+# ---- row G2: masked GAE of the multi-agent buffer (first hardware run: round-1 driver box, 4 XPASS; strict since round 2)
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,N", [(8, 5), (64, 3), (1, 4), (33, 1024), (8, 8192)])
+def test_masked_gae_bit_exact_vs_oracle(T, N):
+    """spo_gae_masked against oracle/ma_oracle.masked_gae -- itself pinned bit for bit to the reference's
+    SeparatedReplayBuffer.compute_returns -- for reward and cost returns: bit-exact (sequential fp32 recurrence)."""
+    from safepo.common.buffer import masked_gae_returns
+    from oracle import ma_oracle as MA
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(T * 1000 + N)
+    pop = MA.OraclePopArt(1)
+    for _ in range(3):
+        pop.normalize(torch.randn(40, 1, generator=g) * 3 + 1.5)
+    mean, var = pop.running_mean_var()
+    sqrt_var = torch.sqrt(var)
+    vp = torch.randn(T + 1, N, 1, generator=g)
+    rew = torch.randn(T, N, 1, generator=g)
+    masks = (torch.rand(T + 1, N, 1, generator=g) > 0.15).float()
+    want = MA.masked_gae(rew, vp, masks, pop, 0.96, 0.95)
+    got = masked_gae_returns(rew.to(dev), vp.to(dev), masks.to(dev), float(mean), float(sqrt_var), 0.96, 0.95).cpu()
+    assert torch.equal(got, want), float((got - want).abs().max())
