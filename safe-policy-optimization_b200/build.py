@@ -34,16 +34,19 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and up_to_date():
+def build(force=False, verbose=False, timers=False):
+    """timers=True: a second library tools/libspo_timers.so with -DSPO_PHASE_TIMERS (clock64 phase marks in the
+    update kernel, read back with spo_debug_phase_cycles; tools/phase_timers.py)."""
+    out = os.path.join(ROOT, "tools", "libspo_timers.so") if timers else OUT
+    if not timers and not force and up_to_date():
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
-    objdir = os.path.join(OUT_DIR, "obj")
+    objdir = os.path.join(OUT_DIR, "obj_timers" if timers else "obj")
     os.makedirs(objdir, exist_ok=True)
 
     def cc(src):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [NVCC] + FLAGS + (["-DSPO_PHASE_TIMERS"] if timers else []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -53,12 +56,12 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(cc, sources()))
-    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, timers="--timers" in sys.argv))

@@ -1,30 +1,52 @@
-// The minibatch update loop as one persistent launch per pass.
+// The minibatch update loop as one persistent launch per pass -- round-2 design: every net is spread over FOUR
+// SMs of one 12-CTA thread-block cluster; the CTAs exchange activations by reading each other's shared memory
+// (ld.shared::cluster) behind relaxed hardware cluster barriers.
 //
-// Reference: safepo/single_agent/ppo_lag.py:297-336 (PPO-Lag), focops.py:309-357
-// (FOCOPS), cpo.py:543-571 / trpo_lag.py:466-494 (critic regression).  Per minibatch:
-// forward of the three nets, losses, backward, critic L2 term, ONE joint grad-norm clip
-// over all three nets (ppo_lag.py:325), three Adam steps.
+// Reference: safepo/single_agent/ppo_lag.py:297-336 (PPO-Lag), focops.py:309-357 (FOCOPS), cpo.py:543-571 /
+// trpo_lag.py:466-494 (critic regression).  Per minibatch: forward of the three nets, losses, backward, critic L2
+// term, ONE joint grad-norm clip over all three nets (ppo_lag.py:325), three Adam steps.
 //
-// GEMMs: every 64x64xK product of the step runs on the tensor pipe as warp-level
-// mma.sync.m16n8k8 TF32 with the 3xTF32 split in registers (csrc/spo_mma.cuh) -- the FFMA
-// register-tile version of r01 was bound by shared-memory bandwidth at 4.1-4.8 k cycles per
-// GEMM (profiles/r01_update_phase_cycles.md).  Accumulator fragments of the dW products
-// are the gradients; their owner threads also hold the Adam moments in registers.
+// Why: the chain of minibatch steps is strictly serial (each step needs the previous step's weights), so the only
+// figure of merit is the latency of ONE step.  Round 1 ran one CTA per net (3 working SMs): 27.4 k cycles per step,
+// 48 % of it in five 64x64x64 3xTF32 GEMMs at 2.6 k cycles each and another 35 % in per-parameter / per-row phases
+// that one SM has to walk through alone (profiles/r01_update_phase_cycles.md).  Here the hidden layer is split by
+// UNITS: CTA (net n, quarter q) owns hidden units [16q, 16q+16) of both layers -- the matching rows of W1 and W2,
+// their biases, the matching columns of W3, and the Adam moments of exactly those parameters (in registers).  Nothing
+// is replicated except b3 / log_std (<= 16 floats), no weight ever moves; what moves per step is activations:
 //
-// Mapping: a thread-block cluster of 4 CTAs (the 4th only joins the barriers: a cluster of
-// 4 synchronises faster than one of 3 on B200), one net per CTA -- actor / reward critic / cost
-// critic, 512 threads each.  A CTA keeps its net's weights, the Adam moments and all
-// activations of the 64-row tile in shared memory / registers for the whole pass; per step it
-// reads the 64 minibatch rows (staged in registers a step ahead, their indices two steps
-// ahead) and exchanges one float through distributed shared memory for the joint gradient
-// norm.  Weights and moments touch HBM once per launch.
+//   forward   h1[:, slice] = tanh(x W1[slice]^T)          -> all-gather of the 64x16 slices inside the net (16 KB per CTA)
+//             h2[:, slice] = tanh(h1 W2[slice]^T)         (needs all of h1, local afterwards)
+//             y partial    = h2[:, slice] W3[:, slice]^T  -> all-gather of 64 x O partial sums (tiny)
+//   loss rows              (replicated in the four CTAs of a net: every CTA holds all 64 rows of y)
+//   backward  dz2[:, slice], dW3[:, slice], dW2[slice, :] = dz2[:, slice]^T h1       (local)
+//             dh1 partial  = dz2[:, slice] W2[slice, :]   -> reduce-scatter by column quarter (16 KB per CTA)
+//             dz1[:, slice], dW1[slice, :] = dz1[:, slice]^T x                       (local)
+//   clip      (sum g^2, sum theta^2) of the slice         -> all-to-all of one float2 between the 12 CTAs
+//   Adam      on the slice, weights rewritten in place in shared memory
 //
-// The chain of steps is strictly sequential (each step needs the weights of the previous
-// one), so this kernel is latency-bound by construction: what is optimised is
-// microseconds per step, not bandwidth.  Every phase between two barriers is spread over all
-// 16 warps (loss rows as (row, action dim), reductions as 8-way row splits + shuffles):
-// with 4 warps per scheduler an instruction executed by every thread costs 4 issue cycles,
-// and a phase run by one warp stalls the other 15 (profiles/r01_update_phase_cycles.md).
+// Each exchange is a PULL: the producer stores into its own shared memory, the cluster passes a hardware barrier
+// (one thread fences at cluster scope, all arrive relaxed: 100-125 cycles measured for 12 CTAs), the consumers load
+// what they need straight from the producers' shared memory (one ld.shared::cluster round trip, the loads of a thread
+// are independent).  Pushing with st.async + mbarrier complete_tx was measured first and rejected: ~1.1-1.4 k cycles
+// of fixed latency per exchange (tools/cluster_probe.cu, profiles/r02_cluster_probe.txt).  Buffer reuse is safe
+// because every consumer finishes its loads before it arrives at the NEXT barrier, and a producer overwrites a buffer
+// only after that barrier (four barriers per step).
+//
+// GEMMs: warp-level mma.sync.m16n8k8 TF32 with the 3xTF32 split in registers (csrc/spo_mma.cuh); every product of
+// the step is now 64x16x64 (or its transposes), 385 cycles at the measured 510 FMA/clk/SM.  tcgen05 was evaluated
+// for this kernel and rejected on latency, not throughput: one M=64,N=64 3xTF32 product measured 1 378 cycles from
+// first issue to completion (profiles/r01_tc64_test.txt) against ~400 for the same work split over four SMs, and
+// the operands here change every step (each is produced by the previous phase), so there is nothing for TMA to
+// prefetch.  The full-batch kernels (csrc/spo_tc_forward.cu), where tiles are independent, are the tcgen05 ones.
+//
+// Shared-memory leading dimensions are all == 8 (mod 32): with the mma fragment pattern (g = lane/4, t = lane%4) both
+// the [m][k] reads (8g + t) and the transposed [k][m] reads (8t + g) are bank-conflict free (round 1 had 30 %).
+//
+// Data-parallel ranks (spo_pg_update_dp): every CTA pushes its slice of the gradient to the same CTA of every peer
+// GPU as 8-byte {value, sequence} words (posted NVLink stores into peer-mapped staging memory), dW2 / dW3 / db2 as soon
+// as they exist (dh1 exchange and the dW1 product still ahead), the rest after dW1; a receiver polls the words
+// themselves -- no fence, no flag, no barrier (the sequence number in every word is the flag).  Sums run in rank
+// order on every rank, so the replicas stay bit-identical.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include "spo_common.cuh"
@@ -32,34 +54,41 @@
 
 namespace cg = cooperative_groups;
 
-// Optional phase timers (build with -DSPO_PHASE_TIMERS): thread 0 of every CTA accumulates
-// clock64() deltas per phase of the step; read back with spo_debug_phase_cycles().
 #ifdef SPO_PHASE_TIMERS
-__device__ unsigned long long g_phase_cycles[4][16];
-__device__ long long g_trace[4][16][24];   // arrival time of every warp at every mark during step 50
-#define TRACE_MARK(idx)                                                   \
-  do {                                                                    \
-    if (lane == 0 && step_idx == 50) g_trace[rank & 3][wid][idx] = clock64(); \
-  } while (0)
+__device__ unsigned long long g_phase_cycles[16][24];
 #define PHASE_MARK(idx)                                                   \
   do {                                                                    \
-    TRACE_MARK(idx);                                                      \
     if (tid == 0) {                                                       \
       const long long now__ = clock64();                                  \
-      sm_phase__[idx] += static_cast<unsigned long long>(now__ - phase_t__); /* no global traffic inside the step */ \
+      sm_phase__[idx] += static_cast<unsigned long long>(now__ - phase_t__); \
       phase_t__ = now__;                                                  \
     }                                                                     \
   } while (0)
 #else
 #define PHASE_MARK(idx) do { } while (0)
-#define TRACE_MARK(idx) do { } while (0)
 #endif
 
 namespace {
 
-constexpr int AUXW = 28;       // per-row side data: act[8] | logp adv tgt _ | old_mean[8] | old_std[8]
+constexpr int UT = 256;                 // threads per CTA: 8 warps, 2 per scheduler
+constexpr int NQ = 4;                   // CTAs per net
+constexpr int SL = SPO_HID / NQ;        // hidden units per CTA (16)
+constexpr int NCTA = 3 * NQ;            // working CTAs of the cluster
+constexpr int LDA = 72;                 // leading dimension of 64-wide tiles   (== 8 mod 32)
+constexpr int LDS = 40;                 // leading dimension of SL-wide slices  (== 8 mod 32)
+constexpr int AUXW = 28;                // per-row side data: act[8] | logp adv tgt _ | old_mean[8] | old_std[8]
 constexpr int AUX_LOGP = 8, AUX_ADV = 9, AUX_TGT = 10, AUX_OMEAN = 12, AUX_OSTD = 20;
 constexpr float kLogSqrt2Pi = 0.91893853320467274178f;
+// small parameters of a slice: b1[SL] b2[SL] w3[MAX_ACT][SL] b3[MAX_ACT] log_std[MAX_ACT]   (thread i owns entry i)
+constexpr int SP_B1 = 0, SP_B2 = SL, SP_W3 = 2 * SL, SP_B3 = 2 * SL + SPO_MAX_ACT * SL, SP_LS = SP_B3 + SPO_MAX_ACT;
+constexpr int SPN = SP_LS + SPO_MAX_ACT;   // 176
+static_assert(SPN <= UT, "one thread per small parameter");
+
+__host__ __device__ constexpr int upd_ldx(int nt1) { return 64 * nt1 + 8; }
+// per-CTA gradient slot of the cross-GPU exchange, in 8-byte {value, seq} words: W2 frags, W1 frags, small
+__host__ __device__ constexpr int dp_slot_words(int nt1) { return UT * 4 * (1 + nt1) + UT; }
+
+template <int N> struct IC { static constexpr int value = N; };
 
 struct UpdArgs {
   float *params, *adam_m, *adam_v;
@@ -68,44 +97,57 @@ struct UpdArgs {
   const int64_t* perm;
   int64_t perm_len;
   int batch, kind, D, A;
-  int actor_only;   // CUP projection stage: the critic CTAs only join the barriers
+  int actor_only;   // CUP projection stage: the critic CTAs only take part in the step barrier
   spo_hparams hp;
   spo_update_ctrl* ctrl;
-  spo_comm comm;   // world <= 1: single GPU
+  spo_comm comm;    // world <= 1: single GPU
 };
 
-// system-scope accesses for the cross-GPU gradient exchange (peer memory over NVLink)
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+// ---- PTX helpers -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
 }
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// relaxed hardware cluster barrier: the caller has just passed a __syncthreads (all local stores performed); one thread
+// fences at cluster scope (a release arrive would put a MEMBAR.ALL.GPU into every thread: 1.1 k cycles per step in r01)
+__device__ __forceinline__ void cluster_arrive(int tid) {
+  if (tid == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float4 ld_relaxed_sys_f4(const float4* p) {
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
   float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
-__device__ __forceinline__ float ld_relaxed_sys_f(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+__device__ __forceinline__ float2 ld_dsmem_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
   return v;
 }
-
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem)), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+// cross-GPU words: {value, seq} as one 8-byte access (single-copy atomic), system scope, no caching games
+__device__ __forceinline__ void st_ll(float2* p, float v, unsigned seq) {
+  asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(seq) : "memory");
+}
+__device__ __forceinline__ bool ld_ll(const float2* p, unsigned seq, float& v) {
+  unsigned a, b;
+  asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
+  v = __uint_as_float(a);
+  return b == seq;
+}
 
 // One Adam step on a scalar in torch's _multi_tensor_adam op order:
 //   m = lerp(m, g, 1-b1) (fused mul-add);  v = v*b2 + ((1-b2)*g)*g;
 //   denom = sqrt(v)/sqrt(bc2) + eps;  p = p + (step_size*m)/denom,  step_size = -lr/bc1.
-// sqrt and the division use the SFU approximations (sqrt.approx / div.approx,
-// <= 2 ulp), 1/sqrt(bc2) is a precomputed factor: IEEE-exact versions cost ~60 issue slots per parameter (profiles/r01) for
-// differences far below the 1e-5 parity bar.
+// sqrt and the division use the SFU approximations (sqrt.approx / div.approx, <= 2 ulp), 1/sqrt(bc2) is a precomputed
+// factor (measured error of whole chains: tests/test_gpu_parity.py prints it).
 struct AdamK {
   float w1, b2, w2, ibc2s, eps, ss;  // w1 = 1-b1, w2 = 1-b2, ibc2s = 1/sqrt(1-b2^t)
 };
@@ -121,160 +163,162 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
   return __fadd_rn(p, __fdividef(__fmul_rn(k.ss, m), denom));
 }
 
-// small parameters of a net in the order b1[64] b2[64] w3[O*64] b3[O] log_std[A(actor)]
-struct SmallMap {
-  int O, A_ls;  // A_ls = A for the actor, 0 for critics
-  __device__ int count() const { return 2 * SPO_HID + O * SPO_HID + O + A_ls; }
-  // global offset (within packed buffer) of small param i
-  __device__ int goff(const SpoNetOff& o, int i) const {
-    if (i < SPO_HID) return o.b1 + i;
-    i -= SPO_HID;
-    if (i < SPO_HID) return o.b2 + i;
-    i -= SPO_HID;
-    if (i < O * SPO_HID) return o.w3 + i;
-    i -= O * SPO_HID;
-    if (i < O) return o.b3 + i;
-    return o.log_std + (i - O);
+// One 16-row m-tile x NTL 8-column n-tiles of C (+)= A * B on the tensor pipe, 3xTF32 with the three partial
+// products in separate accumulator chains (lo*hi, hi*lo, hi*hi; small terms are added first at the end).
+//   A(m, k) = A[m * a_sm + k * a_sk]      B(k, n) = B[k * b_sk + n * b_sn]      (shared memory, K = 8 * KSTEPS)
+// Fragment ownership (g = lane >> 2, t = lane & 3): acc[nt][0..3] = C(m0+g, n0+8nt+2t), (.., +1), (m0+g+8, ..), (.., +1)
+template <int NTL, int KSTEPS, bool ACCUM>
+__device__ __forceinline__ void warp_gemm(float (&acc)[NTL][4], const float* __restrict__ A, int a_sm, int a_sk,
+                                          const float* __restrict__ B, int b_sk, int b_sn, int m0, int n0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const float* a_ptr = A + (m0 + g) * a_sm + t * a_sk;
+  const float* b_ptr = B + t * b_sk + (n0 + g) * b_sn;
+  float c_lh[NTL][4], c_hl[NTL][4], c_hh[NTL][4];
+#pragma unroll
+  for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { c_lh[nt][e] = 0.f; c_hl[nt][e] = 0.f; c_hh[nt][e] = 0.f; }
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    const int k0 = ks * 8;
+    uint32_t ah[4], al[4];
+    const float* p = a_ptr + k0 * a_sk;
+    spo_split_tf32(p[0], ah[0], al[0]);
+    spo_split_tf32(p[8 * a_sm], ah[1], al[1]);
+    spo_split_tf32(p[4 * a_sk], ah[2], al[2]);
+    spo_split_tf32(p[8 * a_sm + 4 * a_sk], ah[3], al[3]);
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) {
+      uint32_t bh[2], bl[2];
+      const float* pb = b_ptr + nt * 8 * b_sn + k0 * b_sk;
+      spo_split_tf32(pb[0], bh[0], bl[0]);
+      spo_split_tf32(pb[4 * b_sk], bh[1], bl[1]);
+      spo_mma_tf32(c_lh[nt], al, bh);
+      spo_mma_tf32(c_hl[nt], ah, bl);
+      spo_mma_tf32(c_hh[nt], ah, bh);
+    }
   }
-};
-
-constexpr int UT = 512;   // threads per CTA: 16 warps, 4 per scheduler -- every phase of the step is a short dependent
-                          // chain, so latency hiding (not issue width) sets the pace (profiles/r01_update_phase_cycles.md)
-constexpr int FE = 8;     // accumulator-fragment elements per thread per 64x64 product (16 x 16 patch per warp)
-
-// Every shared-memory extent is a compile-time constant: the observation tile / W1 image are padded to
-// KX = 64 * NT1 input columns (zeros beyond obs_dim), leading dimension KX + 4 (== 4 mod 8: rows g = 0..7 of
-// an mma fragment fall in 8 different bank groups), the output layer and the small-parameter slots are
-// sized for SPO_MAX_ACT.  Addresses are then immediates off one base -- with runtime extents the
-// compiler rematerialised pointer arithmetic inside the step (18 % of the issued instructions, profiles/r01).
-__host__ __device__ constexpr int upd_ldx(int nt1) { return 64 * nt1 + 4; }
-constexpr int SPN = (2 * SPO_HID + SPO_MAX_ACT * SPO_HID + 2 * SPO_MAX_ACT + 3) & ~3;   // small-parameter slots
-
-// element e = nt*4 + c of the 16 x 16 warp patch of a 64-wide output owned by thread tid
-__device__ __forceinline__ void frag_rc(int tid, int e8, int col_base, int& row, int& col) {
-  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int nt = e8 >> 2, e = e8 & 3;
-  row = (warp & 3) * 16 + g + ((e >> 1) << 3);
-  col = col_base + (warp >> 2) * 16 + nt * 8 + 2 * t + (e & 1);
+#pragma unroll
+  for (int nt = 0; nt < NTL; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float s = (c_lh[nt][e] + c_hl[nt][e]) + c_hh[nt][e];
+      acc[nt][e] = ACCUM ? acc[nt][e] + s : s;
+    }
 }
 
 template <int NT1>
 __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ int comm_dead;   // a peer never showed up: stop waiting (ctrl->stop = 2 tells the host)
+  __shared__ int comm_dead;   // a peer GPU never showed up: stop waiting (ctrl->stop = 2 tells the host)
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
-  if (threadIdx.x == 0) comm_dead = 0;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   spo_update_ctrl* ctrl = a.ctrl;
   if (*reinterpret_cast<volatile int*>(&ctrl->stop)) return;  // whole cluster takes this branch together
 
   const int D = a.D, A = a.A;
-  constexpr int KX = 64 * NT1, ldx = upd_ldx(NT1);
-  const bool idle = rank >= 3;
-  const int net = idle ? 2 : static_cast<int>(rank);
-  const bool is_actor = (net == 0) && !idle;
+  constexpr int ldx = upd_ldx(NT1);
+  const bool idle = rank >= NCTA;                 // fallback cluster of 16: the last four CTAs only join the barriers
+  const int net = idle ? 2 : static_cast<int>(rank) / NQ;
+  const int q = static_cast<int>(rank) % NQ;      // hidden-unit quarter
+  const unsigned grp0 = static_cast<unsigned>(net * NQ);
+  const bool is_actor = (net == 0);
   const bool active = !idle && !(is_actor && a.kind == SPO_LOSS_CRITIC_ONLY) && !(!is_actor && a.actor_only);
   const SpoNetOff off = spo_net_off(D, A, net);
   const int O = off.out;
-  const SmallMap sm{O, is_actor ? A : 0};
-  const int SP = sm.count();
-  const int mb = (wid & 3) * 16, nb = (wid >> 2) * 16;   // 16 x 16 warp patch of every 64x64 product
   const int g8 = lane >> 2, t4 = lane & 3;
 
-  // ---- shared memory carve-up (weights in nn.Linear orientation [out][in]) ----
+  // ---- shared memory carve-up -------------------------------------------------------------------------------
   float* p = smem;
-  // minibatch row indices of tile q in slot q & 1: requested a step ahead of the rows they address, so the
-  // gather never waits on a dependent global load
-  int64_t* idxbuf = reinterpret_cast<int64_t*>(p); p += 2 * 2 * SPO_ROWS;   // [2][64] int64
+  int64_t* idxbuf = reinterpret_cast<int64_t*>(p); p += 2 * 2 * SPO_ROWS;   // [2][64] int64: row indices of tile q & 1
   float* lsc = p; p += 4 * SPO_MAX_ACT;           // per action dim: std, 1/var, log(std), spare (refreshed every step)
-  float* adk = p; p += 8;                         // Adam scalars of the current step (one thread does the fp64 math)
-  float* w1 = p;  p += SPO_HID * ldx;
-  float* b1 = p;  p += SPO_HID;
-  float* w2 = p;  p += SPO_HID * SPO_LDH;
-  float* b2 = p;  p += SPO_HID;
-  // every CTA of the cluster carves the SAME layout (actor-sized output layer): the peers read
-  // xchg through distributed shared memory at their own offset of it
-  float* w3 = p;  p += SPO_MAX_ACT * SPO_HID;
-  float* b3 = p;  p += SPO_MAX_ACT;
-  float* log_std = p; p += 8;
-  float* msmall = p;  p += SPN;
-  float* vsmall = p;  p += SPN;
-  float* gsmall = p;  p += SPN;
-  float* x = p;   p += SPO_ROWS * ldx;      // observation tile (the next one is staged in registers)
-  float* aux = p; p += SPO_ROWS * AUXW;     // per-row side data
-  float* h1 = p;  p += SPO_ROWS * SPO_LDH;
-  float* h2 = p;  p += SPO_ROWS * SPO_LDH;   // becomes dz1 during backward
-  float* dz2 = p; p += SPO_ROWS * SPO_LDH;
+  float* adk = p; p += 8;                         // Adam scalars of the current step
+  float* w1s = p; p += SL * ldx;                  // W1[16q + j][k]
+  float* w2s = p; p += SL * LDA;                  // W2[16q + j][k]
+  float* sp = p;  p += SPN;                       // small parameters (layout SP_*)
+  float* gsmall = p; p += SPN;                    // their gradients
+  float* x = p;   p += SPO_ROWS * ldx;            // observation tile (the next one is staged in registers)
+  float* aux = p; p += SPO_ROWS * AUXW;           // per-row side data
+  float* h1 = p;  p += SPO_ROWS * LDA;            // all 64 units: own slice + the three received ones
+  float* h2s = p; p += SPO_ROWS * LDS;            // own slice; becomes dz1 slice during backward
+  float* dz2s = p; p += SPO_ROWS * LDS;
+  float* ypo = p; p += SPO_ROWS * SPO_MAX_ACT;    // own partial of the output layer (read by the three peers)
   float* y = p;   p += SPO_ROWS * SPO_MAX_ACT;
   float* dy = p;  p += SPO_ROWS * SPO_MAX_ACT;
-  float* dls = p; p += SPO_ROWS * SPO_MAX_ACT;   // per-row d loss / d log_std
-  float* red = p; p += 64;                       // block-reduction scratch
-  float* xchg = p; p += 4;                       // [parity] CTA grad sumsq, read by peers through DSMEM
-  float* mv1b = nullptr;                         // moments of the second W1 column block (obs_dim > 64): thread-private slots
-  if (NT1 > 1) { mv1b = p; p += 2 * FE * UT; }
-  float* dz1 = h2;
+  float* dls = p; p += SPO_ROWS * SPO_MAX_ACT;    // per-row d loss / d log_std
+  float* dh1f = p; p += SPO_ROWS * LDA;           // own partial of dh1, all 64 columns (each peer reads its quarter)
+  float* red = p; p += 64;                        // block-reduction scratch
+  float* xchg = p; p += 4;                        // [parity]{sum g^2, sum theta^2} of this CTA (read by all peers)
+  float* dz1s = h2s;
+  float* b1s = sp + SP_B1; float* b2s = sp + SP_B2; float* w3s = sp + SP_W3; float* b3 = sp + SP_B3; float* log_std = sp + SP_LS;
 
   const int tps = (a.batch + SPO_ROWS - 1) / SPO_ROWS;                    // tiles per step
   const int64_t n_steps = (a.perm_len + a.batch - 1) / a.batch;
   const int64_t n_tiles = n_steps * tps;
 
+  if (tid == 0) comm_dead = 0;
+
+  // ---- small-parameter entry of this thread ----
+  bool sp_valid = false, sp_counted = false;
+  int sp_goff = 0;
+  if (tid < SPN && !idle) {
+    const int i = tid;
+    sp_counted = true;
+    if (i < SP_B2) { sp_valid = true; sp_goff = off.b1 + SL * q + i; }
+    else if (i < SP_W3) { sp_valid = true; sp_goff = off.b2 + SL * q + (i - SP_B2); }
+    else if (i < SP_B3) { const int o = (i - SP_W3) / SL, kk = (i - SP_W3) % SL; sp_valid = o < O; sp_goff = off.w3 + o * SPO_HID + SL * q + kk; }
+    else if (i < SP_LS) { const int o = i - SP_B3; sp_valid = o < O; sp_goff = off.b3 + o; sp_counted = (q == 0); }
+    else { const int j = i - SP_LS; sp_valid = is_actor && j < A; sp_goff = off.log_std + j; sp_counted = (q == 0); }
+  }
+  float sp_m = 0.f, sp_v = 0.f;
+
   // ---- one-time loads ----
   if (!idle) {
-    for (int i = tid; i < SPO_HID * ldx; i += UT) {
+    for (int i = tid; i < SL * ldx; i += UT) {
       const int j = i / ldx, k = i - j * ldx;
-      w1[i] = (k < D) ? __ldg(a.params + off.w1 + j * D + k) : 0.f;
+      w1s[i] = (k < D) ? __ldg(a.params + off.w1 + (SL * q + j) * D + k) : 0.f;
     }
-    for (int i = tid; i < SPO_HID * SPO_LDH; i += UT) {
-      const int j = i / SPO_LDH, k = i - j * SPO_LDH;
-      w2[i] = (k < SPO_HID) ? __ldg(a.params + off.w2 + j * SPO_HID + k) : 0.f;
+    for (int i = tid; i < SL * LDA; i += UT) {
+      const int j = i / LDA, k = i - j * LDA;
+      w2s[i] = (k < SPO_HID) ? __ldg(a.params + off.w2 + (SL * q + j) * SPO_HID + k) : 0.f;
     }
-    for (int i = tid; i < SPO_HID; i += UT) { b1[i] = __ldg(a.params + off.b1 + i); b2[i] = __ldg(a.params + off.b2 + i); }
-    for (int i = tid; i < O * SPO_HID; i += UT) w3[i] = __ldg(a.params + off.w3 + i);
-    for (int i = tid; i < O; i += UT) b3[i] = __ldg(a.params + off.b3 + i);
-    for (int i = tid; i < SP; i += UT) {
-      msmall[i] = a.adam_m[sm.goff(off, i)];
-      vsmall[i] = a.adam_v[sm.goff(off, i)];
+    if (tid < SPN) {
+      sp[tid] = sp_valid ? a.params[sp_goff] : 0.f;
+      gsmall[tid] = 0.f;
+      if (sp_valid) { sp_m = a.adam_m[sp_goff]; sp_v = a.adam_v[sp_goff]; }
     }
-    if (is_actor && tid < A) log_std[tid] = a.params[off.log_std + tid];
     for (int i = tid; i < SPO_ROWS * ldx; i += UT) x[i] = 0.f;
     for (int i = tid; i < SPO_ROWS * AUXW; i += UT) aux[i] = 0.f;
   }
-  // Adam moments of this thread's fragment elements: W2 and the first 64 input columns of W1 in registers
-  float mW2[FE], vW2[FE], mW1[FE], vW1[FE];
-  if (active) {
+  // Adam moments of this thread's accumulator-fragment elements.  Fragment e of the dW2 slice product (warp w = n-tile w):
+  //   (j, k) = (g + 8*(e>>1), 8w + 2t + (e&1));  the dW1 slice product has n-tiles w + 8*i, i < NT1.
+  float mW2[4], vW2[4], mW1[NT1][4], vW1[NT1][4];
+  auto frag_jk = [&](int e, int ntile, int& j, int& k) { j = g8 + ((e >> 1) << 3); k = 8 * ntile + 2 * t4 + (e & 1); };
 #pragma unroll
-    for (int e = 0; e < FE; ++e) {
-      int j, k;
-      frag_rc(tid, e, 0, j, k);
-      mW2[e] = a.adam_m[off.w2 + j * SPO_HID + k];
-      vW2[e] = a.adam_v[off.w2 + j * SPO_HID + k];
-      const bool ok = k < D;
-      mW1[e] = ok ? a.adam_m[off.w1 + j * D + k] : 0.f;
-      vW1[e] = ok ? a.adam_v[off.w1 + j * D + k] : 0.f;
-      if (NT1 > 1) {
-        const bool ok2 = (k + 64) < D;
-        mv1b[e * UT + tid] = ok2 ? a.adam_m[off.w1 + j * D + k + 64] : 0.f;
-        mv1b[(FE + e) * UT + tid] = ok2 ? a.adam_v[off.w1 + j * D + k + 64] : 0.f;
-      }
+  for (int e = 0; e < 4; ++e) {
+    int j, k;
+    frag_jk(e, wid, j, k);
+    mW2[e] = active ? a.adam_m[off.w2 + (SL * q + j) * SPO_HID + k] : 0.f;
+    vW2[e] = active ? a.adam_v[off.w2 + (SL * q + j) * SPO_HID + k] : 0.f;
+#pragma unroll
+    for (int i = 0; i < NT1; ++i) {
+      frag_jk(e, wid + 8 * i, j, k);
+      const bool ok = active && k < D;
+      mW1[i][e] = ok ? a.adam_m[off.w1 + (SL * q + j) * D + k] : 0.f;
+      vW1[i][e] = ok ? a.adam_v[off.w1 + (SL * q + j) * D + k] : 0.f;
     }
   }
-  const int t0 = idle ? 0 : a.adam_t[net];
-  double b1pow = pow(static_cast<double>(a.hp.beta1), static_cast<double>(t0));
+  const int t0 = a.adam_t[net];
+  double b1pow = pow(static_cast<double>(a.hp.beta1), static_cast<double>(t0));   // thread 0 keeps them current
   double b2pow = pow(static_cast<double>(a.hp.beta2), static_cast<double>(t0));
   const float lr = (net == 0) ? a.hp.lr_actor : (net == 1 ? a.hp.lr_reward : a.hp.lr_cost);
-  const float extra_sumsq = (is_actor && a.kind == SPO_LOSS_CRITIC_ONLY) ? ctrl->extra_sumsq : 0.f;
+  const float extra_sumsq = (is_actor && q == 0 && a.kind == SPO_LOSS_CRITIC_ONLY && !idle) ? ctrl->extra_sumsq : 0.f;
   const float vcoef = (net == 1) ? a.hp.value_coef : 1.f;
   const float reg = is_actor ? 0.f : __fmul_rn(vcoef, __fmul_rn(a.hp.critic_l2, 2.f));
 
-  // The next tile is staged in registers: its rows are requested with plain loads at the end of the current
-  // step (between the arrive and the wait of the cluster barrier) and stored to shared memory at the top of the
-  // next one, Adam in between hides the latency.  (cp.async gathers cost 1.5 k cycles of issue per tile for
-  // the rows plus 1.7 k for the side data -- LDGSTS issues at ~50 cycles per warp instruction here,
-  // profiles/r01_update_phase_cycles.md.)
-  // Item it of this thread: obs_dim % 4 == 0: float4 chunk i = tid + it*UT -> (row, chunk) = (i / (D/4), i % (D/4)),
-  // decoded once; otherwise scalar element i -> (i / D, i % D).
-  constexpr int PF_MAX = (NT1 == 1) ? 2 : 4;
+  // ---- staging of the next tile in registers (requested at the end of a step, stored at the top of the next) ----
+  constexpr int PF_MAX = 4 * NT1;
   const bool vec_rows = (D & 3) == 0;
   int pf_rc[PF_MAX];
   int pf_n = 0;
@@ -284,15 +328,16 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     pf_rc[it] = 0xFF;
     if (vec_rows && i < SPO_ROWS * per_row) { pf_rc[it] = (i / per_row) | ((i % per_row) << 8); pf_n = it + 1; }
   }
-  float xr[4 * PF_MAX];   // staged observation values
-  float auxr[4];          // staged side data: column c = q8s + 8*i of row r8s
+  float xr[4 * PF_MAX];
 #pragma unroll
   for (int i = 0; i < 4 * PF_MAX; ++i) xr[i] = 0.f;
+  // side data: thread (row r4s = tid >> 2, lane q4s = tid & 3) stages columns q4s, q4s + 4, ...
+  constexpr int AUX_IT = 7;   // 4 * 7 = 28 >= A + 2 + 2A for A = 8
+  float auxr[AUX_IT];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) auxr[i] = 0.f;
-  const int r8s = tid >> 3, q8s = tid & 7;
+  for (int i = 0; i < AUX_IT; ++i) auxr[i] = 0.f;
+  const int r4s = tid >> 2, q4s = tid & 3;
   const int aux_per = !is_actor ? 1 : A + 2 + (a.kind == SPO_LOSS_FOCOPS ? 2 * A : 0);   // <= 26 columns
-  // shared-memory slot of side-data column c
   auto aux_slot = [&](int c) {
     if (!is_actor) return AUX_TGT;
     if (c < A) return c;
@@ -301,8 +346,6 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     if (c < 2 * A + 2) return AUX_OMEAN + (c - A - 2);
     return AUX_OSTD + (c - 2 * A - 2);
   };
-
-  // global source of side-data column c (row g at src + g * (A or 1))
   auto aux_by_row = [&](int c) { return is_actor && (c < A || c >= A + 2); };
   auto aux_src = [&](int c) -> const float* {
     if (!is_actor) return (net == 1) ? a.data.target_r : a.data.target_c;
@@ -312,29 +355,28 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     if (c < 2 * A + 2) return a.data.old_mean + (c - A - 2);
     return a.data.old_std + (c - 2 * A - 2);
   };
-  const float* aux_src0 = aux_src(q8s < aux_per ? q8s : 0);   // column q8s: decoded once
-  const int aux_mul0 = aux_by_row(q8s) ? A : 1;
-  const int aux_slot0 = aux_slot(q8s < aux_per ? q8s : 0);
+  const float* aux_src0 = aux_src(q4s < aux_per ? q4s : 0);
+  const int aux_mul0 = aux_by_row(q4s) ? A : 1;
+  const int aux_slot0 = aux_slot(q4s < aux_per ? q4s : 0);
 
   int64_t step_idx = 0;
 #ifdef SPO_PHASE_TIMERS
-  __shared__ unsigned long long sm_phase__[16];
-  if (tid < 16) sm_phase__[tid] = 0ull;
+  __shared__ unsigned long long sm_phase__[24];
+  if (tid < 24) sm_phase__[tid] = 0ull;
+  long long phase_t__ = clock64();
 #endif
-  // tile (step, sub) after n more tiles -- no 64-bit division on the per-step path
   auto tile_after = [&](int64_t step, int sub, int n, int64_t& step_o, int& sub_o) {
     step_o = step; sub_o = sub;
     for (int i = 0; i < n; ++i)
       if (++sub_o == tps) { sub_o = 0; ++step_o; }
   };
-  // request the rows of tile q = (step, sub): global -> registers (rows beyond the valid range stage zeros)
-  auto load_next = [&](int64_t q, int64_t step, int sub) {
-    if (!active || q >= n_tiles) return;
+  auto load_next = [&](int64_t qt, int64_t step, int sub) {
+    if (!active || qt >= n_tiles) return;
     int64_t rs = a.perm_len - step * a.batch;
     if (rs > a.batch) rs = a.batch;
     int rows = static_cast<int>(rs) - sub * SPO_ROWS;
     rows = rows < 0 ? 0 : (rows > SPO_ROWS ? SPO_ROWS : rows);
-    const int64_t* ridx = idxbuf + (q & 1) * SPO_ROWS;
+    const int64_t* ridx = idxbuf + (qt & 1) * SPO_ROWS;
     if (vec_rows) {
 #pragma unroll
       for (int it = 0; it < PF_MAX; ++it) {
@@ -350,20 +392,19 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         xr[it] = (r < rows) ? __ldg(a.data.obs + ridx[r] * D + c) : 0.f;
       }
     }
-    const bool rv = r8s < rows;
-    const int64_t g = rv ? ridx[r8s] : 0;
-    auxr[0] = (rv && q8s < aux_per) ? __ldg(aux_src0 + g * aux_mul0) : 0.f;
-    if (aux_per > 8) {   // wide action spaces only
+    const bool rv = r4s < rows;
+    const int64_t g = rv ? ridx[r4s] : 0;
+    auxr[0] = (rv && q4s < aux_per) ? __ldg(aux_src0 + g * aux_mul0) : 0.f;
+    if (aux_per > 4) {
 #pragma unroll
-      for (int i = 1; i < 4; ++i) {
-        const int c = q8s + 8 * i;
+      for (int i = 1; i < AUX_IT; ++i) {
+        const int c = q4s + 4 * i;
         float v = 0.f;
         if (rv && c < aux_per) v = __ldg(aux_src(c) + g * (aux_by_row(c) ? A : 1));
         auxr[i] = v;
       }
     }
   };
-  // registers -> the tile buffers
   auto store_next = [&]() {
     if (!active) return;
     if (vec_rows) {
@@ -379,57 +420,35 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         if (r < SPO_ROWS) x[r * ldx + c] = xr[it];
       }
     }
-    if (q8s < aux_per) aux[r8s * AUXW + aux_slot0] = auxr[0];
-    if (aux_per > 8) {
+    if (q4s < aux_per) aux[r4s * AUXW + aux_slot0] = auxr[0];
+    if (aux_per > 4) {
 #pragma unroll
-      for (int i = 1; i < 4; ++i) {
-        const int c = q8s + 8 * i;
-        if (c < aux_per) aux[r8s * AUXW + aux_slot(c)] = auxr[i];
+      for (int i = 1; i < AUX_IT; ++i) {
+        const int c = q4s + 4 * i;
+        if (c < aux_per) aux[r4s * AUXW + aux_slot(c)] = auxr[i];
       }
     }
   };
-  // row indices of tile q -> idxbuf slot q & 1 (lands with the cp.async group it is committed in)
-  auto fetch_idx = [&](int64_t q, int64_t step, int sub) {
-    if (!active || q >= n_tiles) return;
+  auto fetch_idx = [&](int64_t qt, int64_t step, int sub) {
+    if (!active || qt >= n_tiles) return;
     const int64_t first = step * a.batch + sub * SPO_ROWS;
     int64_t rs = a.perm_len - first;
     if (rs > a.batch - sub * SPO_ROWS) rs = a.batch - sub * SPO_ROWS;
-    if (tid < SPO_ROWS && tid < rs) cp_async8(idxbuf + (q & 1) * SPO_ROWS + tid, a.perm + first + tid);
+    if (tid < SPO_ROWS && tid < rs) cp_async8(idxbuf + (qt & 1) * SPO_ROWS + tid, a.perm + first + tid);
   };
-
-#ifdef SPO_PHASE_TIMERS
-  long long phase_t__ = clock64();
-#endif
-  // hidden layer: out[r][j] = tanh(b[j] + sum_k in[r][k] * W[j][k]) on the tensor pipe.  The 64-wide case
-  // (second layer always; first layer when obs_dim pads to 64) gets compile-time strides: immediate
-  // offsets instead of per-load address arithmetic (2.7 k -> 1.7 k cycles per product)
-  auto hidden = [&](const float* in, int ldin, int K, const float* W, int ldw, const float* bias, float* out) {
-    float acc[1][2][4];
-    spo_mma_zero<1>(acc);
-    spo_warp_mma_3xtf32<1>(acc, in, ldin, 1, W, 1, ldw, mb, nb, K);   // all extents are constants after inlining
-    PHASE_MARK(11);  // (sub) hidden-layer GEMM only, as seen by warp 0
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      const int r = mb + g8, j = nb + nt * 8 + 2 * t4;
-      const float2 bb = *reinterpret_cast<const float2*>(bias + j);
-      *reinterpret_cast<float2*>(out + r * SPO_LDH + j) = make_float2(spo_tanh_fast(acc[0][nt][0] + bb.x), spo_tanh_fast(acc[0][nt][1] + bb.y));
-      *reinterpret_cast<float2*>(out + (r + 8) * SPO_LDH + j) = make_float2(spo_tanh_fast(acc[0][nt][2] + bb.x), spo_tanh_fast(acc[0][nt][3] + bb.y));
-    }
-  };
-  // column sums over the 64 rows of a [64][SPO_LDH] tile, all 512 threads: thread (c = tid >> 3, q = tid & 7)
-  // adds rows q, q+8, ... (bank = 4q + c: conflict-free), three shuffles finish the sum
+  // column sums over the 64 rows of a [64][LDS] slice: thread (c = tid >> 4, rg = tid & 15) adds rows rg + 16 i
   auto colsum_into = [&](const float* buf, float* dst) {
-    const int c = tid >> 3, q8 = tid & 7;
+    const int c = tid >> 4, rg = tid & 15;
     float s = 0.f;
 #pragma unroll
-    for (int rr = 0; rr < SPO_ROWS / 8; ++rr) s += buf[(rr * 8 + q8) * SPO_LDH + c];
+    for (int i = 0; i < 4; ++i) s += buf[(rg + 16 * i) * LDS + c];
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (q8 == 0) dst[c] += s;
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    if (rg == 0) dst[c] += s;
   };
 
-  __syncthreads();
   {
     int64_t st; int sb;
     fetch_idx(0, 0, 0);
@@ -442,23 +461,40 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     cp_async_commit();
   }
 
-  // gradient accumulators = accumulator fragments of the dW products (persist across the tiles of a step)
-  float gW2[FE], gW1[NT1][FE];
+  // shared::cluster addresses of the buffers this CTA pulls from: the four CTAs of its net, all CTAs for the norm
+  uint32_t r_h1[NQ], r_yp[NQ], r_dh[NQ];
 #pragma unroll
-  for (int e = 0; e < FE; ++e) {
-    gW2[e] = 0.f;
+  for (int d = 0; d < NQ; ++d) {
+    r_h1[d] = mapa(smem_u32(h1), grp0 + d);
+    r_yp[d] = mapa(smem_u32(ypo), grp0 + d);
+    r_dh[d] = mapa(smem_u32(dh1f), grp0 + d);
+  }
+  const uint32_t r_xchg = mapa(smem_u32(xchg), lane < NCTA ? lane : 0);
+
+  // gradient accumulators = accumulator fragments of the dW products (persist across the tiles of a step)
+  float gW2[1][4], gW1[NT1][4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    gW2[0][e] = 0.f;
 #pragma unroll
     for (int i = 0; i < NT1; ++i) gW1[i][e] = 0.f;
   }
-  for (int i = tid; i < SP; i += UT) gsmall[i] = 0.f;
-  double acc_loss = 0.0;        // thread 0: sum over steps of this net's logged loss
-  float step_loss = 0.f;        // thread 0: loss numerator of the current step (sum over its tiles)
-  float step_aux0 = 0.f, step_aux1 = 0.f;  // FOCOPS: sum(ratio*adv), sum(mask)
+  double acc_loss = 0.0;        // thread 0 of quarter 0: sum over steps of this net's logged loss
+  float step_loss = 0.f, step_aux0 = 0.f, step_aux1 = 0.f;   // thread 0: loss numerators of the current step
 
-  int64_t step = 0;   // tile q = (step, sub)
+  // cross-GPU staging of this CTA: [parity][source rank][cta][dp_slot_words] 8-byte words
+  const int world = a.comm.world, me = a.comm.rank;
+  constexpr int DPW = dp_slot_words(NT1);
+  const int mt = wid & 3, ntl = wid >> 2;     // 16 x 8 tile of the 64 x 16 slice products
+  const int rA = mt * 16 + g8, cA = ntl * 8 + 2 * t4;
+  const int r4 = tid >> 2, k4 = tid & 3;      // (row, quarter-of-a-slice) mapping of the element-wise phases
+
+  cluster.sync();   // nobody reads a peer's shared memory before every CTA of the cluster runs
+
+  int64_t step = 0;
   int sub = 0;
   auto next_tile = [&]() { if (++sub == tps) { sub = 0; ++step; } };
-  for (int64_t q = 0; q < n_tiles; ++q, next_tile()) {
+  for (int64_t qt = 0; qt < n_tiles; ++qt, next_tile()) {
     int64_t rs64 = a.perm_len - step * a.batch;
     if (rs64 > a.batch) rs64 = a.batch;
     const int rows_step = static_cast<int>(rs64);
@@ -466,21 +502,60 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     rows = rows < 0 ? 0 : (rows > SPO_ROWS ? SPO_ROWS : rows);
     const bool last_tile = (sub == tps - 1);
     const float inv_b = __fdiv_rn(1.f, static_cast<float>(rows_step));
-    // stage tile q+1 (its indices landed a step ago) and request the indices of tile q+2
+    const unsigned seq = static_cast<unsigned>(a.comm.seq_base + static_cast<unsigned long long>(step_idx) + 1ull);
+    const int par = static_cast<int>(step_idx & 1);
     auto stage_next = [&]() {
       int64_t st; int sb;
       tile_after(step, sub, 1, st, sb);
-      load_next(q + 1, st, sb);
+      load_next(qt + 1, st, sb);
       tile_after(st, sb, 1, st, sb);
-      fetch_idx(q + 2, st, sb);
+      fetch_idx(qt + 2, st, sb);
       cp_async_commit();
     };
+    // push `n` of this thread's gradient values (word index w0 + i * UT + tid of the CTA slot) to every peer GPU
+    auto dp_push = [&](const float* vals, auto n_c, int w0) {
+      constexpr int n = decltype(n_c)::value;
+      const size_t base = ((static_cast<size_t>(seq & 1u) * world + me) * NCTA + rank) * DPW;
+      for (int r = 0; r < world; ++r) {
+        if (r == me) continue;
+        float2* dst = reinterpret_cast<float2*>(a.comm.grad_bufs[r]) + base;
+#pragma unroll
+        for (int i = 0; i < n; ++i) st_ll(dst + w0 + i * UT + tid, vals[i], seq);
+      }
+    };
+    // rank-ordered sum of `n` values with the words received from every peer GPU, scaled by 1/world
+    auto dp_sum = [&](float* vals, auto n_c, int w0) {
+      constexpr int n = decltype(n_c)::value;
+      const unsigned limit = a.comm.spin_limit ? a.comm.spin_limit : 400000000u;
+      float acc[n];
+#pragma unroll
+      for (int i = 0; i < n; ++i) acc[i] = 0.f;
+      for (int r = 0; r < world; ++r) {
+        if (r == me) {
+#pragma unroll
+          for (int i = 0; i < n; ++i) acc[i] += vals[i];
+          continue;
+        }
+        const float2* src = reinterpret_cast<const float2*>(a.comm.grad_bufs[me]) + ((static_cast<size_t>(seq & 1u) * world + r) * NCTA + rank) * DPW;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          float v = 0.f;
+          unsigned polls = 0;
+          while (!ld_ll(src + w0 + i * UT + tid, seq, v)) {
+            if (*reinterpret_cast<volatile int*>(&comm_dead)) { v = 0.f; break; }
+            if (++polls > limit) { comm_dead = 1; atomicExch(&ctrl->stop, 2); v = 0.f; break; }
+          }
+          acc[i] += v;
+        }
+      }
+      const float inv_w = __fdiv_rn(1.f, static_cast<float>(world));
+#pragma unroll
+      for (int i = 0; i < n; ++i) vals[i] = __fmul_rn(acc[i], inv_w);
+    };
 
-    store_next();      // tile q: registers -> shared memory (every warp left tile q-1 barriers ago)
-    TRACE_MARK(22);
-    __syncthreads();   // tile q in place; Adam's weight writes visible
-    TRACE_MARK(15);
-    if (is_actor && tid >= UT - 32 && tid - (UT - 32) < A) {
+    store_next();      // tile qt: registers -> shared memory (every warp left tile qt-1 before the last barrier)
+    __syncthreads();   // tile qt in place; Adam's weight writes visible
+    if (is_actor && active && tid >= UT - 32 && tid - (UT - 32) < A) {
       // row-independent pieces of the Gaussian log-density (log_std changed in the last Adam step)
       const int j = tid - (UT - 32);
       const float sd = expf(log_std[j]);
@@ -490,124 +565,170 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     }
     PHASE_MARK(0);   // top of the step: stage-in + barrier
 
+    // ---------------- forward, layer 1: own 16 units ----------------
     if (active) {
-      // ---------------- forward ----------------
-      hidden(x, ldx, KX, w1, ldx, b1, h1);
-      __syncthreads();
-      PHASE_MARK(1);
-      hidden(h1, SPO_LDH, SPO_HID, w2, SPO_LDH, b2, h2);
-      __syncthreads();
-      PHASE_MARK(2);
-      // output layer: thread (row r = tid >> 3, eighth q8 of k): h2 chunks q8 and q8+8 stay in registers for all
-      // outputs (the tile is read from shared memory once); three shuffles finish each dot product
-      const int r8 = tid >> 3, q8 = tid & 7;
-      {
-        const float4 ha = *reinterpret_cast<const float4*>(h2 + r8 * SPO_LDH + 4 * q8);
-        const float4 hb = *reinterpret_cast<const float4*>(h2 + r8 * SPO_LDH + 32 + 4 * q8);
-        for (int o = 0; o < O; ++o) {
-          const float4 wa = *reinterpret_cast<const float4*>(w3 + o * SPO_HID + 4 * q8);
-          const float4 wb = *reinterpret_cast<const float4*>(w3 + o * SPO_HID + 32 + 4 * q8);
-          float sacc = (fmaf(ha.x, wa.x, ha.y * wa.y) + fmaf(ha.z, wa.z, ha.w * wa.w)) +
-                       (fmaf(hb.x, wb.x, hb.y * wb.y) + fmaf(hb.z, wb.z, hb.w * wb.w));
-          sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-          sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-          sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
-          if (q8 == 0) y[r8 * SPO_MAX_ACT + o] = sacc + b3[o];
-        }
-      }
-      TRACE_MARK(17);
-      __syncthreads();
-      if (tid == UT - 32 && last_tile) {
-        // Adam scalars of this step, computed once per CTA by a thread that has no loss row; only this
-        // thread tracks the beta powers (fp64, like torch's Python floats)
+      float acc[1][4];
+      warp_gemm<1, 8 * NT1, false>(acc, x, ldx, 1, w1s, 1, ldx, mt * 16, ntl * 8);
+      const float2 bb = *reinterpret_cast<const float2*>(b1s + cA);
+      *reinterpret_cast<float2*>(h1 + rA * LDA + SL * q + cA) = make_float2(spo_tanh_fast(acc[0][0] + bb.x), spo_tanh_fast(acc[0][1] + bb.y));
+      *reinterpret_cast<float2*>(h1 + (rA + 8) * LDA + SL * q + cA) = make_float2(spo_tanh_fast(acc[0][2] + bb.x), spo_tanh_fast(acc[0][3] + bb.y));
+      if (tid == 0 && last_tile) {
+        // Adam scalars of this step (fp64 like torch's Python floats); the barriers of the step publish them
         b1pow *= static_cast<double>(a.hp.beta1);
         b2pow *= static_cast<double>(a.hp.beta2);
         adk[0] = static_cast<float>(1.0 - static_cast<double>(a.hp.beta1));
         adk[1] = a.hp.beta2;
         adk[2] = static_cast<float>(1.0 - static_cast<double>(a.hp.beta2));
-        // the root and the quotients in fp32 (<= 1 ulp from torch's fp64-then-round)
         adk[3] = __fdiv_rn(1.f, sqrtf(static_cast<float>(1.0 - b2pow)));
         adk[4] = a.hp.adam_eps;
         adk[5] = -__fdiv_rn(lr, static_cast<float>(1.0 - b1pow));
       }
-
-      // ---------------- loss and d loss / d output: thread (row r8, action dim j = q8) ----------------
+    }
+    PHASE_MARK(1);   // layer-1 product + epilogue
+    __syncthreads();
+    cluster_arrive(tid);
+    cluster_wait();                                   // ---- barrier 1: every h1 slice of the cluster is in place
+    PHASE_MARK(2);
+    float yv[SPO_MAX_ACT];                            // output-layer rows of this thread's row r4 (after the y exchange)
+    if (active) {
+      // all-gather of h1: one float4 per peer, thread (row r4, chunk k4)
+      float4 v[NQ];
+#pragma unroll
+      for (int d = 0; d < NQ; ++d)
+        if (d != q) v[d] = ld_dsmem_f4(r_h1[d] + static_cast<uint32_t>((r4 * LDA + SL * d + 4 * k4) * 4));
+#pragma unroll
+      for (int d = 0; d < NQ; ++d)
+        if (d != q) *reinterpret_cast<float4*>(h1 + r4 * LDA + SL * d + 4 * k4) = v[d];
+      __syncthreads();
+      PHASE_MARK(3);   // h1 pull
+      // ---------------- forward, layer 2 + partial output layer ----------------
+      {
+        float acc[1][4];
+        warp_gemm<1, 8, false>(acc, h1, LDA, 1, w2s, 1, LDA, mt * 16, ntl * 8);
+        const float2 bb = *reinterpret_cast<const float2*>(b2s + cA);
+        *reinterpret_cast<float2*>(h2s + rA * LDS + cA) = make_float2(spo_tanh_fast(acc[0][0] + bb.x), spo_tanh_fast(acc[0][1] + bb.y));
+        *reinterpret_cast<float2*>(h2s + (rA + 8) * LDS + cA) = make_float2(spo_tanh_fast(acc[0][2] + bb.x), spo_tanh_fast(acc[0][3] + bb.y));
+      }
+      __syncthreads();
+      // output layer, partial over the own 16 hidden units: thread (row r4, quarter of the slice k4), two shuffles
+      {
+        const float4 hv = *reinterpret_cast<const float4*>(h2s + r4 * LDS + 4 * k4);
+        for (int o = 0; o < O; ++o) {
+          const float4 wv = *reinterpret_cast<const float4*>(w3s + o * SL + 4 * k4);
+          float sacc = fmaf(hv.x, wv.x, hv.y * wv.y) + fmaf(hv.z, wv.z, hv.w * wv.w);
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+          sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+          if (k4 == (o & 3)) ypo[r4 * SPO_MAX_ACT + o] = sacc;
+        }
+      }
+    }
+    PHASE_MARK(4);   // layer 2 + partial output layer
+    __syncthreads();
+    cluster_arrive(tid);
+    cluster_wait();                                   // ---- barrier 2: partial outputs in place
+    PHASE_MARK(5);
+    if (active) {
+      // y[r][o] = b3[o] + sum over the four quarters: lane k4 of a row pulls quarter k4's partial (two float4),
+      // a butterfly over the four lanes finishes the sum (fixed order (p0 + p1) + (p2 + p3) in every CTA)
+      {
+        float4 lo, hi = make_float4(0.f, 0.f, 0.f, 0.f);
+        lo = ld_dsmem_f4(r_yp[k4] + static_cast<uint32_t>(r4 * SPO_MAX_ACT * 4));
+        if (O > 4) hi = ld_dsmem_f4(r_yp[k4] + static_cast<uint32_t>((r4 * SPO_MAX_ACT + 4) * 4));
+        yv[0] = lo.x; yv[1] = lo.y; yv[2] = lo.z; yv[3] = lo.w; yv[4] = hi.x; yv[5] = hi.y; yv[6] = hi.z; yv[7] = hi.w;
+#pragma unroll
+        for (int o = 0; o < SPO_MAX_ACT; ++o) {
+          yv[o] += __shfl_xor_sync(0xffffffffu, yv[o], 1);
+          yv[o] += __shfl_xor_sync(0xffffffffu, yv[o], 2);
+          yv[o] = (o < O) ? __fadd_rn(yv[o], b3[o]) : 0.f;
+        }
+      }
+      // ---------------- loss and d loss / d output: thread (row r4, action dims j = k4 and k4 + 4) ----------------
       float part0 = 0.f, part1 = 0.f, part2 = 0.f;
       {
-        const int r = r8, j = q8;
+        const int r = r4;
         const bool valid = r < rows;
-        const float* ax = aux + r * AUXW;
+        float* ax = aux + r * AUXW;
         if (!is_actor) {
-          if (j == 0) {
-            const float dv = __fsub_rn(y[r * SPO_MAX_ACT], ax[AUX_TGT]);
+          if (k4 == 0) {
+            const float dv = __fsub_rn(yv[0], ax[AUX_TGT]);
             part0 = valid ? __fmul_rn(dv, dv) : 0.f;
             dy[r * SPO_MAX_ACT] = valid ? __fmul_rn(__fmul_rn(__fmul_rn(2.f, dv), inv_b), vcoef) : 0.f;
           }
         } else {
-          const bool jv = j < A;
-          float term = 0.f, klj = 0.f, dmu_lp = 0.f, dls_lp = 0.f, dmu_kl = 0.f, dls_kl = 0.f;
-          if (jv) {
-            const float mean = y[r * SPO_MAX_ACT + j];
-            const float std = lsc[4 * j], inv_var = lsc[4 * j + 1];
-            const float diff = __fsub_rn(ax[j], mean);
-            const float d2 = __fmul_rn(diff, diff);
-            const float q2 = __fmul_rn(d2, inv_var);           // (a - mu)^2 / var
-            term = __fsub_rn(__fsub_rn(__fmul_rn(-0.5f, q2), lsc[4 * j + 2]), kLogSqrt2Pi);
-            dmu_lp = __fmul_rn(diff, inv_var);
-            dls_lp = __fsub_rn(q2, 1.f);
-            if (a.kind == SPO_LOSS_FOCOPS) {
-              // KL(new || old), torch _kl_normal_normal(p=new, q=old)
-              // padded rows carry zeros: keep their (discarded) arithmetic finite
-              const float os = valid ? ax[AUX_OSTD + j] : 1.f, om = ax[AUX_OMEAN + j];
-              const float ios = __fdiv_rn(1.f, os);
-              const float sr = __fmul_rn(std, ios);
-              const float vr = __fmul_rn(sr, sr);
-              const float dm = __fmul_rn(__fsub_rn(mean, om), ios);
-              const float t1 = __fmul_rn(dm, dm);
-              klj = __fmul_rn(0.5f, __fsub_rn(__fsub_rn(__fadd_rn(vr, t1), 1.f), logf(vr)));
-              dmu_kl = __fmul_rn(dm, ios);
-              dls_kl = __fsub_rn(vr, 1.f);
+          float term[2] = {0.f, 0.f}, klj[2] = {0.f, 0.f}, dmu_lp[2], dls_lp[2], dmu_kl[2] = {0.f, 0.f}, dls_kl[2] = {0.f, 0.f};
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int j = k4 + 4 * h;
+            dmu_lp[h] = 0.f; dls_lp[h] = 0.f;
+            if (j < A) {
+              // yv[j] with a compile-time index: j = k4 + 4h
+              const float m_lo = (k4 == 0) ? yv[0] : (k4 == 1) ? yv[1] : (k4 == 2) ? yv[2] : yv[3];
+              const float m_hi = (k4 == 0) ? yv[4] : (k4 == 1) ? yv[5] : (k4 == 2) ? yv[6] : yv[7];
+              const float mean = h ? m_hi : m_lo;
+              const float std = lsc[4 * j], inv_var = lsc[4 * j + 1];
+              const float diff = __fsub_rn(ax[j], mean);
+              const float d2 = __fmul_rn(diff, diff);
+              const float q2 = __fmul_rn(d2, inv_var);           // (a - mu)^2 / var
+              term[h] = __fsub_rn(__fsub_rn(__fmul_rn(-0.5f, q2), lsc[4 * j + 2]), kLogSqrt2Pi);
+              dmu_lp[h] = __fmul_rn(diff, inv_var);
+              dls_lp[h] = __fsub_rn(q2, 1.f);
+              if (a.kind == SPO_LOSS_FOCOPS) {
+                // KL(new || old), torch _kl_normal_normal(p=new, q=old); padded rows carry zeros: keep them finite
+                const float os = valid ? ax[AUX_OSTD + j] : 1.f, om = ax[AUX_OMEAN + j];
+                const float ios = __fdiv_rn(1.f, os);
+                const float sr = __fmul_rn(std, ios);
+                const float vr = __fmul_rn(sr, sr);
+                const float dm = __fmul_rn(__fsub_rn(mean, om), ios);
+                const float t1 = __fmul_rn(dm, dm);
+                klj[h] = __fmul_rn(0.5f, __fsub_rn(__fsub_rn(__fadd_rn(vr, t1), 1.f), logf(vr)));
+                dmu_kl[h] = __fmul_rn(dm, ios);
+                dls_kl[h] = __fsub_rn(vr, 1.f);
+              }
             }
           }
-          // sums over the action dims: the 8 lanes of a row (lanes j >= A hold zeros)
-          float lp = term, kl = klj;
+          // sums over the action dims: the 4 lanes of a row, two dims each
+          float lp = term[0] + term[1], kl = klj[0] + klj[1];
           lp += __shfl_xor_sync(0xffffffffu, lp, 1);
           lp += __shfl_xor_sync(0xffffffffu, lp, 2);
-          lp += __shfl_xor_sync(0xffffffffu, lp, 4);
           if (a.kind == SPO_LOSS_FOCOPS) {
             kl += __shfl_xor_sync(0xffffffffu, kl, 1);
             kl += __shfl_xor_sync(0xffffffffu, kl, 2);
-            kl += __shfl_xor_sync(0xffffffffu, kl, 4);
           }
           const float ratio = expf(__fsub_rn(lp, ax[AUX_LOGP]));
           const float adv = ax[AUX_ADV];
           if (a.kind == SPO_LOSS_PPO_CLIP) {
             const float s1 = __fmul_rn(ratio, adv);
             const float s2 = __fmul_rn(fminf(fmaxf(ratio, a.hp.clip_lo), a.hp.clip_hi), adv);
-            if (j == 0) part0 = valid ? -fminf(s1, s2) : 0.f;
+            if (k4 == 0) part0 = valid ? -fminf(s1, s2) : 0.f;
             // d(-mean(min))/d logp = -(1/B) * adv * ratio where the unclipped branch is active
             const float gl = (valid && s1 <= s2) ? -__fmul_rn(__fmul_rn(adv, ratio), inv_b) : 0.f;
-            if (jv) {
-              dy[r * SPO_MAX_ACT + j] = __fmul_rn(gl, dmu_lp);
-              dls[r * SPO_MAX_ACT + j] = __fmul_rn(gl, dls_lp);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int j = k4 + 4 * h;
+              if (j < A) {
+                dy[r * SPO_MAX_ACT + j] = __fmul_rn(gl, dmu_lp[h]);
+                dls[r * SPO_MAX_ACT + j] = __fmul_rn(gl, dls_lp[h]);
+              }
             }
           } else {
-            // FOCOPS needs mean(mask) over the minibatch before gradients can be formed:
-            // stash per-row pieces, finish after the block reduction below.
+            // FOCOPS needs mean(mask) over the minibatch before gradients can be formed: stash per-row pieces,
+            // finish after the block reduction below
             const float mask = (valid && kl <= a.hp.focops_kl) ? 1.f : 0.f;
-            if (j == 0) {
+            if (k4 == 0) {
               part0 = valid ? __fmul_rn(kl, mask) : 0.f;
               part1 = valid ? __fmul_rn(ratio, adv) : 0.f;
               part2 = mask;
             }
-            if (jv) {
-              // first term: (1/B) * mask * d kl ; second term scaled later by mean(mask)
-              const float gl = valid ? __fmul_rn(__fmul_rn(adv, ratio), inv_b) : 0.f;
-              dy[r * SPO_MAX_ACT + j] = __fmul_rn(__fmul_rn(mask, inv_b), dmu_kl);
-              dls[r * SPO_MAX_ACT + j] = __fmul_rn(__fmul_rn(mask, inv_b), dls_kl);
-              y[r * SPO_MAX_ACT + j] = __fmul_rn(gl, dmu_lp);
-              // d logp / d log_std piece: into the (now free) old-mean slot of the current aux row
-              const_cast<float*>(ax)[AUX_OMEAN + j] = __fmul_rn(gl, dls_lp);
+            const float gl = valid ? __fmul_rn(__fmul_rn(adv, ratio), inv_b) : 0.f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int j = k4 + 4 * h;
+              if (j < A) {
+                dy[r * SPO_MAX_ACT + j] = __fmul_rn(__fmul_rn(mask, inv_b), dmu_kl[h]);
+                dls[r * SPO_MAX_ACT + j] = __fmul_rn(__fmul_rn(mask, inv_b), dls_kl[h]);
+                y[r * SPO_MAX_ACT + j] = __fmul_rn(gl, dmu_lp[h]);
+                ax[AUX_OMEAN + j] = __fmul_rn(gl, dls_lp[h]);   // the old-mean slot of the row is free now
+              }
             }
           }
         }
@@ -615,7 +736,6 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         if (is_actor && a.kind == SPO_LOSS_FOCOPS) { part1 = spo_warp_sum(part1); part2 = spo_warp_sum(part2); }
         if (lane == 0) { red[wid * 4 + 0] = part0; red[wid * 4 + 1] = part1; red[wid * 4 + 2] = part2; }
       }
-      TRACE_MARK(18);
       __syncthreads();
       if (tid == 0) {
         float l0 = 0.f, l1 = 0.f, l2 = 0.f;
@@ -626,410 +746,308 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         step_aux1 += l2;
       }
       if (is_actor && a.kind == SPO_LOSS_FOCOPS) {
-        // This formulation needs the whole minibatch in one tile (batch <= 64): mean(mask)
-        // and the per-row pieces are combined here.  (focops.py uses batch 64.)
+        // This formulation needs the whole minibatch in one tile (batch <= 64).  (focops.py uses batch 64.)
         float msum = 0.f;
 #pragma unroll
         for (int w = 0; w < UT / 32; ++w) msum += red[w * 4 + 2];
         const float mbar = __fmul_rn(msum, inv_b);
         const float c2 = -__fmul_rn(__fdiv_rn(1.f, a.hp.focops_lam), mbar);
-        if (q8 < A) {
-          const float* ax = aux + r8 * AUXW;
-          dy[r8 * SPO_MAX_ACT + q8] = __fadd_rn(dy[r8 * SPO_MAX_ACT + q8], __fmul_rn(c2, y[r8 * SPO_MAX_ACT + q8]));
-          dls[r8 * SPO_MAX_ACT + q8] = __fadd_rn(dls[r8 * SPO_MAX_ACT + q8], __fmul_rn(c2, ax[AUX_OMEAN + q8]));
+        const float* ax = aux + r4 * AUXW;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = k4 + 4 * h;
+          if (j < A) {
+            dy[r4 * SPO_MAX_ACT + j] = __fadd_rn(dy[r4 * SPO_MAX_ACT + j], __fmul_rn(c2, y[r4 * SPO_MAX_ACT + j]));
+            dls[r4 * SPO_MAX_ACT + j] = __fadd_rn(dls[r4 * SPO_MAX_ACT + j], __fmul_rn(c2, ax[AUX_OMEAN + j]));
+          }
         }
         __syncthreads();
       }
+      PHASE_MARK(6);   // y pull + loss rows
 
-      PHASE_MARK(3);   // output layer + loss rows
       // ---------------- backward ----------------
-      // (a) small grads of the output layer: dW3[o][k] = sum_r dy[r][o] h2[r][k], thread (k = tid >> 3, q8): rows
-      //     q8, q8+8, ... with the h2 column in registers for all outputs; three shuffles finish each sum.
-      //     db3[o] / dlog_std[j] (column sums of dy / dls): the first four warps, same row split.
+      // (a) small grads of the output layer, own 16 columns: dW3[o][kk] = sum_r dy[r][o] h2[r][kk];
+      //     thread (kk = tid >> 4, rg = tid & 15) adds rows rg + 16 i, four shuffles finish each sum.
+      //     db3[o] / dlog_std[j] (replicated in the four CTAs): column sums of dy / dls, same split.
       {
-        const int k = r8;
-        float hv[SPO_ROWS / 8];
+        const int kk = tid >> 4, rg = tid & 15;
+        float hv[4];
 #pragma unroll
-        for (int rr = 0; rr < SPO_ROWS / 8; ++rr) hv[rr] = h2[(rr * 8 + q8) * SPO_LDH + k];
+        for (int i = 0; i < 4; ++i) hv[i] = h2s[(rg + 16 * i) * LDS + kk];
         for (int o = 0; o < O; ++o) {
           float sa = 0.f;
 #pragma unroll
-          for (int rr = 0; rr < SPO_ROWS / 8; ++rr) sa = fmaf(dy[(rr * 8 + q8) * SPO_MAX_ACT + o], hv[rr], sa);
+          for (int i = 0; i < 4; ++i) sa = fmaf(dy[(rg + 16 * i) * SPO_MAX_ACT + o], hv[i], sa);
           sa += __shfl_xor_sync(0xffffffffu, sa, 1);
           sa += __shfl_xor_sync(0xffffffffu, sa, 2);
           sa += __shfl_xor_sync(0xffffffffu, sa, 4);
-          if (q8 == 0) gsmall[2 * SPO_HID + o * SPO_HID + k] += sa;
+          sa += __shfl_xor_sync(0xffffffffu, sa, 8);
+          if (rg == 0) gsmall[SP_W3 + o * SL + kk] += sa;
         }
-        if (tid < 128) {
-          const int c = tid >> 3, col = c & 7;          // c < 8: dy column (db3), else dls column (dlog_std)
-          const bool need = (c < 8) ? (col < O) : (col < sm.A_ls);
-          const float* src = (c < 8) ? dy : dls;
-          float sa = 0.f;
-          if (need) {
+        const int col = kk & 7;                    // kk < 8: dy column (db3), else dls column (dlog_std)
+        const bool need = (kk < 8) ? (col < O) : (is_actor && col < A);
+        const float* src = (kk < 8) ? dy : dls;
+        float sa = 0.f;
+        if (need) {
 #pragma unroll
-            for (int rr = 0; rr < SPO_ROWS / 8; ++rr) sa += src[(rr * 8 + q8) * SPO_MAX_ACT + col];
-          }
-          sa += __shfl_xor_sync(0xffffffffu, sa, 1);
-          sa += __shfl_xor_sync(0xffffffffu, sa, 2);
-          sa += __shfl_xor_sync(0xffffffffu, sa, 4);
-          if (need && q8 == 0) gsmall[2 * SPO_HID + O * SPO_HID + ((c < 8) ? col : O + col)] += sa;
+          for (int i = 0; i < 4; ++i) sa += src[(rg + 16 * i) * SPO_MAX_ACT + col];
         }
+        sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+        sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+        sa += __shfl_xor_sync(0xffffffffu, sa, 4);
+        sa += __shfl_xor_sync(0xffffffffu, sa, 8);
+        if (need && rg == 0) gsmall[(kk < 8 ? SP_B3 : SP_LS) + col] += sa;
       }
-      TRACE_MARK(19);
-      // (b) dz2[r][k] = (sum_o dy[r][o] * w3[o][k]) * (1 - h2[r][k]^2)
+      // (b) dz2[r][kk] = (sum_o dy[r][o] * w3[o][kk]) * (1 - h2[r][kk]^2), own 16 columns
       {
-        const int r0 = (tid >> 4) * 2, kk = (tid & 15) * 4;
-#pragma unroll
-        for (int ri = 0; ri < 2; ++ri) {
-          const int r = r0 + ri;
-          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int o = 0; o < O; ++o) {
-            const float d = dy[r * SPO_MAX_ACT + o];
-            const float4 wv = *reinterpret_cast<const float4*>(w3 + o * SPO_HID + kk);
-            s.x = fmaf(d, wv.x, s.x); s.y = fmaf(d, wv.y, s.y); s.z = fmaf(d, wv.z, s.z); s.w = fmaf(d, wv.w, s.w);
-          }
-          const float4 h = *reinterpret_cast<const float4*>(h2 + r * SPO_LDH + kk);
-          s.x *= (1.f - h.x * h.x); s.y *= (1.f - h.y * h.y); s.z *= (1.f - h.z * h.z); s.w *= (1.f - h.w * h.w);
-          *reinterpret_cast<float4*>(dz2 + r * SPO_LDH + kk) = s;
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int o = 0; o < O; ++o) {
+          const float d = dy[r4 * SPO_MAX_ACT + o];
+          const float4 wv = *reinterpret_cast<const float4*>(w3s + o * SL + 4 * k4);
+          s4.x = fmaf(d, wv.x, s4.x); s4.y = fmaf(d, wv.y, s4.y); s4.z = fmaf(d, wv.z, s4.z); s4.w = fmaf(d, wv.w, s4.w);
         }
+        const float4 h = *reinterpret_cast<const float4*>(h2s + r4 * LDS + 4 * k4);
+        s4.x *= (1.f - h.x * h.x); s4.y *= (1.f - h.y * h.y); s4.z *= (1.f - h.z * h.z); s4.w *= (1.f - h.w * h.w);
+        *reinterpret_cast<float4*>(dz2s + r4 * LDS + 4 * k4) = s4;
       }
       __syncthreads();
-      PHASE_MARK(4);   // small grads + dz2
-      // (c) dW2[j][k] += sum_r dz2[r][j] * h1[r][k];  db2[j] += sum_r dz2[r][j]
-      spo_warp_mma_3xtf32<1>(reinterpret_cast<float (&)[1][2][4]>(gW2), dz2, 1, SPO_LDH, h1, SPO_LDH, 1, mb, nb, SPO_ROWS);
-      PHASE_MARK(12);  // (sub) dW2 GEMM
-      colsum_into(dz2, gsmall + SPO_HID);
-      PHASE_MARK(13);  // (sub) db2 column sums
-      // (d) dz1[r][k] = (sum_j dz2[r][j] * W2[j][k]) * (1 - h1[r][k]^2)   -> overwrites h2
+      PHASE_MARK(7);   // small grads + dz2
+      // (c) dh1 partial [64 x 64] = dz2[:, slice] W2[slice, :] -> own buffer; each peer pulls its 16 columns
       {
-        float acc[1][2][4];
-        spo_mma_zero<1>(acc);
-        spo_warp_mma_3xtf32<1>(acc, dz2, SPO_LDH, 1, w2, SPO_LDH, 1, mb, nb, SPO_HID);
-        PHASE_MARK(14);  // (sub) dh1 GEMM
+        float acc[4][4];
+        warp_gemm<4, 2, false>(acc, dz2s, LDS, 1, w2s, LDA, 1, mt * 16, (wid >> 2) * 32);
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          const int r = mb + g8, k = nb + nt * 8 + 2 * t4;
-          const float2 ha = *reinterpret_cast<const float2*>(h1 + r * SPO_LDH + k);
-          const float2 hb = *reinterpret_cast<const float2*>(h1 + (r + 8) * SPO_LDH + k);
-          *reinterpret_cast<float2*>(dz1 + r * SPO_LDH + k) =
-              make_float2(acc[0][nt][0] * (1.f - ha.x * ha.x), acc[0][nt][1] * (1.f - ha.y * ha.y));
-          *reinterpret_cast<float2*>(dz1 + (r + 8) * SPO_LDH + k) =
-              make_float2(acc[0][nt][2] * (1.f - hb.x * hb.x), acc[0][nt][3] * (1.f - hb.y * hb.y));
+        for (int nt = 0; nt < 4; ++nt) {
+          const int c = (wid >> 2) * 32 + nt * 8 + 2 * t4;
+          *reinterpret_cast<float2*>(dh1f + rA * LDA + c) = make_float2(acc[nt][0], acc[nt][1]);
+          *reinterpret_cast<float2*>(dh1f + (rA + 8) * LDA + c) = make_float2(acc[nt][2], acc[nt][3]);
         }
       }
+      // (d) dW2[slice j][k] += sum_r dz2[r][j] * h1[r][k] (warp w: columns 8w..8w+7);  db2[j] += sum_r dz2[r][j]
+      warp_gemm<1, 8, true>(gW2, dz2s, 1, LDS, h1, LDA, 1, 0, wid * 8);
+      colsum_into(dz2s, gsmall + SP_B2);
+      PHASE_MARK(8);   // dh1 partial + dW2 + db2
+      if (world > 1 && last_tile) {
+        // data-parallel ranks: dW2 / db2 / dW3 / db3 / dlog_std leave for the peer GPUs now, two exchanges ahead of their use
+        __syncthreads();                                   // gsmall[b2, w3, b3, log_std] complete
+        float sv = (tid >= SP_B2 && tid < SPN) ? gsmall[tid] : 0.f;
+        dp_push(gW2[0], IC<4>{}, 0);
+        if (tid >= SP_B2 && tid < SPN) dp_push(&sv, IC<1>{}, 4 * (1 + NT1));
+      }
+    }
+    __syncthreads();
+    cluster_arrive(tid);
+    cluster_wait();                                   // ---- barrier 3: dh1 partials in place
+    PHASE_MARK(9);
+    if (active) {
+      // (e) dz1[r][jj] = (sum over the four partials, quarter order) * (1 - h1[r][16q + jj]^2)   -> overwrites h2s
+      {
+        float4 v[NQ];
+#pragma unroll
+        for (int d = 0; d < NQ; ++d) {
+          if (d != q) v[d] = ld_dsmem_f4(r_dh[d] + static_cast<uint32_t>((r4 * LDA + SL * q + 4 * k4) * 4));
+          else v[d] = *reinterpret_cast<const float4*>(dh1f + r4 * LDA + SL * q + 4 * k4);
+        }
+        float4 s4 = v[0];
+#pragma unroll
+        for (int d = 1; d < NQ; ++d) { s4.x += v[d].x; s4.y += v[d].y; s4.z += v[d].z; s4.w += v[d].w; }
+        const float4 h = *reinterpret_cast<const float4*>(h1 + r4 * LDA + SL * q + 4 * k4);
+        s4.x *= (1.f - h.x * h.x); s4.y *= (1.f - h.y * h.y); s4.z *= (1.f - h.z * h.z); s4.w *= (1.f - h.w * h.w);
+        *reinterpret_cast<float4*>(dz1s + r4 * LDS + 4 * k4) = s4;
+      }
       __syncthreads();
-      PHASE_MARK(5);   // dW2 + dh1
-      // (e) dW1[j][k] += sum_r dz1[r][j] * x[r][k];  db1[j] += sum_r dz1[r][j]
+      PHASE_MARK(10);  // dh1 pull + dz1
+      // (f) dW1[slice j][k] += sum_r dz1[r][j] * x[r][k];  db1[j] += sum_r dz1[r][j]
 #pragma unroll
       for (int i = 0; i < NT1; ++i)
-        spo_warp_mma_3xtf32<1>(reinterpret_cast<float (&)[1][2][4]>(gW1[i]), dz1, 1, SPO_LDH, x, ldx, 1, mb, i * 64 + nb, SPO_ROWS);
-      colsum_into(dz1, gsmall);
-    }  // active
+        warp_gemm<1, 8, true>(reinterpret_cast<float (&)[1][4]>(gW1[i]), dz1s, 1, LDS, x, ldx, 1, 0, (wid + 8 * i) * 8);
+      colsum_into(dz1s, gsmall + SP_B1);
+      PHASE_MARK(11);  // dW1 + db1
+    }
 
-    PHASE_MARK(6);   // dW1
-    cp_async_wait_all();   // indices of tile q+1 (requested a step ago); the barrier below publishes them
-    if (!last_tile) {      // next tile of the same step accumulates into the same gradients
-      __syncthreads();
+    cp_async_wait_all();   // indices of tile qt+1 (requested a step ago); the barriers below publish them
+    __syncthreads();       // gsmall complete
+    if (!last_tile) {
+      // more tiles of the same step follow: barrier 4 only orders the buffer reuse
+      cluster_arrive(tid);
       stage_next();
+      cluster_wait();
       continue;
     }
 
     // ---------------- cross-GPU gradient sum (data-parallel ranks), in rank order ----------------
-    // Push protocol: every rank stores its gradient straight into each peer's staging slot
-    // [parity][source rank][net] over NVLink (posted remote stores), fences, then raises the
-    // peer's flag [source rank][net] = seq.  A receiver only polls and reads its OWN memory.
-    // Slot reuse is safe: a slot of parity p is rewritten at step s+2, after this rank saw every
-    // peer's flag of step s+1, which a peer raises only after it finished reading step s.
-    if (a.comm.world > 1 && active) {
-      __syncthreads();  // gsmall complete
-      constexpr int Q = FE / 4;   // float4s per tile per thread
-      const int world = a.comm.world, me = a.comm.rank;
-      const unsigned seq = static_cast<unsigned>(a.comm.seq_base + static_cast<unsigned long long>(step_idx) + 1ull);
-      const size_t slot = static_cast<size_t>(UT) * FE * (1 + NT1) + spo_pad4(2 * SPO_HID + A * SPO_HID + 2 * A);
-      const size_t par_off = static_cast<size_t>(seq & 1u) * world * 3 * slot;
-      for (int r = 0; r < world; ++r) {
-        if (r == me) continue;
-        float4* dst = reinterpret_cast<float4*>(a.comm.grad_bufs[r] + par_off + (static_cast<size_t>(me) * 3 + net) * slot);
+    if (world > 1 && active) {
+      float sv = 0.f;
+      if (tid < SP_B2) { sv = gsmall[tid]; dp_push(&sv, IC<1>{}, 4 * (1 + NT1)); }
 #pragma unroll
-        for (int i = 0; i < Q; ++i) dst[i * UT + tid] = make_float4(gW2[4 * i], gW2[4 * i + 1], gW2[4 * i + 2], gW2[4 * i + 3]);
+      for (int i = 0; i < NT1; ++i) dp_push(gW1[i], IC<4>{}, 4 * (1 + i));
+      dp_sum(gW2[0], IC<4>{}, 0);
 #pragma unroll
-        for (int t = 0; t < NT1; ++t)
-#pragma unroll
-          for (int i = 0; i < Q; ++i)
-            dst[(Q + t * Q + i) * UT + tid] = make_float4(gW1[t][4 * i], gW1[t][4 * i + 1], gW1[t][4 * i + 2], gW1[t][4 * i + 3]);
-        float* dst_small = reinterpret_cast<float*>(dst + (Q + Q * NT1) * UT);
-        for (int i = tid; i < SP; i += UT) dst_small[i] = gsmall[i];
-      }
-      __threadfence_system();
-      __syncthreads();
-      if (tid < world && tid != me) st_release_sys(a.comm.flags[tid] + me * 3 + net, seq);
-      if (tid < world && tid != me && !comm_dead) {
-        const unsigned limit = a.comm.spin_limit ? a.comm.spin_limit : 400000000u;
-        const unsigned* f = a.comm.flags[me] + tid * 3 + net;     // local memory
-        unsigned polls = 0;
-        while (static_cast<int>(ld_acquire_sys(f) - seq) < 0) {
-          if (++polls > limit) { comm_dead = 1; atomicExch(&ctrl->stop, 2); break; }
-        }
-      }
-      __syncthreads();
-      float sW2[FE], sW1[NT1][FE];
-#pragma unroll
-      for (int e = 0; e < FE; ++e) {
-        sW2[e] = 0.f;
-#pragma unroll
-        for (int t = 0; t < NT1; ++t) sW1[t][e] = 0.f;
-      }
-      for (int r = 0; r < world; ++r) {
-        if (r == me) {
-#pragma unroll
-          for (int e = 0; e < FE; ++e) {
-            sW2[e] += gW2[e];
-#pragma unroll
-            for (int t = 0; t < NT1; ++t) sW1[t][e] += gW1[t][e];
-          }
-        } else {
-          const float4* src = reinterpret_cast<const float4*>(a.comm.grad_bufs[me] + par_off + (static_cast<size_t>(r) * 3 + net) * slot);
-          float4 v2[Q], v1[NT1][Q];
-#pragma unroll
-          for (int i = 0; i < Q; ++i) v2[i] = ld_relaxed_sys_f4(src + i * UT + tid);
-#pragma unroll
-          for (int t = 0; t < NT1; ++t)
-#pragma unroll
-            for (int i = 0; i < Q; ++i) v1[t][i] = ld_relaxed_sys_f4(src + (Q + t * Q + i) * UT + tid);
-#pragma unroll
-          for (int i = 0; i < Q; ++i) {
-            sW2[4 * i] += v2[i].x; sW2[4 * i + 1] += v2[i].y; sW2[4 * i + 2] += v2[i].z; sW2[4 * i + 3] += v2[i].w;
-#pragma unroll
-            for (int t = 0; t < NT1; ++t) {
-              sW1[t][4 * i] += v1[t][i].x; sW1[t][4 * i + 1] += v1[t][i].y; sW1[t][4 * i + 2] += v1[t][i].z; sW1[t][4 * i + 3] += v1[t][i].w;
-            }
-          }
-        }
-      }
-      const float inv_w = __fdiv_rn(1.f, static_cast<float>(world));
-#pragma unroll
-      for (int e = 0; e < FE; ++e) {
-        gW2[e] = __fmul_rn(sW2[e], inv_w);
-#pragma unroll
-        for (int t = 0; t < NT1; ++t) gW1[t][e] = __fmul_rn(sW1[t][e], inv_w);
-      }
-      for (int i = tid; i < SP; i += UT) {
-        float sm_ = 0.f;
-        for (int r = 0; r < world; ++r) {
-          if (r == me) sm_ += gsmall[i];
-          else sm_ += ld_relaxed_sys_f(reinterpret_cast<const float*>(reinterpret_cast<const float4*>(
-                          a.comm.grad_bufs[me] + par_off + (static_cast<size_t>(r) * 3 + net) * slot) + (Q + Q * NT1) * UT) + i);
-        }
-        gsmall[i] = __fmul_rn(sm_, inv_w);
-      }
+      for (int i = 0; i < NT1; ++i) dp_sum(gW1[i], IC<4>{}, 4 * (1 + i));
+      if (tid < SPN) { sv = gsmall[tid]; dp_sum(&sv, IC<1>{}, 4 * (1 + NT1)); gsmall[tid] = sv; }
     }
+    PHASE_MARK(12);  // cross-GPU gradient exchange
 
-    PHASE_MARK(7);   // cross-GPU gradient exchange
     // ---------------- joint gradient norm (cluster-wide), clip, Adam ----------------
-    float ss = 0.f, th2 = 0.f;
     if (active) {
-      __syncthreads();  // gsmall complete
-      if (is_actor) {   // no regulariser, no logged L2 term: nothing to read back
-        // (dW1 columns >= obs_dim are exact zeros: the padded observation columns are)
+      float ss = 0.f, th2 = 0.f;
 #pragma unroll
-        for (int e = 0; e < FE; ++e) {
-          ss = fmaf(gW2[e], gW2[e], ss);
-#pragma unroll
-          for (int i = 0; i < NT1; ++i) ss = fmaf(gW1[i][e], gW1[i][e], ss);
-        }
-        for (int i = tid; i < SP; i += UT) ss = fmaf(gsmall[i], gsmall[i], ss);
-      } else {
-#pragma unroll
-      for (int e = 0; e < FE; ++e) {
+      for (int e = 0; e < 4; ++e) {
         int j, k;
-        frag_rc(tid, e, 0, j, k);
-        const float th = w2[j * SPO_LDH + k];
-        const float g = fmaf(reg, th, gW2[e]);
-        gW2[e] = g;
-        ss = fmaf(g, g, ss);
-        th2 = fmaf(th, th, th2);
+        frag_jk(e, wid, j, k);
+        if (!is_actor) {
+          const float th = w2s[j * LDA + k];
+          gW2[0][e] = fmaf(reg, th, gW2[0][e]);
+          th2 = fmaf(th, th, th2);
+        }
+        ss = fmaf(gW2[0][e], gW2[0][e], ss);
 #pragma unroll
         for (int i = 0; i < NT1; ++i) {
-          const int kk = k + 64 * i;
-          if (kk < D) {
-            const float t1 = w1[j * ldx + kk];
-            const float g1 = fmaf(reg, t1, gW1[i][e]);
-            gW1[i][e] = g1;
-            ss = fmaf(g1, g1, ss);
-            th2 = fmaf(t1, t1, th2);
+          frag_jk(e, wid + 8 * i, j, k);
+          if (k < D) {
+            if (!is_actor) {
+              const float t1 = w1s[j * ldx + k];
+              gW1[i][e] = fmaf(reg, t1, gW1[i][e]);
+              th2 = fmaf(t1, t1, th2);
+            }
+            ss = fmaf(gW1[i][e], gW1[i][e], ss);
           } else {
-            gW1[i][e] = 0.f;
+            gW1[i][e] = 0.f;   // padded observation columns are exact zeros anyway
           }
         }
       }
-      for (int i = tid; i < SP; i += UT) {
-        float th;
-        if (i < SPO_HID) th = b1[i];
-        else if (i < 2 * SPO_HID) th = b2[i - SPO_HID];
-        else if (i < 2 * SPO_HID + O * SPO_HID) th = w3[i - 2 * SPO_HID];
-        else if (i < 2 * SPO_HID + O * SPO_HID + O) th = b3[i - 2 * SPO_HID - O * SPO_HID];
-        else th = log_std[i - 2 * SPO_HID - O * SPO_HID - O];
-        const float g = fmaf(reg, th, gsmall[i]);
-        gsmall[i] = g;
-        ss = fmaf(g, g, ss);
-        th2 = fmaf(th, th, th2);
-      }
+      if (tid < SPN && sp_valid) {
+        const float th = sp[tid];
+        const float g = fmaf(reg, th, gsmall[tid]);
+        gsmall[tid] = g;
+        if (sp_counted) { ss = fmaf(g, g, ss); th2 = fmaf(th, th, th2); }
       }
       ss = spo_warp_sum(ss);
       if (!is_actor) th2 = spo_warp_sum(th2);
       if (lane == 0) { red[16 + wid] = ss; red[32 + wid] = th2; }
-      TRACE_MARK(20);
       __syncthreads();
     }
-    const int par = static_cast<int>(step_idx & 1);
     if (wid == 0) {
       float s = 0.f, t2 = 0.f;
       if (active && lane < UT / 32) { s = red[16 + lane]; t2 = red[32 + lane]; }
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
+      for (int o = 4; o > 0; o >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
         t2 += __shfl_xor_sync(0xffffffffu, t2, o);
       }
-      s += extra_sumsq;
-      if (tid == 0) {
-      xchg[par] = idle ? 0.f : s;
-      // logged loss of this step (ppo_lag.py:330-336): critics include the L2 term
-      if (active) {
-        float L;
-        if (!is_actor) L = fmaf(a.hp.critic_l2, t2, __fmul_rn(step_loss, inv_b));
-        else if (a.kind == SPO_LOSS_PPO_CLIP) L = __fmul_rn(step_loss, inv_b);
-        else L = __fsub_rn(__fmul_rn(step_loss, inv_b),
-                           __fmul_rn(__fmul_rn(__fdiv_rn(1.f, a.hp.focops_lam), __fmul_rn(step_aux0, inv_b)), __fmul_rn(step_aux1, inv_b)));
-        acc_loss += static_cast<double>(L);
-      }
-      step_loss = 0.f; step_aux0 = 0.f; step_aux1 = 0.f;
-      }
+      if (lane == 0) *reinterpret_cast<float2*>(xchg + 2 * par) = make_float2(s + extra_sumsq, t2);
     }
-    PHASE_MARK(8);   // regulariser + sum of squares + block reduction
-    // cluster barrier, split: the rows of the next tile are requested while the arrivals propagate
-    // (only thread 0 has something to publish -- xchg; a release arrive makes all 512 threads execute a
-    //  gpu-scope MEMBAR, 1.1 k cycles per step in the r01 source profile)
-    if (tid == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
-    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-    stage_next();
-    TRACE_MARK(16);
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    PHASE_MARK(9);   // cluster barrier (includes waiting for the slowest net)
-    float total = 0.f;
+    PHASE_MARK(13);  // regulariser + sum of squares
+    __syncthreads();
+    cluster_arrive(tid);
+    stage_next();    // rows of the next tile are requested while the barrier completes
+    cluster_wait();                                   // ---- barrier 4: every CTA's (sum g^2, sum theta^2) in place
+    PHASE_MARK(14);
+    // every warp pulls the 12 pairs itself (lane b from CTA b) and reduces them with the same shuffle tree
+    float total, t2net;
     {
-      const unsigned nblk = cluster.num_blocks();
-      for (unsigned b = 0; b < nblk; ++b) total += *cluster.map_shared_rank(xchg + par, b);
+      float2 v = make_float2(0.f, 0.f);
+      if (lane < NCTA) v = ld_dsmem_f2(r_xchg + static_cast<uint32_t>(2 * par * 4));
+      float s = v.x, t2 = v.y;
+      t2 += __shfl_xor_sync(0xffffffffu, t2, 1);
+      t2 += __shfl_xor_sync(0xffffffffu, t2, 2);       // lanes 4n..4n+3: sum theta^2 of net n
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      total = __shfl_sync(0xffffffffu, s, 0);
+      t2net = __shfl_sync(0xffffffffu, t2, net * NQ);
     }
-    // clip coefficient max_norm / (norm + 1e-6), capped at 1 (SFU sqrt and division: <= 2 ulp, and exactly 1 whenever
-    // the norm is below the limit)
+    if (tid == 0 && q == 0 && active) {
+      // logged loss of this step (ppo_lag.py:330-336): critics include the L2 term over the whole net
+      float L;
+      if (!is_actor) L = fmaf(a.hp.critic_l2, t2net, __fmul_rn(step_loss, inv_b));
+      else if (a.kind == SPO_LOSS_PPO_CLIP) L = __fmul_rn(step_loss, inv_b);
+      else L = __fsub_rn(__fmul_rn(step_loss, inv_b),
+                         __fmul_rn(__fmul_rn(__fdiv_rn(1.f, a.hp.focops_lam), __fmul_rn(step_aux0, inv_b)), __fmul_rn(step_aux1, inv_b)));
+      acc_loss += static_cast<double>(L);
+    }
+    if (tid == 0) { step_loss = 0.f; step_aux0 = 0.f; step_aux1 = 0.f; }
+    // clip coefficient max_norm / (norm + 1e-6), capped at 1 (SFU sqrt and division: <= 2 ulp, exactly 1 below the limit)
     const float clip = fminf(__fdividef(a.hp.max_grad_norm, __fadd_rn(sqrt_approx(total), 1e-6f)), 1.f);
 
     if (active) {
       AdamK k;
       k.w1 = adk[0]; k.b2 = adk[1]; k.w2 = adk[2]; k.ibc2s = adk[3]; k.eps = adk[4]; k.ss = adk[5];
 #pragma unroll
-      for (int e = 0; e < FE; e += 2) {   // elements e, e+1 are neighbours in a weight row
+      for (int e = 0; e < 4; e += 2) {   // elements e, e+1 are neighbours in a weight row
         int j, kc;
-        frag_rc(tid, e, 0, j, kc);
-        float2* pw = reinterpret_cast<float2*>(w2 + j * SPO_LDH + kc);
+        frag_jk(e, wid, j, kc);
+        float2* pw = reinterpret_cast<float2*>(w2s + j * LDA + kc);
         float2 wv = *pw;
-        wv.x = adam_update(wv.x, __fmul_rn(gW2[e], clip), mW2[e], vW2[e], k);
-        wv.y = adam_update(wv.y, __fmul_rn(gW2[e + 1], clip), mW2[e + 1], vW2[e + 1], k);
+        wv.x = adam_update(wv.x, __fmul_rn(gW2[0][e], clip), mW2[e], vW2[e], k);
+        wv.y = adam_update(wv.y, __fmul_rn(gW2[0][e + 1], clip), mW2[e + 1], vW2[e + 1], k);
         *pw = wv;
-        gW2[e] = 0.f; gW2[e + 1] = 0.f;
-        if (kc < D) {   // D and kc even or the pair straddles D: handle the second element on its own
-          float* p1 = w1 + j * ldx + kc;
-          p1[0] = adam_update(p1[0], __fmul_rn(gW1[0][e], clip), mW1[e], vW1[e], k);
-          if (kc + 1 < D) p1[1] = adam_update(p1[1], __fmul_rn(gW1[0][e + 1], clip), mW1[e + 1], vW1[e + 1], k);
-        }
-        gW1[0][e] = 0.f; gW1[0][e + 1] = 0.f;
-        if (NT1 > 1) {
+        gW2[0][e] = 0.f; gW2[0][e + 1] = 0.f;
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-            if (kc + h + 64 < D) {
-              float* p1 = w1 + j * ldx + kc + h + 64;
-              float m = mv1b[(e + h) * UT + tid], v = mv1b[(FE + e + h) * UT + tid];
-              *p1 = adam_update(*p1, __fmul_rn(gW1[NT1 - 1][e + h], clip), m, v, k);
-              mv1b[(e + h) * UT + tid] = m;
-              mv1b[(FE + e + h) * UT + tid] = v;
-            }
-          gW1[NT1 - 1][e] = 0.f; gW1[NT1 - 1][e + 1] = 0.f;
+        for (int i = 0; i < NT1; ++i) {
+          frag_jk(e, wid + 8 * i, j, kc);
+          float* p1 = w1s + j * ldx + kc;
+          if (kc < D) p1[0] = adam_update(p1[0], __fmul_rn(gW1[i][e], clip), mW1[i][e], vW1[i][e], k);
+          if (kc + 1 < D) p1[1] = adam_update(p1[1], __fmul_rn(gW1[i][e + 1], clip), mW1[i][e + 1], vW1[i][e + 1], k);
+          gW1[i][e] = 0.f; gW1[i][e + 1] = 0.f;
         }
       }
-      TRACE_MARK(21);
-      for (int i = tid; i < SP; i += UT) {
-        float* th;
-        if (i < SPO_HID) th = b1 + i;
-        else if (i < 2 * SPO_HID) th = b2 + (i - SPO_HID);
-        else if (i < 2 * SPO_HID + O * SPO_HID) th = w3 + (i - 2 * SPO_HID);
-        else if (i < 2 * SPO_HID + O * SPO_HID + O) th = b3 + (i - 2 * SPO_HID - O * SPO_HID);
-        else th = log_std + (i - 2 * SPO_HID - O * SPO_HID - O);
-        float m = msmall[i], v = vsmall[i];
-        *th = adam_update(*th, __fmul_rn(gsmall[i], clip), m, v, k);
-        msmall[i] = m; vsmall[i] = v;
-        gsmall[i] = 0.f;
+      if (tid < SPN) {
+        if (sp_valid) sp[tid] = adam_update(sp[tid], __fmul_rn(gsmall[tid], clip), sp_m, sp_v, k);
+        gsmall[tid] = 0.f;
       }
     }
-    PHASE_MARK(10);  // Adam
+    PHASE_MARK(15);  // Adam
     ++step_idx;
-    // the __syncthreads at the top of the next iteration orders these weight writes
-    // before the next forward
+    // the __syncthreads at the top of the next iteration orders these weight writes before the next forward
   }
   cp_async_wait_all();
   __syncthreads();
 
   // ---- write back: weights, moments, step counters, logged losses ----
   if (active) {
-    for (int i = tid; i < SPO_HID * D; i += UT) {
+    for (int i = tid; i < SL * D; i += UT) {
       const int j = i / D, kx = i - j * D;
-      a.params[off.w1 + i] = w1[j * ldx + kx];
+      a.params[off.w1 + (SL * q + j) * D + kx] = w1s[j * ldx + kx];
     }
-    for (int i = tid; i < SPO_HID * SPO_HID; i += UT)
-      a.params[off.w2 + i] = w2[(i >> 6) * SPO_LDH + (i & 63)];
-    for (int i = tid; i < SP; i += UT) {
-      float th;
-      if (i < SPO_HID) th = b1[i];
-      else if (i < 2 * SPO_HID) th = b2[i - SPO_HID];
-      else if (i < 2 * SPO_HID + O * SPO_HID) th = w3[i - 2 * SPO_HID];
-      else if (i < 2 * SPO_HID + O * SPO_HID + O) th = b3[i - 2 * SPO_HID - O * SPO_HID];
-      else th = log_std[i - 2 * SPO_HID - O * SPO_HID - O];
-      const int g = sm.goff(off, i);
-      a.params[g] = th;
-      a.adam_m[g] = msmall[i];
-      a.adam_v[g] = vsmall[i];
+    for (int i = tid; i < SL * SPO_HID; i += UT)
+      a.params[off.w2 + (SL * q + (i >> 6)) * SPO_HID + (i & 63)] = w2s[(i >> 6) * LDA + (i & 63)];
+    if (tid < SPN && sp_valid && (sp_counted || tid < SP_B3)) {
+      a.params[sp_goff] = sp[tid];
+      a.adam_m[sp_goff] = sp_m;
+      a.adam_v[sp_goff] = sp_v;
     }
 #pragma unroll
-    for (int e = 0; e < FE; ++e) {
+    for (int e = 0; e < 4; ++e) {
       int j, kc;
-      frag_rc(tid, e, 0, j, kc);
-      a.adam_m[off.w2 + j * SPO_HID + kc] = mW2[e];
-      a.adam_v[off.w2 + j * SPO_HID + kc] = vW2[e];
-      if (kc < D) {
-        a.adam_m[off.w1 + j * D + kc] = mW1[e];
-        a.adam_v[off.w1 + j * D + kc] = vW1[e];
-      }
-      if (NT1 > 1 && kc + 64 < D) {
-        a.adam_m[off.w1 + j * D + kc + 64] = mv1b[e * UT + tid];
-        a.adam_v[off.w1 + j * D + kc + 64] = mv1b[(FE + e) * UT + tid];
+      frag_jk(e, wid, j, kc);
+      a.adam_m[off.w2 + (SL * q + j) * SPO_HID + kc] = mW2[e];
+      a.adam_v[off.w2 + (SL * q + j) * SPO_HID + kc] = vW2[e];
+#pragma unroll
+      for (int i = 0; i < NT1; ++i) {
+        frag_jk(e, wid + 8 * i, j, kc);
+        if (kc < D) {
+          a.adam_m[off.w1 + (SL * q + j) * D + kc] = mW1[i][e];
+          a.adam_v[off.w1 + (SL * q + j) * D + kc] = vW1[i][e];
+        }
       }
     }
-    if (tid == 0) {
+    if (tid == 0 && q == 0) {
       a.adam_t[net] = t0 + static_cast<int>(n_steps);
       const int slot = (net == 0) ? 2 : (net == 1 ? 0 : 1);
       atomicAdd(&ctrl->loss_sum[slot], acc_loss);
     }
   }
 #ifdef SPO_PHASE_TIMERS
-  if (tid < 16) atomicAdd(&g_phase_cycles[rank & 3][tid], sm_phase__[tid]);
+  if (tid < 24) atomicAdd(&g_phase_cycles[rank & 15][tid], sm_phase__[tid]);
 #endif
-  if (rank == 1 && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->steps), static_cast<unsigned long long>(n_steps));
+  if (rank == NQ && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&ctrl->steps), static_cast<unsigned long long>(n_steps));
   cluster.sync();  // no CTA may exit while a peer can still read its shared memory
 }
 
 size_t update_smem_bytes(int nt1) {
   const int ldx = upd_ldx(nt1);
-  size_t f = 4 * SPO_ROWS + 4 * SPO_MAX_ACT + 8 + SPO_HID * ldx + SPO_HID + SPO_HID * SPO_LDH + SPO_HID + SPO_MAX_ACT * SPO_HID + SPO_MAX_ACT + 8 +
-             3 * SPN + SPO_ROWS * ldx + SPO_ROWS * AUXW + 3 * SPO_ROWS * SPO_LDH + 3 * SPO_ROWS * SPO_MAX_ACT + 64 + 4 + (nt1 > 1 ? 2 * FE * UT : 0);
+  size_t f = 4 * SPO_ROWS + 4 * SPO_MAX_ACT + 8 + SL * ldx + SL * LDA + 2 * SPN + SPO_ROWS * ldx + SPO_ROWS * AUXW + SPO_ROWS * LDA +
+             2 * SPO_ROWS * LDS + 4 * SPO_ROWS * SPO_MAX_ACT + SPO_ROWS * LDA + 64 + 4;
   return f * sizeof(float);
 }
 
@@ -1037,14 +1055,17 @@ template <int NT1>
 int launch_update(const UpdArgs& a, cudaStream_t stream) {
   const size_t smem = update_smem_bytes(NT1);
   SPO_REQUIRE(smem <= 227 * 1024, SPO_ERR_UNSUPPORTED, "spo_pg_update: obs_dim=%d needs %zu B of shared memory (> 227 KB)", a.D, smem);
-  static int cluster_size = 0;   // 4 preferred (barrier measured faster than for 3, profiles/r01_ubench.txt); 3 as fallback
+  // 12 CTAs are needed; clusters above 8 are "non-portable" sizes: 12 is tried first, 16 (four CTAs idle) second.
+  // The choice is cached per process: one process drives one GPU (torchrun-style data parallelism).
+  static int cluster_size = 0;
   SPO_CUDA_TRY(cudaFuncSetAttribute(spo_update_kernel<NT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  SPO_CUDA_TRY(cudaFuncSetAttribute(spo_update_kernel<NT1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   if (!cluster_size) {
-    const char* env = getenv("SPO_CLUSTER");   // debugging aid: pin the cluster size (3 or 4)
-    if (env && (env[0] == '3' || env[0] == '4')) cluster_size = env[0] - '0';
+    const char* env = getenv("SPO_CLUSTER");   // debugging aid: pin the cluster size (12 or 16)
+    if (env && atoi(env) >= NCTA && atoi(env) <= 16) cluster_size = atoi(env);
   }
   for (int attempt = 0; attempt < 2; ++attempt) {
-    const int cs = cluster_size ? cluster_size : (attempt == 0 ? 4 : 3);
+    const int cs = cluster_size ? cluster_size : (attempt == 0 ? NCTA : 16);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(cs);
     cfg.blockDim = dim3(UT);
@@ -1071,26 +1092,28 @@ int launch_update(const UpdArgs& a, cudaStream_t stream) {
 }  // namespace
 
 #ifdef SPO_PHASE_TIMERS
-extern "C" int spo_debug_phase_cycles(unsigned long long* out64, int reset) {
-  SPO_CUDA_TRY(cudaMemcpyFromSymbol(out64, g_phase_cycles, sizeof(unsigned long long) * 64));
+extern "C" int spo_debug_phase_cycles(unsigned long long* out_16x24, int reset) {
+  SPO_CUDA_TRY(cudaMemcpyFromSymbol(out_16x24, g_phase_cycles, sizeof(unsigned long long) * 16 * 24));
   if (reset) {
-    unsigned long long z[64] = {0};
+    unsigned long long z[16 * 24] = {0};
     SPO_CUDA_TRY(cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)));
   }
   return SPO_OK;
 }
-extern "C" int spo_debug_trace(long long* out_4x16x24) {
-  SPO_CUDA_TRY(cudaMemcpyFromSymbol(out_4x16x24, g_trace, sizeof(long long) * 4 * 16 * 24));
-  return SPO_OK;
-}
 #endif
+
+extern "C" int spo_pg_update_v1_dp(const spo_dims* d, float* params, float* adam_m, float* adam_v, int* adam_t,
+                                   const spo_batch* data, const int64_t* perm, int64_t perm_len, int batch,
+                                   spo_loss_kind kind, const spo_hparams* hp, spo_update_ctrl* ctrl,
+                                   const spo_comm* comm, void* stream);
 
 extern "C" int spo_comm_slot_floats(const spo_dims* d, int* slot_floats) {
   int rc = spo_check_dims(d);
   if (rc) return rc;
   SPO_REQUIRE(slot_floats, SPO_ERR_INVALID_ARG, "spo_comm_slot_floats: null output");
+  // per net: four CTA slots of 8-byte {value, sequence} words
   const int nt1 = d->obs_dim <= 64 ? 1 : 2;
-  *slot_floats = UT * FE * (1 + nt1) + spo_pad4(2 * SPO_HID + d->act_dim * SPO_HID + 2 * d->act_dim);
+  *slot_floats = NQ * dp_slot_words(nt1) * 2;
   return SPO_OK;
 }
 
@@ -1117,6 +1140,10 @@ extern "C" int spo_pg_update_dp(const spo_dims* d, float* params, float* adam_m,
     SPO_REQUIRE(data->old_mean && data->old_std, SPO_ERR_INVALID_ARG, "spo_pg_update: FOCOPS needs old_mean/old_std");
     SPO_REQUIRE(batch <= SPO_ROWS, SPO_ERR_UNSUPPORTED, "spo_pg_update: FOCOPS supports batch <= %d (got %d)", SPO_ROWS, batch);
   }
+  {
+    const char* v1 = getenv("SPO_UPDATE_V1");   // development only: the round-1 kernel (one CTA per net), for A/B runs
+    if (v1 && v1[0] == '1') return spo_pg_update_v1_dp(d, params, adam_m, adam_v, adam_t, data, perm, perm_len, batch, kind, hp, ctrl, comm, stream);
+  }
   UpdArgs a{};
   a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.adam_t = adam_t;
   a.data = *data; a.perm = perm; a.perm_len = perm_len; a.batch = batch; a.kind = kind;
@@ -1137,7 +1164,7 @@ extern "C" int spo_pg_update_dp(const spo_dims* d, float* params, float* adam_m,
     a.hp.clip_hi = INFINITY;
   }
   if (comm && comm->world > 1) {
-    SPO_REQUIRE(comm->rank >= 0 && comm->rank < comm->world && comm->world <= 32 && comm->grad_bufs && comm->flags,
+    SPO_REQUIRE(comm->rank >= 0 && comm->rank < comm->world && comm->world <= 32 && comm->grad_bufs,
                 SPO_ERR_INVALID_ARG, "spo_pg_update_dp: bad spo_comm (world=%d rank=%d)", comm->world, comm->rank);
     a.comm = *comm;
   } else {
