@@ -110,12 +110,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// relaxed hardware cluster barrier: the caller has just passed a __syncthreads (all local stores performed); one thread
-// fences at cluster scope (a release arrive would put a MEMBAR.ALL.GPU into every thread: 1.1 k cycles per step in r01)
-__device__ __forceinline__ void cluster_arrive(int tid) {
-  if (tid == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
-  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-}
+// Hardware cluster barrier, relaxed arrive.  The caller has just passed a __syncthreads: every st.shared of the CTA has
+// been performed on this SM's shared memory (which has no cache in front of it), and a peer's ld.shared::cluster can
+// only be issued after the barrier completed, i.e. after every thread of this CTA arrived.  A release arrive (or a
+// cluster-scope fence by one thread) is a MEMBAR.ALL.GPU in SASS: +290..380 cycles per barrier measured
+// (tools/dsmem_probe.cu, profiles/r02_dsmem_probe.txt: S3 vs S1), four times per step.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
   float4 v;
@@ -167,6 +167,8 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
 // products in separate accumulator chains (lo*hi, hi*lo, hi*hi; small terms are added first at the end).
 //   A(m, k) = A[m * a_sm + k * a_sk]      B(k, n) = B[k * b_sk + n * b_sn]      (shared memory, K = 8 * KSTEPS)
 // Fragment ownership (g = lane >> 2, t = lane & 3): acc[nt][0..3] = C(m0+g, n0+8nt+2t), (.., +1), (m0+g+8, ..), (.., +1)
+// With two warps per scheduler nothing hides a load -> split -> mma chain: all operand fragments of a chunk of (up to)
+// eight k-steps are requested before the first split, then the chunk's splits and mmas run from registers.
 template <int NTL, int KSTEPS, bool ACCUM>
 __device__ __forceinline__ void warp_gemm(float (&acc)[NTL][4], const float* __restrict__ A, int a_sm, int a_sk,
                                           const float* __restrict__ B, int b_sk, int b_sn, int m0, int n0) {
@@ -178,24 +180,34 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[NTL][4], const float* __r
   for (int nt = 0; nt < NTL; ++nt)
 #pragma unroll
     for (int e = 0; e < 4; ++e) { c_lh[nt][e] = 0.f; c_hl[nt][e] = 0.f; c_hh[nt][e] = 0.f; }
+  constexpr int CH = KSTEPS < 8 ? KSTEPS : 8;
 #pragma unroll
-  for (int ks = 0; ks < KSTEPS; ++ks) {
-    const int k0 = ks * 8;
-    uint32_t ah[4], al[4];
-    const float* p = a_ptr + k0 * a_sk;
-    spo_split_tf32(p[0], ah[0], al[0]);
-    spo_split_tf32(p[8 * a_sm], ah[1], al[1]);
-    spo_split_tf32(p[4 * a_sk], ah[2], al[2]);
-    spo_split_tf32(p[8 * a_sm + 4 * a_sk], ah[3], al[3]);
+  for (int kc = 0; kc < KSTEPS; kc += CH) {
+    float af[CH][4], bf[CH][NTL][2];
 #pragma unroll
-    for (int nt = 0; nt < NTL; ++nt) {
-      uint32_t bh[2], bl[2];
-      const float* pb = b_ptr + nt * 8 * b_sn + k0 * b_sk;
-      spo_split_tf32(pb[0], bh[0], bl[0]);
-      spo_split_tf32(pb[4 * b_sk], bh[1], bl[1]);
-      spo_mma_tf32(c_lh[nt], al, bh);
-      spo_mma_tf32(c_hl[nt], ah, bl);
-      spo_mma_tf32(c_hh[nt], ah, bh);
+    for (int ks = 0; ks < CH; ++ks) {
+      const float* p = a_ptr + (kc + ks) * 8 * a_sk;
+      af[ks][0] = p[0]; af[ks][1] = p[8 * a_sm]; af[ks][2] = p[4 * a_sk]; af[ks][3] = p[8 * a_sm + 4 * a_sk];
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        const float* pb = b_ptr + nt * 8 * b_sn + (kc + ks) * 8 * b_sk;
+        bf[ks][nt][0] = pb[0]; bf[ks][nt][1] = pb[4 * b_sk];
+      }
+    }
+#pragma unroll
+    for (int ks = 0; ks < CH; ++ks) {
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) spo_split_tf32(af[ks][i], ah[i], al[i]);
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        uint32_t bh[2], bl[2];
+        spo_split_tf32(bf[ks][nt][0], bh[0], bl[0]);
+        spo_split_tf32(bf[ks][nt][1], bh[1], bl[1]);
+        spo_mma_tf32(c_lh[nt], al, bh);
+        spo_mma_tf32(c_hl[nt], ah, bl);
+        spo_mma_tf32(c_hh[nt], ah, bh);
+      }
     }
   }
 #pragma unroll
@@ -205,6 +217,46 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[NTL][4], const float* __r
       const float s = (c_lh[nt][e] + c_hl[nt][e]) + c_hh[nt][e];
       acc[nt][e] = ACCUM ? acc[nt][e] + s : s;
     }
+}
+
+// The same product when BOTH operands are contiguous along k (A[m][k], B[n][k]: the two forward layers): the mma's k
+// slots are bound to memory as slot t <-> k0 + 2t, slot t + 4 <-> k0 + 2t + 1, so that a thread's two k values of a row are
+// one 8-byte load.  With leading dimensions == 8 (mod 32) a half-warp's 64-bit accesses (g = 0..3, t = 0..3: banks
+// 8g + 2t, +1) are conflict-free, whereas the 32-bit fragment loads of warp_gemm collide two-way for this orientation
+// (banks 8g + t repeat for g and g + 4) -- 32 % of all shared-memory wavefronts of the first version of this kernel.
+template <int KSTEPS>
+__device__ __forceinline__ void warp_gemm_kk(float (&acc)[1][4], const float* __restrict__ A, int lda,
+                                             const float* __restrict__ B, int ldb, int m0, int n0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const float* a_ptr = A + (m0 + g) * lda + 2 * t;
+  const float* b_ptr = B + (n0 + g) * ldb + 2 * t;
+  float c_lh[4] = {0.f, 0.f, 0.f, 0.f}, c_hl[4] = {0.f, 0.f, 0.f, 0.f}, c_hh[4] = {0.f, 0.f, 0.f, 0.f};
+  constexpr int CH = KSTEPS < 8 ? KSTEPS : 8;
+#pragma unroll
+  for (int kc = 0; kc < KSTEPS; kc += CH) {
+    float2 a0[CH], a1[CH], bb[CH];
+#pragma unroll
+    for (int ks = 0; ks < CH; ++ks) {
+      a0[ks] = *reinterpret_cast<const float2*>(a_ptr + (kc + ks) * 8);
+      a1[ks] = *reinterpret_cast<const float2*>(a_ptr + 8 * lda + (kc + ks) * 8);
+      bb[ks] = *reinterpret_cast<const float2*>(b_ptr + (kc + ks) * 8);
+    }
+#pragma unroll
+    for (int ks = 0; ks < CH; ++ks) {
+      uint32_t ah[4], al[4], bh[2], bl[2];
+      spo_split_tf32(a0[ks].x, ah[0], al[0]);
+      spo_split_tf32(a1[ks].x, ah[1], al[1]);
+      spo_split_tf32(a0[ks].y, ah[2], al[2]);
+      spo_split_tf32(a1[ks].y, ah[3], al[3]);
+      spo_split_tf32(bb[ks].x, bh[0], bl[0]);
+      spo_split_tf32(bb[ks].y, bh[1], bl[1]);
+      spo_mma_tf32(c_lh, al, bh);
+      spo_mma_tf32(c_hl, ah, bl);
+      spo_mma_tf32(c_hh, ah, bh);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) acc[0][e] = (c_lh[e] + c_hl[e]) + c_hh[e];
 }
 
 template <int NT1>
@@ -376,31 +428,34 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     if (rs > a.batch) rs = a.batch;
     int rows = static_cast<int>(rs) - sub * SPO_ROWS;
     rows = rows < 0 ? 0 : (rows > SPO_ROWS ? SPO_ROWS : rows);
-    const int64_t* ridx = idxbuf + (qt & 1) * SPO_ROWS;
+    // sample indices are < 2^31 (checked at the entry point): the low words of the staged int64 indices, one 32 x 32 -> 64
+    // multiply-add per address
+    const uint32_t* ridx = reinterpret_cast<const uint32_t*>(idxbuf + (qt & 1) * SPO_ROWS);
+    const uint32_t Du = static_cast<uint32_t>(D);
     if (vec_rows) {
 #pragma unroll
       for (int it = 0; it < PF_MAX; ++it) {
         const int r = pf_rc[it] & 0xFF, c = pf_rc[it] >> 8;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (it < pf_n && r < rows) v = __ldg(reinterpret_cast<const float4*>(a.data.obs + ridx[r] * D + 4 * c));
+        if (it < pf_n && r < rows) v = __ldg(reinterpret_cast<const float4*>(a.data.obs + static_cast<size_t>(ridx[2 * r]) * Du) + c);
         xr[4 * it] = v.x; xr[4 * it + 1] = v.y; xr[4 * it + 2] = v.z; xr[4 * it + 3] = v.w;
       }
     } else {
 #pragma unroll
       for (int it = 0; it < 4 * PF_MAX; ++it) {
         const int i = tid + it * UT, r = i / D, c = i - r * D;
-        xr[it] = (r < rows) ? __ldg(a.data.obs + ridx[r] * D + c) : 0.f;
+        xr[it] = (r < rows) ? __ldg(a.data.obs + static_cast<size_t>(ridx[2 * r]) * Du + c) : 0.f;
       }
     }
     const bool rv = r4s < rows;
-    const int64_t g = rv ? ridx[r4s] : 0;
-    auxr[0] = (rv && q4s < aux_per) ? __ldg(aux_src0 + g * aux_mul0) : 0.f;
+    const uint32_t g = rv ? ridx[2 * r4s] : 0u;
+    auxr[0] = (rv && q4s < aux_per) ? __ldg(aux_src0 + static_cast<size_t>(g) * static_cast<uint32_t>(aux_mul0)) : 0.f;
     if (aux_per > 4) {
 #pragma unroll
       for (int i = 1; i < AUX_IT; ++i) {
         const int c = q4s + 4 * i;
         float v = 0.f;
-        if (rv && c < aux_per) v = __ldg(aux_src(c) + g * (aux_by_row(c) ? A : 1));
+        if (rv && c < aux_per) v = __ldg(aux_src(c) + static_cast<size_t>(g) * static_cast<uint32_t>(aux_by_row(c) ? A : 1));
         auxr[i] = v;
       }
     }
@@ -568,7 +623,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     // ---------------- forward, layer 1: own 16 units ----------------
     if (active) {
       float acc[1][4];
-      warp_gemm<1, 8 * NT1, false>(acc, x, ldx, 1, w1s, 1, ldx, mt * 16, ntl * 8);
+      warp_gemm_kk<8 * NT1>(acc, x, ldx, w1s, ldx, mt * 16, ntl * 8);
       const float2 bb = *reinterpret_cast<const float2*>(b1s + cA);
       *reinterpret_cast<float2*>(h1 + rA * LDA + SL * q + cA) = make_float2(spo_tanh_fast(acc[0][0] + bb.x), spo_tanh_fast(acc[0][1] + bb.y));
       *reinterpret_cast<float2*>(h1 + (rA + 8) * LDA + SL * q + cA) = make_float2(spo_tanh_fast(acc[0][2] + bb.x), spo_tanh_fast(acc[0][3] + bb.y));
@@ -586,7 +641,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     }
     PHASE_MARK(1);   // layer-1 product + epilogue
     __syncthreads();
-    cluster_arrive(tid);
+    cluster_arrive();
     cluster_wait();                                   // ---- barrier 1: every h1 slice of the cluster is in place
     PHASE_MARK(2);
     float yv[SPO_MAX_ACT];                            // output-layer rows of this thread's row r4 (after the y exchange)
@@ -604,7 +659,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       // ---------------- forward, layer 2 + partial output layer ----------------
       {
         float acc[1][4];
-        warp_gemm<1, 8, false>(acc, h1, LDA, 1, w2s, 1, LDA, mt * 16, ntl * 8);
+        warp_gemm_kk<8>(acc, h1, LDA, w2s, LDA, mt * 16, ntl * 8);
         const float2 bb = *reinterpret_cast<const float2*>(b2s + cA);
         *reinterpret_cast<float2*>(h2s + rA * LDS + cA) = make_float2(spo_tanh_fast(acc[0][0] + bb.x), spo_tanh_fast(acc[0][1] + bb.y));
         *reinterpret_cast<float2*>(h2s + (rA + 8) * LDS + cA) = make_float2(spo_tanh_fast(acc[0][2] + bb.x), spo_tanh_fast(acc[0][3] + bb.y));
@@ -624,22 +679,26 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     }
     PHASE_MARK(4);   // layer 2 + partial output layer
     __syncthreads();
-    cluster_arrive(tid);
+    cluster_arrive();
     cluster_wait();                                   // ---- barrier 2: partial outputs in place
     PHASE_MARK(5);
     if (active) {
       // y[r][o] = b3[o] + sum over the four quarters: lane k4 of a row pulls quarter k4's partial (two float4),
       // a butterfly over the four lanes finishes the sum (fixed order (p0 + p1) + (p2 + p3) in every CTA)
       {
-        float4 lo, hi = make_float4(0.f, 0.f, 0.f, 0.f);
-        lo = ld_dsmem_f4(r_yp[k4] + static_cast<uint32_t>(r4 * SPO_MAX_ACT * 4));
-        if (O > 4) hi = ld_dsmem_f4(r_yp[k4] + static_cast<uint32_t>((r4 * SPO_MAX_ACT + 4) * 4));
+        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t ya = r_yp[k4] + static_cast<uint32_t>(r4 * SPO_MAX_ACT * 4);
+        if (O <= 2) { const float2 t2 = ld_dsmem_f2(ya); lo.x = t2.x; lo.y = t2.y; }   // no more bytes than needed: DSMEM is the narrow pipe
+        else lo = ld_dsmem_f4(ya);
+        if (O > 4) hi = ld_dsmem_f4(ya + 16);
         yv[0] = lo.x; yv[1] = lo.y; yv[2] = lo.z; yv[3] = lo.w; yv[4] = hi.x; yv[5] = hi.y; yv[6] = hi.z; yv[7] = hi.w;
 #pragma unroll
         for (int o = 0; o < SPO_MAX_ACT; ++o) {
-          yv[o] += __shfl_xor_sync(0xffffffffu, yv[o], 1);
-          yv[o] += __shfl_xor_sync(0xffffffffu, yv[o], 2);
-          yv[o] = (o < O) ? __fadd_rn(yv[o], b3[o]) : 0.f;
+          if (o < O) {     // O is uniform over the CTA
+            yv[o] += __shfl_xor_sync(0xffffffffu, yv[o], 1);
+            yv[o] += __shfl_xor_sync(0xffffffffu, yv[o], 2);
+            yv[o] = __fadd_rn(yv[o], b3[o]);
+          }
         }
       }
       // ---------------- loss and d loss / d output: thread (row r4, action dims j = k4 and k4 + 4) ----------------
@@ -823,31 +882,36 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
           *reinterpret_cast<float2*>(dh1f + (rA + 8) * LDA + c) = make_float2(acc[nt][2], acc[nt][3]);
         }
       }
+      PHASE_MARK(8);   // dh1 partial product
+    }
+    __syncthreads();
+    cluster_arrive();
+    cluster_wait();                                   // ---- barrier 3: dh1 partials in place
+    PHASE_MARK(9);
+    if (active) {
+      // the three remote quarters of dh1 are requested now and consumed after the dW2 product (DSMEM moves ~12 B/clk per
+      // SM -- 12 KB take ~1000 cycles, profiles/r02_dsmem_probe.txt -- so the pull hides behind the next GEMM)
+      float4 v[NQ];
+#pragma unroll
+      for (int d = 0; d < NQ; ++d)
+        if (d != q) v[d] = ld_dsmem_f4(r_dh[d] + static_cast<uint32_t>((r4 * LDA + SL * q + 4 * k4) * 4));
       // (d) dW2[slice j][k] += sum_r dz2[r][j] * h1[r][k] (warp w: columns 8w..8w+7);  db2[j] += sum_r dz2[r][j]
       warp_gemm<1, 8, true>(gW2, dz2s, 1, LDS, h1, LDA, 1, 0, wid * 8);
       colsum_into(dz2s, gsmall + SP_B2);
-      PHASE_MARK(8);   // dh1 partial + dW2 + db2
+      PHASE_MARK(10);  // dW2 + db2 (dh1 quarters in flight)
       if (world > 1 && last_tile) {
-        // data-parallel ranks: dW2 / db2 / dW3 / db3 / dlog_std leave for the peer GPUs now, two exchanges ahead of their use
+        // data-parallel ranks: dW2 / db2 / dW3 / db3 / dlog_std leave for the peer GPUs now, ahead of the dW1 product
         __syncthreads();                                   // gsmall[b2, w3, b3, log_std] complete
         float sv = (tid >= SP_B2 && tid < SPN) ? gsmall[tid] : 0.f;
         dp_push(gW2[0], IC<4>{}, 0);
         if (tid >= SP_B2 && tid < SPN) dp_push(&sv, IC<1>{}, 4 * (1 + NT1));
       }
-    }
-    __syncthreads();
-    cluster_arrive(tid);
-    cluster_wait();                                   // ---- barrier 3: dh1 partials in place
-    PHASE_MARK(9);
-    if (active) {
       // (e) dz1[r][jj] = (sum over the four partials, quarter order) * (1 - h1[r][16q + jj]^2)   -> overwrites h2s
       {
-        float4 v[NQ];
+        const float4 own = *reinterpret_cast<const float4*>(dh1f + r4 * LDA + SL * q + 4 * k4);
 #pragma unroll
-        for (int d = 0; d < NQ; ++d) {
-          if (d != q) v[d] = ld_dsmem_f4(r_dh[d] + static_cast<uint32_t>((r4 * LDA + SL * q + 4 * k4) * 4));
-          else v[d] = *reinterpret_cast<const float4*>(dh1f + r4 * LDA + SL * q + 4 * k4);
-        }
+        for (int d = 0; d < NQ; ++d)
+          if (d == q) v[d] = own;
         float4 s4 = v[0];
 #pragma unroll
         for (int d = 1; d < NQ; ++d) { s4.x += v[d].x; s4.y += v[d].y; s4.z += v[d].z; s4.w += v[d].w; }
@@ -856,20 +920,20 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         *reinterpret_cast<float4*>(dz1s + r4 * LDS + 4 * k4) = s4;
       }
       __syncthreads();
-      PHASE_MARK(10);  // dh1 pull + dz1
+      PHASE_MARK(11);  // dh1 reduce + dz1
       // (f) dW1[slice j][k] += sum_r dz1[r][j] * x[r][k];  db1[j] += sum_r dz1[r][j]
 #pragma unroll
       for (int i = 0; i < NT1; ++i)
         warp_gemm<1, 8, true>(reinterpret_cast<float (&)[1][4]>(gW1[i]), dz1s, 1, LDS, x, ldx, 1, 0, (wid + 8 * i) * 8);
       colsum_into(dz1s, gsmall + SP_B1);
-      PHASE_MARK(11);  // dW1 + db1
+      PHASE_MARK(12);  // dW1 + db1
     }
 
     cp_async_wait_all();   // indices of tile qt+1 (requested a step ago); the barriers below publish them
     __syncthreads();       // gsmall complete
     if (!last_tile) {
       // more tiles of the same step follow: barrier 4 only orders the buffer reuse
-      cluster_arrive(tid);
+      cluster_arrive();
       stage_next();
       cluster_wait();
       continue;
@@ -886,7 +950,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       for (int i = 0; i < NT1; ++i) dp_sum(gW1[i], IC<4>{}, 4 * (1 + i));
       if (tid < SPN) { sv = gsmall[tid]; dp_sum(&sv, IC<1>{}, 4 * (1 + NT1)); gsmall[tid] = sv; }
     }
-    PHASE_MARK(12);  // cross-GPU gradient exchange
+    PHASE_MARK(13);  // cross-GPU gradient exchange
 
     // ---------------- joint gradient norm (cluster-wide), clip, Adam ----------------
     if (active) {
@@ -924,25 +988,26 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       }
       ss = spo_warp_sum(ss);
       if (!is_actor) th2 = spo_warp_sum(th2);
-      if (lane == 0) { red[16 + wid] = ss; red[32 + wid] = th2; }
+      if (lane == 0) *reinterpret_cast<float2*>(red + 16 + 2 * wid) = make_float2(ss, th2);
       __syncthreads();
     }
-    if (wid == 0) {
+    if (tid == 0) {
       float s = 0.f, t2 = 0.f;
-      if (active && lane < UT / 32) { s = red[16 + lane]; t2 = red[32 + lane]; }
+      if (active) {
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+        for (int w = 0; w < UT / 32; w += 2) {
+          const float4 v = *reinterpret_cast<const float4*>(red + 16 + 2 * w);
+          s += v.x + v.z; t2 += v.y + v.w;
+        }
       }
-      if (lane == 0) *reinterpret_cast<float2*>(xchg + 2 * par) = make_float2(s + extra_sumsq, t2);
+      *reinterpret_cast<float2*>(xchg + 2 * par) = make_float2(s + extra_sumsq, t2);
     }
-    PHASE_MARK(13);  // regulariser + sum of squares
+    PHASE_MARK(14);  // regulariser + sum of squares
     __syncthreads();
-    cluster_arrive(tid);
+    cluster_arrive();
     stage_next();    // rows of the next tile are requested while the barrier completes
     cluster_wait();                                   // ---- barrier 4: every CTA's (sum g^2, sum theta^2) in place
-    PHASE_MARK(14);
+    PHASE_MARK(15);
     // every warp pulls the 12 pairs itself (lane b from CTA b) and reduces them with the same shuffle tree
     float total, t2net;
     {
@@ -972,31 +1037,54 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     if (active) {
       AdamK k;
       k.w1 = adk[0]; k.b2 = adk[1]; k.w2 = adk[2]; k.ibc2s = adk[3]; k.eps = adk[4]; k.ss = adk[5];
+      // all loads first, then the arithmetic, then all stores: shared-memory loads cannot be moved across possibly
+      // aliasing stores by the compiler, which would serialise twelve load -> sqrt -> rcp -> store chains per thread
+      float2 w2v[2];
+      float w1v[NT1][4];
+      float spv = 0.f, spg = 0.f;
 #pragma unroll
-      for (int e = 0; e < 4; e += 2) {   // elements e, e+1 are neighbours in a weight row
+      for (int e = 0; e < 4; e += 2) {
         int j, kc;
         frag_jk(e, wid, j, kc);
-        float2* pw = reinterpret_cast<float2*>(w2s + j * LDA + kc);
-        float2 wv = *pw;
-        wv.x = adam_update(wv.x, __fmul_rn(gW2[0][e], clip), mW2[e], vW2[e], k);
-        wv.y = adam_update(wv.y, __fmul_rn(gW2[0][e + 1], clip), mW2[e + 1], vW2[e + 1], k);
-        *pw = wv;
-        gW2[0][e] = 0.f; gW2[0][e + 1] = 0.f;
+        w2v[e >> 1] = *reinterpret_cast<const float2*>(w2s + j * LDA + kc);
 #pragma unroll
         for (int i = 0; i < NT1; ++i) {
           frag_jk(e, wid + 8 * i, j, kc);
-          float* p1 = w1s + j * ldx + kc;
-          if (kc < D) p1[0] = adam_update(p1[0], __fmul_rn(gW1[i][e], clip), mW1[i][e], vW1[i][e], k);
-          if (kc + 1 < D) p1[1] = adam_update(p1[1], __fmul_rn(gW1[i][e + 1], clip), mW1[i][e + 1], vW1[i][e + 1], k);
+          const float2 t = *reinterpret_cast<const float2*>(w1s + j * ldx + kc);   // columns >= D are zero padding
+          w1v[i][e] = t.x; w1v[i][e + 1] = t.y;
+        }
+      }
+      if (tid < SPN) { spv = sp[tid]; spg = gsmall[tid]; }
+#pragma unroll
+      for (int e = 0; e < 4; e += 2) {
+        w2v[e >> 1].x = adam_update(w2v[e >> 1].x, __fmul_rn(gW2[0][e], clip), mW2[e], vW2[e], k);
+        w2v[e >> 1].y = adam_update(w2v[e >> 1].y, __fmul_rn(gW2[0][e + 1], clip), mW2[e + 1], vW2[e + 1], k);
+        gW2[0][e] = 0.f; gW2[0][e + 1] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NT1; ++i) {
+          int j, kc;
+          frag_jk(e, wid + 8 * i, j, kc);
+          // padded columns (kc >= D): gradient 0, moments 0 -> the update is exactly 0, the padding stays 0
+          w1v[i][e] = adam_update(w1v[i][e], __fmul_rn(gW1[i][e], clip), mW1[i][e], vW1[i][e], k);
+          w1v[i][e + 1] = adam_update(w1v[i][e + 1], __fmul_rn(gW1[i][e + 1], clip), mW1[i][e + 1], vW1[i][e + 1], k);
           gW1[i][e] = 0.f; gW1[i][e + 1] = 0.f;
         }
       }
-      if (tid < SPN) {
-        if (sp_valid) sp[tid] = adam_update(sp[tid], __fmul_rn(gsmall[tid], clip), sp_m, sp_v, k);
-        gsmall[tid] = 0.f;
+      if (tid < SPN && sp_valid) spv = adam_update(spv, __fmul_rn(spg, clip), sp_m, sp_v, k);
+#pragma unroll
+      for (int e = 0; e < 4; e += 2) {
+        int j, kc;
+        frag_jk(e, wid, j, kc);
+        *reinterpret_cast<float2*>(w2s + j * LDA + kc) = w2v[e >> 1];
+#pragma unroll
+        for (int i = 0; i < NT1; ++i) {
+          frag_jk(e, wid + 8 * i, j, kc);
+          *reinterpret_cast<float2*>(w1s + j * ldx + kc) = make_float2(w1v[i][e], w1v[i][e + 1]);
+        }
       }
+      if (tid < SPN) { sp[tid] = spv; gsmall[tid] = 0.f; }
     }
-    PHASE_MARK(15);  // Adam
+    PHASE_MARK(16);  // Adam
     ++step_idx;
     // the __syncthreads at the top of the next iteration orders these weight writes before the next forward
   }
@@ -1130,8 +1218,8 @@ extern "C" int spo_pg_update_dp(const spo_dims* d, float* params, float* adam_m,
   int rc = spo_check_dims(d);
   if (rc) return rc;
   SPO_REQUIRE(params && adam_m && adam_v && adam_t && data && perm && hp && ctrl, SPO_ERR_INVALID_ARG, "spo_pg_update: null argument");
-  SPO_REQUIRE(batch > 0 && perm_len > 0 && perm_len <= data->count, SPO_ERR_INVALID_ARG,
-              "spo_pg_update: batch=%d perm_len=%lld count=%lld", batch, (long long)perm_len, (long long)data->count);
+  SPO_REQUIRE(batch > 0 && perm_len > 0 && perm_len <= data->count && data->count <= 0x7fffffffLL, SPO_ERR_INVALID_ARG,
+              "spo_pg_update: batch=%d perm_len=%lld count=%lld (count must be < 2^31)", batch, (long long)perm_len, (long long)data->count);
   SPO_REQUIRE(kind >= SPO_LOSS_PPO_CLIP && kind <= SPO_LOSS_CUP_PROJECTION, SPO_ERR_INVALID_ARG, "spo_pg_update: kind=%d", (int)kind);
   SPO_REQUIRE(data->obs && data->target_r && data->target_c, SPO_ERR_INVALID_ARG, "spo_pg_update: batch obs/targets null");
   if (kind != SPO_LOSS_CRITIC_ONLY)

@@ -107,10 +107,59 @@ __global__ void __launch_bounds__(NT, 1) probe(int active, int iters, unsigned l
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     t_cb += clock64() - c0;
   }
+  // (c2) __syncthreads + fence by one thread + relaxed arrive + wait   (c3) cluster.sync()   (d) barrier + pull of 3 float4 per thread
+  unsigned long long t_c2 = 0, t_c3 = 0, t_pull = 0, t_pull_only = 0;
+  for (int it = 0; it < iters; ++it) {
+    long long c0 = clock64();
+    __syncthreads();
+    if (tid == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    t_c2 += clock64() - c0;
+  }
+  for (int it = 0; it < iters; ++it) {
+    long long c0 = clock64();
+    cluster.sync();
+    t_c3 += clock64() - c0;
+  }
+  {
+    const int r4 = tid >> 2, k4 = tid & 3;
+    float keep = 0.f;
+    for (int it = 0; it < iters; ++it) {
+      h1[r4 * LDS + 16 * (rank & 3) + 4 * k4] = static_cast<float>(it);
+      __syncthreads();
+      asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      long long c0 = clock64();
+      float4 v[4];
+#pragma unroll
+      for (unsigned d = 0; d < 4; ++d) {
+        if (d == (rank & 3)) continue;
+        const uint32_t a = mapa(smem_u32(h1), (rank & ~3u) + d) + (r4 * LDS + 16 * d + 4 * k4) * 4;
+        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[d].x), "=f"(v[d].y), "=f"(v[d].z), "=f"(v[d].w) : "r"(a) : "memory");
+      }
+      float sacc = 0.f;
+#pragma unroll
+      for (unsigned d = 0; d < 4; ++d) if (d != (rank & 3)) sacc += v[d].x;
+      keep += sacc;
+      long long c1 = clock64();
+#pragma unroll
+      for (unsigned d = 0; d < 4; ++d) if (d != (rank & 3)) *reinterpret_cast<float4*>(h1 + r4 * LDS + 16 * d + 4 * k4) = v[d];
+      __syncthreads();
+      long long c2 = clock64();
+      t_pull_only += c1 - c0;
+      t_pull += c2 - c0;
+      asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    if (keep == 12345.f) errors[1] = 1;
+  }
   if (tid == 0) {
     cyc[rank * 3 + 0] = t_ag;
     cyc[rank * 3 + 1] = t_ss;
     cyc[rank * 3 + 2] = t_cb;
+    if (rank == 0) printf("   [rank 0] sync+fence+barrier %.0f   cluster.sync() %.0f   pull 3xfloat4: loads %.0f, +stores+sync %.0f cycles\n",
+                          double(t_c2) / iters, double(t_c3) / iters, double(t_pull_only) / iters, double(t_pull) / iters);
   }
   if (bad) atomicAdd(errors, bad);
 }
@@ -119,9 +168,9 @@ static int run(int cs, int active, int iters) {
   unsigned long long* cyc;
   int* err;
   cudaMalloc(&cyc, sizeof(unsigned long long) * 3 * 16);
-  cudaMalloc(&err, sizeof(int));
+  cudaMalloc(&err, 2 * sizeof(int));
   cudaMemset(cyc, 0, sizeof(unsigned long long) * 3 * 16);
-  cudaMemset(err, 0, sizeof(int));
+  cudaMemset(err, 0, 2 * sizeof(int));
   cudaError_t e = cudaFuncSetAttribute(probe, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   if (e != cudaSuccess) printf("  set non-portable: %s\n", cudaGetErrorString(e));
   cudaLaunchConfig_t cfg{};
@@ -163,7 +212,7 @@ int main() {
   cudaDeviceProp p;
   cudaGetDeviceProperties(&p, 0);
   printf("%s, %d SMs\n", p.name, p.multiProcessorCount);
-  const int iters = 2000;
+  const int iters = 500;
   run(4, 4, iters);
   run(8, 8, iters);
   run(12, 12, iters);

@@ -34,8 +34,8 @@ upd.run(data, perms=[perm])
 torch.cuda.synchronize()
 lib.spo_debug_phase_cycles(buf, 1)
 names = ["top (stage-in+sync)", "L1 GEMM+tanh", "barrier 1", "h1 pull", "L2+ypartial", "barrier 2", "y pull+loss rows", "small grads+dz2",
-         "dh1 partial+dW2+db2", "barrier 3", "dh1 pull+dz1", "dW1+db1", "dp exchange", "reg+sumsq", "barrier 4", "Adam"]
+         "dh1 partial", "barrier 3", "dW2+db2 (dh1 in flight)", "dh1 reduce+dz1", "dW1+db1", "dp exchange", "reg+sumsq", "barrier 4", "Adam"]
 for rank in range(12):
-    row = [buf[rank * 24 + i] / steps for i in range(16)]
+    row = [buf[rank * 24 + i] / steps for i in range(17)]
     net = ("actor", "reward critic", "cost critic")[rank // 4]
     print(f"{net:13s} q{rank % 4} total {sum(row):7.0f} cyc/step | " + " ".join(f"{n}={v:.0f}" for n, v in zip(names, row)))
