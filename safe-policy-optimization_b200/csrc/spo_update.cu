@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       fetch_idx(qt + 2, st, sb);
       cp_async_commit();
     };
-    // push `n` of this thread's gradient values (word index w0 + i * UT + tid of the CTA slot) to every peer GPU
+    // push `n` of this thread's gradient values (words (w0 + i) * UT + tid of the CTA slot) to every peer GPU
     auto dp_push = [&](const float* vals, auto n_c, int w0) {
       constexpr int n = decltype(n_c)::value;
       const size_t base = ((static_cast<size_t>(seq & 1u) * world + me) * NCTA + rank) * DPW;
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         if (r == me) continue;
         float2* dst = reinterpret_cast<float2*>(a.comm.grad_bufs[r]) + base;
 #pragma unroll
-        for (int i = 0; i < n; ++i) st_ll(dst + w0 + i * UT + tid, vals[i], seq);
+        for (int i = 0; i < n; ++i) st_ll(dst + (w0 + i) * UT + tid, vals[i], seq);
       }
     };
     // rank-ordered sum of `n` values with the words received from every peer GPU, scaled by 1/world
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         for (int i = 0; i < n; ++i) {
           float v = 0.f;
           unsigned polls = 0;
-          while (!ld_ll(src + w0 + i * UT + tid, seq, v)) {
+          while (!ld_ll(src + (w0 + i) * UT + tid, seq, v)) {
             if (*reinterpret_cast<volatile int*>(&comm_dead)) { v = 0.f; break; }
             if (++polls > limit) { comm_dead = 1; atomicExch(&ctrl->stop, 2); v = 0.f; break; }
           }
