@@ -47,10 +47,34 @@ for p in (ROOT, PKG):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-TASK = "SafetyPointGoal1-v0"
-D_OBS, D_ACT = 60, 2
-BYTES_PER_SAMPLE_UPDATE = 4 * (D_OBS + D_ACT + 4) + 8      # 264 B gathered + 8 B index
-FLOPS_PER_SAMPLE_UPDATE = 3 * 48128                          # fwd + bwd of the three nets
+# BASELINE.json configs[1] (the headline; what the driver runs), configs[2] and configs[3] (per-GPU shard of the 4-GPU config)
+WORKLOADS = {
+    "ppo_lag": dict(algo="ppo_lag", task="SafetyPointGoal1-v0", D=60, A=2, envs=1024, batch=64,
+                    metric="env-steps/sec PPO-Lag SafetyPointGoal1 @1024 envs/GPU",
+                    text="BASELINE.json configs[1]: PPO-Lag SafetyPointGoal1-v0 shape (obs 60, act 2, hidden 64x64)",
+                    update="batch 64, <=40 passes with KL early stop"),
+    "cpo": dict(algo="cpo", task="SafetyCarButton1-v0", D=88, A=2, envs=1024, batch=128,
+                metric="env-steps/sec CPO SafetyCarButton1 @1024 envs/GPU",
+                text="BASELINE.json configs[2]: CPO SafetyCarButton1-v0 shape (obs 88, act 2, hidden 64x64)",
+                update="2 x 15-iteration CG (33 FVPs over the full batch) + line search + 10 passes of batch-128 critic regression"),
+    "focops": dict(algo="focops", task="SafetyAntVelocity-v1", D=27, A=8, envs=512, batch=64,
+                   metric="env-steps/sec FOCOPS SafetyAntVelocity @512 envs/GPU",
+                   text="BASELINE.json configs[3]: FOCOPS SafetyAntVelocity-v1 shape (obs 27, act 8, hidden 64x64), 2048 envs over 4 GPUs = 512 per GPU",
+                   update="batch 64, <=40 passes with KL early stop, KL-projection loss"),
+}
+WL = WORKLOADS["ppo_lag"]
+TASK, D_OBS, D_ACT = WL["task"], WL["D"], WL["A"]
+
+
+def select_workload(name):
+    global WL, TASK, D_OBS, D_ACT
+    WL = WORKLOADS[name]
+    TASK, D_OBS, D_ACT = WL["task"], WL["D"], WL["A"]
+
+
+def bytes_per_sample_update():
+    """obs + act + logp/adv/targets gathered per sample per pass + the 8 B index."""
+    return 4 * (D_OBS + D_ACT + 4) + 8
 
 
 T_START = time.time()
@@ -63,7 +87,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("spo", "reference"), default="spo")
-    ap.add_argument("--num-envs", type=int, default=1024, help="envs per GPU")
+    ap.add_argument("--config", choices=tuple(WORKLOADS), default="ppo_lag",
+                    help="ppo_lag = BASELINE.json configs[1] (headline), cpo = configs[2], focops = configs[3] (per-GPU shard)")
+    ap.add_argument("--num-envs", type=int, default=0, help="envs per GPU (0 = the workload's own)")
     ap.add_argument("--horizon", type=int, default=1000, help="steps per env per epoch (T)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--ref-horizon", type=int, default=0,
@@ -132,45 +158,60 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------
 
 def build_trainer(args, device, rank, resident, dp=None):
-    """The public trainer objects of safepo.single_agent.ppo_lag, assembled once so that
-    epochs can be timed individually."""
+    """The public trainer objects of safepo.single_agent.<algo>, assembled once so that epochs can be timed individually."""
+    import importlib
     from safepo import _lib as L
     from safepo.common.buffer import VectorizedOnPolicyBuffer
     from safepo.common.lagrange import Lagrange
     from safepo.common.logger import EpochLogger
     from safepo.common.model import ActorVCritic
     from safepo.common.synthetic_env import SyntheticVecEnv
-    from safepo.single_agent import ppo_lag
-    from safepo.single_agent._engine import DeviceTapeRollout, PolicyGradientUpdate, Rollout, seed_all
+    from safepo.single_agent._engine import (CriticRegression, DeviceTapeRollout, PolicyGradientUpdate, Rollout, TrustRegionUpdate,
+                                             seed_all)
     from safepo.utils.config import single_agent_args
 
+    algo = WL["algo"]
+    mod = importlib.import_module(f"safepo.single_agent.{algo}")
     N, T = args.num_envs, args.horizon
     a, _ = single_agent_args(["--num-envs", str(N), "--steps-per-epoch", str(N * T), "--total-steps", str(N * T * 1000),
-                              "--seed", str(rank), "--rng", "device"])
+                              "--seed", str(rank), "--rng", "device", "--task", TASK])
     seed_all(rank)
     env = SyntheticVecEnv(N, D_OBS, D_ACT, episode_len=T, seed=rank)
-    cfg = dict(ppo_lag.default_cfg)
+    cfg = dict(mod.default_cfg)
     policy = ActorVCritic(D_OBS, D_ACT, cfg["hidden_sizes"]).to(device)
     buffer = VectorizedOnPolicyBuffer(env.observation_space, env.action_space, size=T, device=device, num_envs=N, gamma=cfg["gamma"])
-    lagrange = Lagrange(a.cost_limit, a.lagrangian_multiplier_init, a.lagrangian_multiplier_lr)
-    log_dir = os.path.join(tempfile.mkdtemp(prefix="spo_bench_"), "exp", TASK, "ppo_lag", f"rank{rank}")
+    lagrange = None if algo == "cpo" else Lagrange(a.cost_limit, a.lagrangian_multiplier_init, a.lagrangian_multiplier_lr,
+                                                   lagrangian_upper_bound=2.0 if algo == "focops" else None)
+    log_dir = os.path.join(tempfile.mkdtemp(prefix="spo_bench_"), "exp", TASK, algo, f"rank{rank}")
     logger = EpochLogger(log_dir, seed=str(rank), verbose=False, use_tensorboard=False)
     roll = (DeviceTapeRollout if resident else Rollout)(env, policy, buffer, logger, a, device)
-    upd = PolicyGradientUpdate(policy, cfg, L.LOSS_PPO_CLIP, epochs=1000, host_rng=False, device=device, dp=dp)
-    return dict(env=env, policy=policy, buffer=buffer, lagrange=lagrange, logger=logger, roll=roll, upd=upd, T=T, N=N, dp=dp,
-                device=device)
+    tr = dict(env=env, policy=policy, buffer=buffer, lagrange=lagrange, logger=logger, roll=roll, T=T, N=N, dp=dp, device=device,
+              algo=algo, args=a, cfg=cfg)
+    if algo == "cpo":
+        tr["trust"] = TrustRegionUpdate(policy, cfg, device, dp=dp)
+        tr["critics"] = CriticRegression(policy, cfg, False, device, dp=dp)
+    else:
+        kind = L.LOSS_FOCOPS if algo == "focops" else L.LOSS_PPO_CLIP
+        tr["upd"] = PolicyGradientUpdate(policy, cfg, kind, epochs=1000, host_rng=False, device=device, dp=dp)
+    return tr
 
 
 def one_epoch(tr):
-    """Exactly the epoch body of run_policy_gradient (ppo_lag.main)."""
+    """Exactly the epoch body of run_policy_gradient / run_trust_region (the algorithms' main())."""
     tr["roll"].run(tr["T"])
-    dp = tr["dp"]
-    jc = tr["logger"].get_stats("Metrics/EpCost") if dp is None else dp.mean_episode_cost(tr["logger"], device=tr["device"])
-    tr["lagrange"].update_lagrange_multiplier(jc)
-    data = tr["buffer"].get(tr["lagrange"].lagrangian_multiplier, all_reduce=None if dp is None else dp.all_reduce_sum)
-    res = tr["upd"].run(data)
+    dp, lg = tr["dp"], tr["logger"]
+    jc = lg.get_stats("Metrics/EpCost") if dp is None else dp.mean_episode_cost(lg, device=tr["device"])
+    red = None if dp is None else dp.all_reduce_sum
+    if tr["algo"] == "cpo":
+        data = tr["buffer"].get(0.0, all_reduce=red)
+        r = tr["trust"].run_cpo(data, jc - tr["args"].cost_limit)
+        c = tr["critics"].run(data)
+        res = {"stop_iter": int(r.get("Misc/AcceptanceStep", 0)), "steps": c["steps"]}
+    else:
+        tr["lagrange"].update_lagrange_multiplier(jc)
+        data = tr["buffer"].get(tr["lagrange"].lagrangian_multiplier, all_reduce=red)
+        res = tr["upd"].run(data)
     tr["buffer"].reset_segments()
-    lg = tr["logger"]
     if not lg.logged:   # keep the logger's per-epoch state machine moving (A3)
         for k in ("Metrics/EpRet", "Metrics/EpCost", "Metrics/EpLen"):
             lg.log_tabular(k)
@@ -191,8 +232,13 @@ def timed_epochs(tr, K, W, world, device):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stops, msteps = [], []
     with ClockSampler(device.index) as clk:
+        flush = None
+        if tr["N"] * tr["T"] * D_OBS * 4 < 126e6:      # inputs smaller than L2: evict them between timed epochs
+            flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
         e0.record()
         for _ in range(K):
+            if flush is not None:
+                flush.fill_(0.0)
             res = one_epoch(tr)
             stops.append(res["stop_iter"]); msteps.append(res["steps"])
         e1.record()
@@ -208,31 +254,74 @@ def timed_epochs(tr, K, W, world, device):
                 h2d=(tr["roll"].bytes_h2d - h0) / K, d2h=(tr["roll"].bytes_d2h - d0) / K)
 
 
-def time_update_kernel(tr, device):
-    """Average duration of one spo_pg_update launch (one pass of 16000 minibatch steps),
-    CUDA events on the launching stream, 3 warm launches + 3 timed."""
+def time_dominant_kernel(tr, device):
+    """Average duration of one launch of the workload's dominant kernel, CUDA events on the launching stream, 3 warm
+    launches + 3 timed.  PPO-Lag / FOCOPS: spo_pg_update (one pass over the epoch's data).  CPO: spo_fvp over the full
+    batch (the 33-per-epoch Fisher-vector product; SURVEY 8d: 98 560 FLOP and 4*D bytes per sample) plus, for the record,
+    one critic-regression pass."""
     import ctypes as C
     from safepo import _lib as L
-    upd, pol = tr["upd"], tr["policy"]
+    pol = tr["policy"]
     data = tr["buffer"].get(0.0)
     S = data["obs"].shape[0]
-    batch = L.Batch(L.ptr(data["obs"]), L.ptr(data["act"]), L.ptr(data["log_prob"]), L.ptr(data["target_value_r"]),
-                    L.ptr(data["target_value_c"]), L.ptr(data["adv"]), None, None, S)
-    upd.ctrl.zero_()
-    times = []
-    for i in range(6):
-        perm = torch.randperm(S, device=device)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        L.check(L.lib().spo_pg_update(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(upd.adam.m), L.ptr(upd.adam.v), L.ptr(upd.adam.t),
-                                      C.byref(batch), L.ptr(perm), S, 64, L.LOSS_PPO_CLIP, C.byref(upd.hp), L.ptr(upd.ctrl),
-                                      L.stream()), "spo_pg_update")
-        e1.record()
-        torch.cuda.synchronize()
-        if i >= 3:
-            times.append(e0.elapsed_time(e1))
+
+    def timed(fn):
+        times = []
+        for i in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                times.append(e0.elapsed_time(e1))
+        return float(np.mean(times))
+
+    out = {}
+    if tr["algo"] == "cpo":
+        trust, crit = tr["trust"], tr["critics"]
+        v = torch.randn(pol.n_actor, device=device)
+        trust._old_dist(data)
+        ms = timed(lambda: trust._fvp(data, v, trust.Fx))
+        flops = S * 5 * 2 * (D_OBS * 64 + 64 * 64 + 64 * D_ACT)
+        out = {"kernel": "spo_fvp (Fisher-vector product over the full batch, fp32 FFMA tile GEMMs)", "ms": ms, "bound": "tensor",
+               "achieved": flops / (ms / 1e3) / 1e12, "unit": "TFLOP/s", "units_per_launch": S}
+        batch = L.Batch(L.ptr(data["obs"]), None, None, L.ptr(data["target_value_r"]), L.ptr(data["target_value_c"]), None, None, None, S)
+        crit.ctrl.zero_()
+        B = tr["cfg"]["batch_size"]
+
+        def crit_pass():
+            perm = torch.randperm(S, device=device)
+            L.check(L.lib().spo_pg_update(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(crit.adam.m), L.ptr(crit.adam.v), L.ptr(crit.adam.t),
+                                          C.byref(batch), L.ptr(perm), S, B, L.LOSS_CRITIC_ONLY, C.byref(crit.hp), L.ptr(crit.ctrl),
+                                          L.stream()), "spo_pg_update")
+        ms_c = timed(crit_pass)
+        out["critic_pass_ms"] = ms_c
+        out["us_per_minibatch_step"] = ms_c * 1e3 / ((S + B - 1) // B)
+    else:
+        upd = tr["upd"]
+        kind = L.LOSS_FOCOPS if tr["algo"] == "focops" else L.LOSS_PPO_CLIP
+        old_mean = old_std = None
+        if kind == L.LOSS_FOCOPS:
+            old_mean = torch.zeros(S, D_ACT, device=device)
+            old_std = torch.ones(S, D_ACT, device=device)
+        batch = L.Batch(L.ptr(data["obs"]), L.ptr(data["act"]), L.ptr(data["log_prob"]), L.ptr(data["target_value_r"]),
+                        L.ptr(data["target_value_c"]), L.ptr(data["adv"]), L.ptr(old_mean), L.ptr(old_std), S)
+        upd.ctrl.zero_()
+
+        def upd_pass():
+            perm = torch.randperm(S, device=device)
+            L.check(L.lib().spo_pg_update(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(upd.adam.m), L.ptr(upd.adam.v), L.ptr(upd.adam.t),
+                                          C.byref(batch), L.ptr(perm), S, 64, kind, C.byref(upd.hp), L.ptr(upd.ctrl), L.stream()),
+                    "spo_pg_update")
+        ms = timed(upd_pass)
+        steps = (S + 63) // 64
+        extra = 8 * D_ACT if kind == L.LOSS_FOCOPS else 0        # old_mean / old_std rows
+        out = {"kernel": f"spo_update_kernel (one {tr['algo']} pass = {steps} serial minibatch steps)", "ms": ms, "bound": "hbm",
+               "achieved": steps * 64 * (bytes_per_sample_update() + extra) / (ms / 1e3) / 1e9, "unit": "GB/s",
+               "units_per_launch": steps, "us_per_minibatch_step": ms * 1e3 / steps}
     tr["buffer"].reset_segments()
-    return float(np.mean(times)), (S + 63) // 64
+    return out
 
 
 def cpu_baseline(args, kind="port", threads=4, horizon=None):
@@ -248,7 +337,8 @@ def cpu_baseline(args, kind="port", threads=4, horizon=None):
     from oracle import trainers as TR
     from safepo.common.synthetic_env import SyntheticVecEnv
     N, T = args.num_envs, args.horizon
-    Ts = horizon or max(1, min(16, int((args.cpu_seconds - 4.0) / 2.5)))
+    per_T = 2.5 * (N / 1024.0) * (0.5 if WL["algo"] == "cpo" else 1.0)     # rough seconds of oracle update per unit of horizon
+    Ts = horizon or max(1, min(16, int((args.cpu_seconds - 4.0) / per_T)))
     torch.set_num_threads(threads)
     # (a) per-step rollout cost away from the epoch end
     torch.manual_seed(0)
@@ -265,10 +355,10 @@ def cpu_baseline(args, kind="port", threads=4, horizon=None):
     t_step = (time.time() - t0) / r
     # (b) one real epoch at horizon Ts through the trainer
     env = SyntheticVecEnv(N, D_OBS, D_ACT, episode_len=T, seed=0)
-    a = TR.default_args(num_envs=N, steps_per_epoch=N * Ts, total_steps=N * Ts * 1000, seed=0, torch_threads=threads)
+    a = TR.default_args(num_envs=N, steps_per_epoch=N * Ts, total_steps=N * Ts * 1000, seed=0, torch_threads=threads, task=TASK)
     t1 = time.time()
     seen = {}
-    _, log, times = TR.train("ppo_lag", a, env, max_epochs=1,
+    _, log, times = TR.train(WL["algo"], a, env, max_epochs=1,
                              hooks={"after_update": lambda epoch, pol_, data_, extra: seen.update(extra)})
     t_epoch = time.time() - t1
     t_roll, t_upd = times["rollout"][0], times["update"][0]
@@ -276,13 +366,17 @@ def cpu_baseline(args, kind="port", threads=4, horizon=None):
     t_close = max(t_roll - (Ts - 1) * t_step, 0.0)
     S_full, S_s = N * T, N * Ts
     epoch_s = (T - 1) * t_step + t_close + t_upd * T / Ts
-    mb = passes * ((S_s + 63) // 64) if passes > 0 else 0
+    B = WL["batch"]
+    if WL["algo"] == "cpo":
+        passes = 10                                   # critic regression: learning_iters = 10 (cpo.py:52), no early stop
+    mb = passes * ((S_s + B - 1) // B) if passes > 0 else 0
     return {"value": S_full / epoch_s, "unit": "env-steps/s", "cores": threads, "kind": kind,
-            "sample": (f"one executed PPO-Lag epoch of the oracle port at {N} envs x {Ts} steps (S={S_s}: rollout {t_roll:.2f} s, "
-                       f"update {t_upd:.2f} s = {passes} passes / {mb} minibatch steps of 64, total {t_epoch:.2f} s) "
+            "sample": (f"one executed {WL['algo']} epoch of the oracle port at {N} envs x {Ts} steps (S={S_s}: rollout {t_roll:.2f} s, "
+                       f"update {t_upd:.2f} s incl. {passes} passes / {mb} minibatch steps of {B}, total {t_epoch:.2f} s) "
                        f"+ {r} mid-epoch vector steps ({t_step*1e3:.1f} ms each); scaled linearly to {T} steps/env"),
             "measured_epoch": {"horizon": Ts, "seconds": t_epoch, "env_steps_per_s": S_s / t_epoch, "passes": passes},
-            "ms_per_minibatch_step": (t_upd / mb * 1e3) if mb else None, "ms_per_vector_env_step": t_step * 1e3, "passes": passes}
+            "ms_per_minibatch_step": (t_upd / mb * 1e3) if (mb and WL["algo"] != "cpo") else None,
+            "ms_per_vector_env_step": t_step * 1e3, "passes": passes}
 
 
 def update_traffic_per_step():
@@ -316,7 +410,7 @@ def run_spo(args):
         dp = DataParallel()
     tr = build_trainer(args, device, rank, resident=True, dp=dp)
     val = timed_epochs(tr, K, W, world, device)
-    kern_ms, kern_steps = time_update_kernel(tr, device) if world == 1 else (float("nan"), 1)
+    dom = time_dominant_kernel(tr, device) if world == 1 else None
     e2e = None
     if not args.no_e2e:
         # same policy / optimizer / buffer objects, host-env rollout front end; one warm-up epoch for its copy path
@@ -346,31 +440,46 @@ def run_spo(args):
     hbm, how = peaks()
     value = S * K * world / (val["ms"] / 1e3)
     passes = int(round(float(np.mean(val["stops"])))) or 1
-    if world > 1:   # per-launch timing is a single-GPU measurement; derive the per-step figure from the epoch
-        kern_steps = (S + 63) // 64
-        kern_ms = val["ms"] / K / max(passes, 1)
-    alg_bytes = kern_steps * 64 * BYTES_PER_SAMPLE_UPDATE
-    achieved = alg_bytes / (kern_ms / 1e3) / 1e9
-    traffic_step, traffic_src = update_traffic_per_step()
+    B = WL["batch"]
+    if dom is None:   # per-launch timing is a single-GPU measurement; under torchrun derive the per-step figure from the epoch
+        steps_per_pass = (S + B - 1) // B
+        n_pass = 10 if WL["algo"] == "cpo" else max(passes, 1)
+        ms = val["ms"] / K / n_pass
+        dom = {"kernel": "spo_update_kernel (per-step figure derived from the epoch: all of the epoch attributed to the update passes)",
+               "ms": ms, "bound": "hbm", "achieved": steps_per_pass * B * bytes_per_sample_update() / (ms / 1e3) / 1e9, "unit": "GB/s",
+               "units_per_launch": steps_per_pass, "us_per_minibatch_step": ms * 1e3 / steps_per_pass}
+    if dom["bound"] == "hbm":
+        peak, peak_how = hbm, how
+    else:
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peak, peak_how = float(json.load(f)["bf16_tflops"]), "measured dense bf16 (MEASURED_PEAKS.json); the kernel itself runs fp32 FFMA"
+        except Exception:
+            peak, peak_how = 1590.0, "fallback dense bf16 (B200_PROFILING.md); the kernel itself runs fp32 FFMA"
+    traffic_step, traffic_src = update_traffic_per_step() if WL["algo"] == "ppo_lag" else (None, None)
+    S_obs_mb = S * D_OBS * 4 / 1e6
     out = {
-        "metric": "env-steps/sec PPO-Lag SafetyPointGoal1 @1024 envs/GPU", "value": value, "unit": "env-steps/s",
+        "metric": WL["metric"], "value": value, "unit": "env-steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": val["ms"] / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[1]: PPO-Lag SafetyPointGoal1-v0 shape (obs 60, act 2, hidden 64x64), "
-                               f"{args.num_envs} envs/GPU x {args.horizon} steps/epoch, batch 64, <=40 passes with KL early stop",
+        "config": {"workload": f"{WL['text']}, {args.num_envs} envs/GPU x {args.horizon} steps/epoch, {WL['update']}",
                    "samples_per_step_per_gpu": S, "stop_iter": val["stops"], "minibatch_steps_per_epoch": val["msteps"],
-                   "us_per_minibatch_step": kern_ms * 1e3 / kern_steps, "ms_per_update_pass": kern_ms,
-                   "l2": "inputs larger than L2 (245.8 MB observation buffer per epoch vs 126 MB L2)",
-                   "parallelism": (f"dp{world}: envs sharded, per-rank batch 64 (global batch {64 * world}), in-kernel NVLink gradient sum per minibatch step"
+                   "us_per_minibatch_step": dom.get("us_per_minibatch_step"), "ms_per_dominant_launch": dom["ms"],
+                   "l2": f"inputs larger than L2 ({S_obs_mb:.1f} MB observation buffer per epoch vs 126 MB L2)" if S_obs_mb > 126
+                         else f"observation buffer {S_obs_mb:.1f} MB fits the 126 MB L2: a 256 MB scratch write flushes it between timed epochs",
+                   "parallelism": (f"dp{world}: envs sharded, per-rank batch {B} (global batch {B * world}), in-kernel NVLink gradient sum per minibatch step"
                                    if world > 1 else "single")},
         "clocks": val["clocks"],
         "gpu_launches": val["launches"],
-        "roofline": {"kernel": "spo_update_kernel (one PPO-Lag pass = 16000 serial minibatch steps)", "bound": "hbm",
-                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": (traffic_step * kern_steps) if traffic_step is not None else None, "traffic_source": traffic_src,
-                     "peak_source": how,
-                     "note": "serial-latency-bound chain of 64-row Adam steps (SURVEY H3): us_per_minibatch_step is the figure of merit"},
+        "roofline": {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": peak, "unit": dom["unit"],
+                     "frac": dom["achieved"] / peak,
+                     "traffic": (traffic_step * dom["units_per_launch"]) if traffic_step is not None else None, "traffic_source": traffic_src,
+                     "peak_source": peak_how,
+                     "note": ("serial-latency-bound chain of minibatch Adam steps (SURVEY H3): us_per_minibatch_step is the figure of merit"
+                              if dom["bound"] == "hbm" else "fp32 FFMA tile GEMMs measured against the tensor roof the survey names for this kernel")},
     }
+    if "critic_pass_ms" in dom:
+        out["config"]["ms_per_critic_regression_pass"] = dom["critic_pass_ms"]
     if e2e is not None:
         out["e2e"] = {"value": S * e2e["K"] * world / (e2e["ms"] / 1e3), "unit": "env-steps/s", "h2d_bytes_per_step": e2e["h2d"],
                       "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": e2e["ms"] / e2e["K"], "steps": e2e["K"], "warmup": 1,
@@ -434,11 +543,10 @@ def run_reference(args):
             vals.append(r)
     v = float(np.mean([r["value"] for r in vals]))
     S = args.num_envs * args.horizon
-    out = {"impl": "reference", "metric": "env-steps/sec PPO-Lag SafetyPointGoal1 @1024 envs/GPU", "value": v, "unit": "env-steps/s",
+    out = {"impl": "reference", "metric": WL["metric"], "value": v, "unit": "env-steps/s",
            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": S / v * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "BASELINE.json configs[1]: PPO-Lag SafetyPointGoal1-v0 shape (obs 60, act 2, hidden 64x64), "
-                                  f"{args.num_envs} envs/GPU x {args.horizon} steps/epoch, batch 64, <=40 passes with KL early stop",
+           "config": {"workload": f"{WL['text']}, {args.num_envs} envs/GPU x {args.horizon} steps/epoch, {WL['update']}",
                       "sampling": f"each step executes one full epoch at {Ts} steps/env and scales it linearly to {args.horizon} (ms_per_step is the scaled epoch)",
                       "passes_observed": [r["passes"] for r in vals],
                       "measured_env_steps_per_s_at_reduced_horizon": float(np.mean([r["measured_epoch"]["env_steps_per_s"] for r in vals]))},
@@ -449,6 +557,9 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse()
+    select_workload(a.config)
+    if a.num_envs <= 0:
+        a.num_envs = WL["envs"]
     if a.impl == "reference":
         run_reference(a)
     else:

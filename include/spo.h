@@ -281,6 +281,14 @@ int spo_conjugate_gradient(const spo_dims* d, const float* params, const float* 
                            const float* b, int iters, float damping, float residual_tol, float eps,
                            float* x, float* work, void* stream);
 
+/* The solver above split at the Fisher-vector product, for data-parallel ranks (exchange 3'): every
+ * FVP result is averaged over the ranks before the step that consumes it.  Same work layout (r | p | z | - | scalars):
+ *   spo_cg_begin(b, x, work);
+ *   repeat iters times: spo_fvp(..., v = work + P_a, out = work + 2*P_a); all-reduce(mean) of work + 2*P_a; spo_cg_update(x, work, ...)
+ * (cpo.py:81-106; the residual break stays a device flag). */
+int spo_cg_begin(const spo_dims* d, const float* b, float* x, float* work, void* stream);
+int spo_cg_update(const spo_dims* d, float* x, float* work, float residual_tol, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

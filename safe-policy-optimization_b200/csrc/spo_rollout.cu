@@ -5,6 +5,11 @@
 // (store), safepo/single_agent/ppo_lag.py:187-234 (segment / bootstrap rule).
 #include "spo_common.cuh"
 
+// csrc/spo_tc_forward.cu: the same step on TMA + tcgen05 (returns 1 when the shape does not qualify)
+int spo_tc_step_launch(const spo_dims* d, const float* params, const float* obs, const float* eps, uint64_t seed, uint64_t offset,
+                       int deterministic, int n, float* act, float* logp, float* v_r, float* v_c, const spo_rollout* store, int t,
+                       int net_base, cudaStream_t stream);
+
 namespace {
 
 constexpr float kLogSqrt2Pi = 0.91893853320467274178f;  // math.log(math.sqrt(2*math.pi))
@@ -174,6 +179,11 @@ int spo_policy_step(const spo_dims* d, const float* params, const float* obs, co
   } else {
     a.store.steps = 1;
   }
+  // batches of >= 128 rows with a TMA-friendly layout run on the tensor-core kernel; single rows ([D] inputs of the
+  // bootstrap calls, ppo_lag.py:206,211), odd obs_dim and obs_dim > 64 on the FFMA tile kernel below
+  rc = spo_tc_step_launch(d, params, obs, eps, seed, offset, deterministic, n, act, logp, v_r, v_c, store, t, 0,
+                          static_cast<cudaStream_t>(stream));
+  if (rc <= 0) return rc;
   return launch_step(a, static_cast<cudaStream_t>(stream));
 }
 
@@ -185,6 +195,8 @@ int spo_critic_values(const spo_dims* d, const float* params, const float* obs, 
   StepArgs a{};
   a.params = params; a.obs = obs; a.n = n; a.D = d->obs_dim; a.A = d->act_dim;
   a.v_r = v_r; a.v_c = v_c; a.net_base = 1; a.store.steps = 1;
+  rc = spo_tc_step_launch(d, params, obs, nullptr, 0, 0, 1, n, nullptr, nullptr, v_r, v_c, nullptr, 0, 1, static_cast<cudaStream_t>(stream));
+  if (rc <= 0) return rc;
   return launch_step(a, static_cast<cudaStream_t>(stream));
 }
 

@@ -1,8 +1,12 @@
-// Full-batch actor forward on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+// MLP forward passes on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
 //
-// Serves spo_actor_forward / spo_actor_kl / spo_actor_kl_accumulate for large batches
+// Serves (a) spo_actor_forward / spo_actor_kl / spo_actor_kl_accumulate for large batches
 // (reference: safepo/single_agent/ppo_lag.py:277 and :338-344 -- policy.actor(data["obs"])
-// over S = 1,024,000 observations and the KL against the old distribution).
+// over S = 1,024,000 observations and the KL against the old distribution), and
+// (b) spo_policy_step / spo_critic_values, the rollout forward of all three nets
+// (safepo/common/model.py:149-170 ActorVCritic.step fused with buffer.py:84-95 store): one launch,
+// grid (row tiles, nets); the actor CTAs sample, evaluate the log-density and write the
+// transition straight into slot t of the env-major rollout arrays from the epilogue.
 //
 // Per 128-row tile of a persistent CTA:
 //   TMA      obs tile [128 x D] -> smem, as a 3-D box (16-byte k-chunk, row, chunk index) so the
@@ -33,15 +37,24 @@ constexpr uint32_t SBO = 128;                // 8 rows x 16 B core matrices back
 constexpr uint32_t X_TILE_BYTES = TC_ROWS * 64 * 4;   // 32 KB
 constexpr uint32_t W_TILE_BYTES = SPO_HID * 64 * 4;   // 16 KB
 
+constexpr float kLogSqrt2Pi = 0.91893853320467274178f;  // math.log(math.sqrt(2*math.pi))
+
 struct TcArgs {
   const float* params;
   const float* old_mean;
   const float* old_log_std;
   float* mean_out;
   int64_t count;
-  int D, A, mode, reduce;     // mode 0: means, 1: KL + finalize, 2: KL accumulate only
+  int D, A, mode, reduce;     // mode 0: means, 1: KL + finalize, 2: KL accumulate only, 3: rollout step (grid.y = nets)
   float target_kl;
   spo_update_ctrl* ctrl;
+  // mode 3 (rollout step): net = net_base + blockIdx.y
+  const float* obs;           // [n, D] (row copy into the buffer slot)
+  const float* eps;           // [n, A] or null (in-kernel Philox)
+  uint64_t seed, offset;
+  int deterministic, net_base, has_store, t;
+  float *act, *logp, *v_r, *v_c;
+  spo_rollout store;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -167,16 +180,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spo_tc_forward_kernel(const __g
   __shared__ bool is_last;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (a.mode >= 1 && *reinterpret_cast<volatile int*>(&a.ctrl->stop)) return;
-  const int D = a.D, A = a.A;
-  const SpoNetOff off = spo_net_off(D, A, 0);
+  if ((a.mode == 1 || a.mode == 2) && *reinterpret_cast<volatile int*>(&a.ctrl->stop)) return;
+  const int D = a.D;
+  const int net = (a.mode == 3) ? a.net_base + static_cast<int>(blockIdx.y) : 0;
+  const SpoNetOff off = spo_net_off(D, a.A, net);
+  const int A = off.out;      // outputs of this net's last layer (act_dim for the actor, 1 for a critic)
   float* b1 = small; float* b2 = small + 64; float* w3 = small + 128; float* b3 = w3 + A * 64; float* ls = b3 + 8; float* ols = ls + 8;
 
   load_weight_tile(a.params + off.w1, D, w1_hi, w1_lo, tid, TC_THREADS);
   load_weight_tile(a.params + off.w2, SPO_HID, w2_hi, w2_lo, tid, TC_THREADS);
   for (int i = tid; i < SPO_HID; i += TC_THREADS) { b1[i] = a.params[off.b1 + i]; b2[i] = a.params[off.b2 + i]; }
   for (int i = tid; i < A * SPO_HID; i += TC_THREADS) w3[i] = a.params[off.w3 + i];
-  if (tid < A) { b3[tid] = a.params[off.b3 + tid]; ls[tid] = a.params[off.log_std + tid]; ols[tid] = a.old_log_std ? a.old_log_std[tid] : 0.f; }
+  if (tid < A) {
+    b3[tid] = a.params[off.b3 + tid];
+    ls[tid] = (net == 0) ? a.params[off.log_std + tid] : 0.f;
+    ols[tid] = a.old_log_std ? a.old_log_std[tid] : 0.f;
+  }
   if (tid == 0) {
     mbar_init(&bar_x_full, 1);
     mbar_init(&bar_xs_full, TC_EPI_THREADS);
@@ -197,6 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spo_tc_forward_kernel(const __g
 
   const int64_t n_tiles = (a.count + TC_ROWS - 1) / TC_ROWS;
   double kl_acc = 0.0;
+  // (mode 3 launches one CTA per tile: the loop body runs once)
   uint32_t phase = 0;
   if (warp == 8 && lane == 0 && static_cast<int64_t>(blockIdx.x) < n_tiles) {   // first tile's observations
     mbar_expect_tx(&bar_x_full, X_TILE_BYTES);
@@ -292,7 +312,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spo_tc_forward_kernel(const __g
       }
       asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");   // the 8 epilogue warps only
       const int64_t g = row0 + r;
-      if (half == 0 && g < a.count) {
+      if (a.mode == 3) {
+        const int T = a.store.steps;
+        if (half == 0 && g < a.count) {
+          if (net == 0) {
+            // sample + log-prob (model.py:161-167; Normal.rsample / log_prob), torch's operation order
+            float lp = 0.f;
+            float* act_out = a.act ? a.act + g * A : nullptr;
+            float* act_st = a.has_store ? a.store.act + (g * T + a.t) * A : nullptr;
+#pragma unroll
+            for (int j = 0; j < SPO_MAX_ACT; ++j)
+              if (j < A) {
+                const float mu = (mean[j] + pmean[r][j]) + b3[j];
+                const float std = expf(ls[j]);
+                float action = mu;
+                if (!a.deterministic) {
+                  float e;
+                  if (a.eps) {
+                    e = __ldg(a.eps + g * A + j);
+                  } else {
+                    const uint4 rnd = spo_philox(make_uint4(static_cast<uint32_t>(g), static_cast<uint32_t>(j >> 1),
+                                                            static_cast<uint32_t>(a.offset), static_cast<uint32_t>(a.offset >> 32)),
+                                                 make_uint2(static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32)));
+                    const float2 z = spo_box_muller(rnd.x, rnd.y);
+                    e = (j & 1) ? z.y : z.x;
+                  }
+                  action = __fadd_rn(mu, __fmul_rn(e, std));  // loc + eps * scale
+                }
+                const float diff = __fsub_rn(action, mu);
+                const float var = __fmul_rn(std, std);
+                const float q = __fdiv_rn(-__fmul_rn(diff, diff), __fmul_rn(2.f, var));
+                const float term = __fsub_rn(__fsub_rn(q, logf(std)), kLogSqrt2Pi);
+                lp = (j == 0) ? term : __fadd_rn(lp, term);
+                if (act_out) act_out[j] = action;
+                if (act_st) act_st[j] = action;
+              }
+            if (a.logp) a.logp[g] = lp;
+            if (a.has_store) a.store.logp[g * T + a.t] = lp;
+          } else {
+            const float v = (mean[0] + pmean[r][0]) + b3[0];
+            float* vout = (net == 1) ? a.v_r : a.v_c;
+            if (vout) vout[g] = v;
+            if (a.has_store) ((net == 1) ? a.store.value_r : a.store.value_c)[g * T + a.t] = v;
+          }
+        }
+        if (net == 0 && a.has_store) {
+          // observation rows into slot t (buffer.py:91-95): bit-exact copy from global (the smem tile holds the TF32 split)
+          const int rows = static_cast<int>((a.count - row0) < TC_ROWS ? (a.count - row0) : TC_ROWS), c4 = D >> 2;
+          for (int i = tid; i < rows * c4; i += TC_EPI_THREADS) {
+            const int rr = i / c4, c = i - rr * c4;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(a.obs + (row0 + rr) * D) + c);
+            *(reinterpret_cast<float4*>(a.store.obs + ((row0 + rr) * T + a.t) * D) + c) = v;
+          }
+        }
+      } else if (half == 0 && g < a.count) {
         if (a.mode == 0) {
 #pragma unroll
           for (int j = 0; j < SPO_MAX_ACT; ++j)
@@ -319,7 +392,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spo_tc_forward_kernel(const __g
     __syncthreads();
   }
 
-  if (a.mode >= 1) {
+  if (a.mode == 1 || a.mode == 2) {
     if (warp < 8) {
       kl_acc = spo_warp_sum(kl_acc);
       if (lane == 0) red[warp] = kl_acc;
@@ -369,25 +442,14 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
-// Returns SPO_OK when the tensor-core path ran, 1 when it does not apply (caller falls back
-// to the FFMA tile kernel), negative on error.
-int spo_tc_forward_launch(const spo_dims* d, const float* params, const float* obs, const float* old_mean,
-                          const float* old_log_std, float* mean_out, int64_t count, int mode, int reduce, float target_kl,
-                          spo_update_ctrl* ctrl, cudaStream_t stream) {
-  const int D = d->obs_dim;
-  if ((D & 3) != 0 || D > 64 || count < 8 * TC_ROWS) return 1;          // TMA needs 16-byte row pitch; K padded to 64
-  if ((reinterpret_cast<uintptr_t>(obs) & 15) != 0) return 1;
-  static int disabled = -1;
-  if (disabled < 0) disabled = (getenv("SPO_DISABLE_TCGEN05") != nullptr) ? 1 : 0;
-  if (disabled) return 1;
+static int encode_obs_map(CUtensorMap* map, const float* obs, int64_t count, int D) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) return 1;
-  CUtensorMap map;
   const cuuint64_t gdim[3] = {4, static_cast<cuuint64_t>(count), static_cast<cuuint64_t>(D / 4)};
   const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(D) * 4, 16};      // bytes: row pitch, k-chunk pitch
   const cuuint32_t box[3] = {4, TC_ROWS, 16};
   const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(obs), gdim, gstride, box, estr,
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(obs), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -399,18 +461,70 @@ int spo_tc_forward_launch(const spo_dims* d, const float* params, const float* o
     }
     return 1;
   }
-  TcArgs a{};
-  a.params = params; a.old_mean = old_mean; a.old_log_std = old_log_std; a.mean_out = mean_out; a.count = count;
-  a.D = D; a.A = d->act_dim; a.mode = mode; a.reduce = reduce; a.target_kl = target_kl; a.ctrl = ctrl;
-  const size_t smem = 4 * X_TILE_BYTES + 4 * W_TILE_BYTES + sizeof(float) * (128 + SPO_MAX_ACT * 64 + 24);   // 198.6 KB
-  static bool attr_set = false;
+  return 0;
+}
+
+static bool tc_path_enabled() {
+  static int disabled = -1;
+  if (disabled < 0) disabled = (getenv("SPO_DISABLE_TCGEN05") != nullptr) ? 1 : 0;
+  return !disabled;
+}
+
+static int tc_set_smem_attr() {
+  static bool attr_set = false;   // per process: one process drives one GPU
   if (!attr_set) {
     SPO_CUDA_TRY(cudaFuncSetAttribute(spo_tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
+  return SPO_OK;
+}
+
+constexpr size_t TC_SMEM_BYTES = 4 * X_TILE_BYTES + 4 * W_TILE_BYTES + sizeof(float) * (128 + SPO_MAX_ACT * 64 + 24);   // 198.6 KB
+
+// Rollout step / bootstrap values on the tensor-core path: grid (ceil(n / 128), nets).  Returns 1 when the shape does
+// not qualify (obs_dim % 4 != 0, obs_dim > 64, fewer than 128 rows, unaligned obs): the caller uses the FFMA tile kernel.
+int spo_tc_step_launch(const spo_dims* d, const float* params, const float* obs, const float* eps, uint64_t seed, uint64_t offset,
+                       int deterministic, int n, float* act, float* logp, float* v_r, float* v_c, const spo_rollout* store, int t,
+                       int net_base, cudaStream_t stream) {
+  const int D = d->obs_dim;
+  if ((D & 3) != 0 || D > 64 || n < TC_ROWS) return 1;
+  if ((reinterpret_cast<uintptr_t>(obs) & 15) != 0) return 1;
+  if (store && (reinterpret_cast<uintptr_t>(store->obs) & 15) != 0) return 1;
+  if (!tc_path_enabled()) return 1;
+  CUtensorMap map;
+  if (encode_obs_map(&map, obs, n, D)) return 1;
+  TcArgs a{};
+  a.params = params; a.count = n; a.D = D; a.A = d->act_dim; a.mode = 3;
+  a.obs = obs; a.eps = eps; a.seed = seed; a.offset = offset; a.deterministic = deterministic; a.net_base = net_base;
+  a.act = act; a.logp = logp; a.v_r = v_r; a.v_c = v_c;
+  if (store) { a.store = *store; a.has_store = 1; a.t = t; } else { a.store.steps = 1; }
+  int rc = tc_set_smem_attr();
+  if (rc) return rc;
+  dim3 grid((n + TC_ROWS - 1) / TC_ROWS, net_base == 0 ? 3 : 2);
+  spo_tc_forward_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, a);
+  SPO_CUDA_TRY(cudaGetLastError());
+  return SPO_OK;
+}
+
+// Returns SPO_OK when the tensor-core path ran, 1 when it does not apply (caller falls back
+// to the FFMA tile kernel), negative on error.
+int spo_tc_forward_launch(const spo_dims* d, const float* params, const float* obs, const float* old_mean,
+                          const float* old_log_std, float* mean_out, int64_t count, int mode, int reduce, float target_kl,
+                          spo_update_ctrl* ctrl, cudaStream_t stream) {
+  const int D = d->obs_dim;
+  if ((D & 3) != 0 || D > 64 || count < 8 * TC_ROWS) return 1;          // TMA needs 16-byte row pitch; K padded to 64
+  if ((reinterpret_cast<uintptr_t>(obs) & 15) != 0) return 1;
+  if (!tc_path_enabled()) return 1;
+  CUtensorMap map;
+  if (encode_obs_map(&map, obs, count, D)) return 1;
+  TcArgs a{};
+  a.params = params; a.old_mean = old_mean; a.old_log_std = old_log_std; a.mean_out = mean_out; a.count = count;
+  a.D = D; a.A = d->act_dim; a.mode = mode; a.reduce = reduce; a.target_kl = target_kl; a.ctrl = ctrl;
+  int rc = tc_set_smem_attr();
+  if (rc) return rc;
   const int64_t n_tiles = (count + TC_ROWS - 1) / TC_ROWS;
   const int grid = static_cast<int>(n_tiles < 148 ? n_tiles : 148);
-  spo_tc_forward_kernel<<<grid, TC_THREADS, smem, stream>>>(map, a);
+  spo_tc_forward_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, a);
   SPO_CUDA_TRY(cudaGetLastError());
   return SPO_OK;
 }

@@ -460,6 +460,31 @@ int spo_linesearch_eval(const spo_dims* d, const float* params, const float* obs
   return launch_trust<MODE_EVAL>(a, st);
 }
 
+// Data-parallel ranks cannot use the monolithic solver below: every Fisher-vector product has to be averaged across the
+// ranks before the step that consumes it (exchange 3').  The same two vector kernels, one call each:
+//   spo_cg_begin   x = 0, r = p = b, rdotr = r.r                (work: r | p | z | - | scalars, like spo_conjugate_gradient)
+//   (host)         spo_fvp(p = work + P  ->  z = work + 2P), all-reduce z, ...
+//   spo_cg_update  one iteration of cpo.py:92-105 with the z it finds in work + 2P
+int spo_cg_begin(const spo_dims* d, const float* b, float* x, float* work, void* stream) {
+  int rc = spo_check_dims(d);
+  if (rc) return rc;
+  SPO_REQUIRE(b && x && work, SPO_ERR_INVALID_ARG, "spo_cg_begin: null argument");
+  const int P = spo_net_off(d->obs_dim, d->act_dim, 0).count;
+  spo_cg_init_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(b, x, work, work + P, work + 4 * P, P);
+  SPO_CUDA_TRY(cudaGetLastError());
+  return SPO_OK;
+}
+
+int spo_cg_update(const spo_dims* d, float* x, float* work, float residual_tol, float eps, void* stream) {
+  int rc = spo_check_dims(d);
+  if (rc) return rc;
+  SPO_REQUIRE(x && work, SPO_ERR_INVALID_ARG, "spo_cg_update: null argument");
+  const int P = spo_net_off(d->obs_dim, d->act_dim, 0).count;
+  spo_cg_step_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(x, work, work + P, work + 2 * P, work + 4 * P, P, residual_tol, eps);
+  SPO_CUDA_TRY(cudaGetLastError());
+  return SPO_OK;
+}
+
 int spo_conjugate_gradient(const spo_dims* d, const float* params, const float* obs, int64_t count,
                            const float* b, int iters, float damping, float residual_tol, float eps,
                            float* x, float* work, void* stream) {

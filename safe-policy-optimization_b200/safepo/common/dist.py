@@ -43,6 +43,13 @@ class DataParallel:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
+    def all_reduce_mean(self, t):
+        """In-place mean over the ranks (equal shard sizes: the mean of the per-rank means is the global mean).
+        Every rank receives bit-identical values, so replicated follow-up arithmetic stays in lock-step."""
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        t.div_(self.world)
+        return t
+
     def broadcast(self, t, src=0):
         dist.broadcast(t, src=src, group=self.group)
         return t

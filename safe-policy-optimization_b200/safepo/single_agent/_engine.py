@@ -385,8 +385,10 @@ class CriticRegression:
     gradients enter the norm.  ``stale_actor_grad_sumsq`` stays as an explicit knob (default 0) for a
     caller whose actor does hold a gradient at this point."""
 
-    def __init__(self, policy, cfg, host_rng, device, lr=1e-3):
-        self.policy, self.cfg, self.host_rng, self.device = policy, cfg, host_rng, device
+    def __init__(self, policy, cfg, host_rng, device, lr=1e-3, dp=None):
+        self.policy, self.cfg, self.host_rng, self.device, self.dp = policy, cfg, host_rng, device, dp
+        if dp is not None and dp._peer is None:
+            dp.setup_peer_buffers(policy.dims, device)
         self.adam = AdamState(policy)
         self.ctrl = make_ctrl(device)
         self.hp = L.HParams(0.0, lr, lr, 0.9, 0.999, 1e-8, cfg["max_grad_norm"],
@@ -407,9 +409,17 @@ class CriticRegression:
                 perm = reference_order(S).to(self.device)
             else:
                 perm = torch.randperm(S, device=self.device)
-            L.check(lib.spo_pg_update(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(self.adam.m), L.ptr(self.adam.v),
-                                      L.ptr(self.adam.t), C.byref(batch), L.ptr(perm), perm.numel(), cfg["batch_size"],
-                                      L.LOSS_CRITIC_ONLY, C.byref(self.hp), L.ptr(self.ctrl), L.stream()), "spo_pg_update")
+            if self.dp is None:
+                L.check(lib.spo_pg_update(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(self.adam.m), L.ptr(self.adam.v),
+                                          L.ptr(self.adam.t), C.byref(batch), L.ptr(perm), perm.numel(), cfg["batch_size"],
+                                          L.LOSS_CRITIC_ONLY, C.byref(self.hp), L.ptr(self.ctrl), L.stream()), "spo_pg_update")
+            else:       # per-rank batch, critic gradients summed inside the kernel over NVLink like the policy-gradient trainers
+                comm = self.dp.comm_struct()
+                L.check(lib.spo_pg_update_dp(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(self.adam.m), L.ptr(self.adam.v),
+                                             L.ptr(self.adam.t), C.byref(batch), L.ptr(perm), perm.numel(), cfg["batch_size"],
+                                             L.LOSS_CRITIC_ONLY, C.byref(self.hp), L.ptr(self.ctrl), C.byref(comm), L.stream()),
+                        "spo_pg_update_dp")
+                self.dp.advance((perm.numel() + cfg["batch_size"] - 1) // cfg["batch_size"])
         c = read_ctrl(self.ctrl)
         steps = max(int(c["steps"]), 1)
         return {"loss_r": c["loss_sum"][0] / steps, "loss_c": c["loss_sum"][1] / steps, "steps": int(c["steps"])}
@@ -422,8 +432,13 @@ class TrustRegionUpdate:
 
     CG_ITERS, SEARCH_STEPS, STEP_FRACTION, DAMPING = 15, 15, 0.8, 0.1
 
-    def __init__(self, policy, cfg, device, logger=None):
-        self.policy, self.cfg, self.device, self.logger = policy, cfg, device, logger
+    def __init__(self, policy, cfg, device, logger=None, dp=None):
+        """``dp``: safepo.common.dist.DataParallel -- ranks hold disjoint env shards and identical weights; the flat
+        gradients g / b, every Fisher-vector product and the line-search means are averaged over the ranks (SURVEY 8e
+        exchange 3'), everything derived from them (CG vectors, the case analysis, the accepted step) is then replicated."""
+        self.policy, self.cfg, self.device, self.logger, self.dp = policy, cfg, device, logger, dp
+        if dp is not None:
+            dp.broadcast(policy.flat)
         P = policy.n_actor
         f32 = dict(dtype=torch.float32, device=device)
         self.g, self.b, self.x, self.p, self.Fx = (torch.zeros(P, **f32) for _ in range(5))
@@ -444,11 +459,26 @@ class TrustRegionUpdate:
         L.check(L.lib().spo_surrogate_grad(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(data["obs"]), L.ptr(data["act"]),
                                            L.ptr(data["log_prob"]), L.ptr(adv), S, L.ptr(self.loss), L.ptr(out), L.stream()),
                 "spo_surrogate_grad")
+        if self.dp is not None:
+            self.dp.all_reduce_mean(out)
+            self.dp.all_reduce_mean(self.loss)
         return self.loss.clone()
 
     def _cg(self, data, rhs, out):
         pol = self.policy
         S = data["obs"].shape[0]
+        if self.dp is not None:
+            # the solver split at the FVP: p = work[P:2P] -> z = work[2P:3P], averaged over the ranks, then one CG step
+            lib, P = L.lib(), pol.n_actor
+            L.check(lib.spo_cg_begin(C.byref(pol.dims), L.ptr(rhs), L.ptr(out), L.ptr(self.work), L.stream()), "spo_cg_begin")
+            p_vec, z_vec = self.work[P:2 * P], self.work[2 * P:3 * P]
+            for _ in range(self.CG_ITERS):
+                L.check(lib.spo_fvp(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(data["obs"]), S, L.ptr(p_vec), self.DAMPING,
+                                    L.ptr(z_vec), L.stream()), "spo_fvp")
+                self.dp.all_reduce_mean(z_vec)
+                L.check(lib.spo_cg_update(C.byref(pol.dims), L.ptr(out), L.ptr(self.work), 1e-10, 1e-6, L.stream()), "spo_cg_update")
+            L.LAUNCHES["n"] += self.CG_ITERS + 1
+            return
         L.check(L.lib().spo_conjugate_gradient(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(data["obs"]), S, L.ptr(rhs),
                                                self.CG_ITERS, self.DAMPING, 1e-10, 1e-6, L.ptr(out), L.ptr(self.work),
                                                L.stream()), "spo_conjugate_gradient")
@@ -459,6 +489,8 @@ class TrustRegionUpdate:
         S = data["obs"].shape[0]
         L.check(L.lib().spo_fvp(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(data["obs"]), S, L.ptr(v), self.DAMPING, L.ptr(out),
                                 L.stream()), "spo_fvp")
+        if self.dp is not None:
+            self.dp.all_reduce_mean(out)
 
     def _eval(self, data, adv_a, adv_b):
         pol = self.policy
@@ -466,6 +498,8 @@ class TrustRegionUpdate:
         L.check(L.lib().spo_linesearch_eval(C.byref(pol.dims), L.ptr(pol.flat), L.ptr(data["obs"]), L.ptr(data["act"]),
                                             L.ptr(data["log_prob"]), L.ptr(adv_a), L.ptr(adv_b), L.ptr(self.old_mean),
                                             L.ptr(self.old_log_std), S, L.ptr(self.out3), L.stream()), "spo_linesearch_eval")
+        if self.dp is not None:
+            self.dp.all_reduce_mean(self.out3)
         return self.out3.cpu()
 
     def _old_dist(self, data):
@@ -641,8 +675,10 @@ class TrustRegionUpdate:
                 "Loss/Loss_actor": -float(sc[1]), "Train/KL": float(o[2])}
 
 
-def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False):
-    """main() of cpo.py / trpo_lag.py and their siblings trpo.py / natural_pg.py / rcpo.py."""
+def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False, dp=None):
+    """main() of cpo.py / trpo_lag.py and their siblings trpo.py / natural_pg.py / rcpo.py.
+    ``dp``: a safepo.common.dist.DataParallel when launched one process per GPU (envs sharded; g, b, every FVP result and
+    the line-search means averaged over the ranks; the critics' gradients summed inside the update kernel)."""
     seed_all(args.seed)
     if args.device != "cuda":
         raise L.SpoError("this build has no CPU path: run with --device cuda")
@@ -669,23 +705,27 @@ def run_trust_region(args, config, algo, env=None, max_epochs=None, quiet=False)
     host_rng = getattr(args, "rng", "device") == "host"
     roll_cls = DeviceTapeRollout if getattr(args, "resident_env", False) else Rollout
     roll = roll_cls(env, policy, buffer, logger, args, device)
-    trust = TrustRegionUpdate(policy, config, device, logger=None if quiet else logger)
-    critics = CriticRegression(policy, config, host_rng, device)
+    trust = TrustRegionUpdate(policy, config, device, logger=None if quiet else logger, dp=dp)
+    critics = CriticRegression(policy, config, host_rng, device, dp=dp)
+    red = None if dp is None else dp.all_reduce_sum
+
+    def jc():
+        return logger.get_stats("Metrics/EpCost") if dp is None else dp.mean_episode_cost(logger, device=device)
     timings = []
     n_epochs = epochs if max_epochs is None else min(epochs, max_epochs)
     for epoch in range(n_epochs):
         t_roll = roll.run(T)
         t1 = time.time()
         if algo in ("trpo_lag", "rcpo"):
-            lagrange.update_lagrange_multiplier(logger.get_stats("Metrics/EpCost"))
-            data = buffer.get(lagrange.lagrangian_multiplier)
+            lagrange.update_lagrange_multiplier(jc())
+            data = buffer.get(lagrange.lagrangian_multiplier, all_reduce=red)
             res = trust.run_trpo(data, data["adv"]) if algo == "trpo_lag" else trust.run_npg(data, data["adv"])
         elif algo in ("trpo", "natural_pg"):       # trpo.py:361: advantage = adv_r
-            data = buffer.get(0.0)
+            data = buffer.get(0.0, all_reduce=red)
             res = trust.run_trpo(data, data["adv"]) if algo == "trpo" else trust.run_npg(data, data["adv"])
         else:
-            data = buffer.get(0.0)
-            ep_costs = logger.get_stats("Metrics/EpCost") - args.cost_limit
+            data = buffer.get(0.0, all_reduce=red)
+            ep_costs = jc() - args.cost_limit
             res = trust.run_cpo(data, ep_costs, variant="pcpo" if algo == "pcpo" else "cpo")
         cres = critics.run(data)
         buffer.reset_segments()

@@ -42,6 +42,10 @@ def _worker(rank, world, port, out):
     w = torch.full((4,), float(rank + 1))
     dp.broadcast(w)
     res["bcast"] = w.tolist()
+    # the trust-region exchange (flat gradient / FVP result / line-search means): mean over the ranks, identical everywhere
+    v = torch.tensor([1.0, 2.0, 3.0]) * (rank + 1)
+    dp.all_reduce_mean(v)
+    res["mean"] = v.tolist()
     dp.advance(7)
     res["seq"] = dp.seq
     out[rank] = res
@@ -59,4 +63,5 @@ def test_dp_host_logic_gloo_world2():
         assert np.isnan(out[r]["jc_nan"])
         assert out[r]["stats"] == [3.0, 4.0, 6.0, 200.0]
         assert out[r]["bcast"] == [1.0] * 4
+        assert out[r]["mean"] == [1.5, 3.0, 4.5]
         assert out[r]["seq"] == 7

@@ -163,6 +163,43 @@ def test_fused_store_and_segment_rule_bit_exact():
         pol.step(torch.zeros(N, D, device=dev), store=(buf.struct, T))
 
 
+@pytest.mark.parametrize("N,D,A", [(1024, 60, 2), (300, 60, 2), (128, 28, 8), (129, 64, 1)])
+def test_tensor_core_rollout_step_and_store(N, D, A):
+    """The rollout step of batches >= 128 rows with obs_dim % 4 == 0 runs on the TMA + tcgen05 kernel (csrc/spo_tc_forward.cu,
+    mode 3: grid (row tiles, nets), sample / log-prob / slot write in the epilogue): outputs against the oracle at 1e-5,
+    the slot written by the kernel bit-identical to what it returned, observation rows copied bit-exactly,
+    bootstrap values (critics only) equal to the step's values."""
+    dev = _cuda()
+    from safepo.common.buffer import VectorizedOnPolicyBuffer
+    from safepo.common.model import ActorVCritic
+    torch.manual_seed(N + D)
+    T = 3
+    pol = ActorVCritic(D, A).to(dev)
+    with torch.no_grad():
+        pol.actor.log_std.copy_(torch.linspace(-0.5, 0.3, A))
+    opol = oracle_policy(policy_state(pol), D, A)
+    buf = VectorizedOnPolicyBuffer(Sp(D), Sp(A), size=T, device=dev, num_envs=N)
+    g = torch.Generator().manual_seed(9)
+    for t in range(T):
+        obs, eps = torch.randn(N, D, generator=g), torch.randn(N, A, generator=g)
+        act, logp, vr, vc = pol.step(obs.to(dev), eps=eps.to(dev), store=(buf.struct, t))
+        with torch.no_grad():
+            oa, ol, orr, oc = O.policy_step(opol, obs, eps=eps)
+        for name, got, want in (("act", act, oa), ("logp", logp, ol), ("v_r", vr, orr), ("v_c", vc, oc)):
+            ok, ea, er = close(got, want, atol=2e-6)
+            assert ok, (name, N, D, A, t, ea, er)
+        torch.cuda.synchronize()
+        assert torch.equal(buf.data["obs"][:, t].cpu(), obs)
+        assert torch.equal(buf.data["act"][:, t], act) and torch.equal(buf.data["log_prob"][:, t], logp)
+        assert torch.equal(buf.data["value_r"][:, t], vr) and torch.equal(buf.data["value_c"][:, t], vc)
+        vr2, vc2 = pol.values(obs.to(dev))
+        assert torch.equal(vr2, vr) and torch.equal(vc2, vc)
+        dact, dlogp, _, _ = pol.step(obs.to(dev), deterministic=True)
+        with torch.no_grad():
+            da, dl, _, _ = O.policy_step(opol, obs, deterministic=True)
+        assert close(dact, da, atol=2e-6)[0] and close(dlogp, dl, atol=2e-6)[0]
+
+
 # ---------------------------------------------------------------------------------------
 # G1 / G3
 # ---------------------------------------------------------------------------------------
