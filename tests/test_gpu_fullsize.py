@@ -54,7 +54,8 @@ def load_oracle_state(pol, adam, opol, opt):
 
 
 def oracle_flat(opol):
-    return torch.cat([p.detach().reshape(-1) for n in O.NET_ORDER for p in opol.params(n)])
+    # packed order of libspo (include/spo.h): actor | reward critic | cost critic -- NOT O.NET_ORDER (the RNG construction order)
+    return torch.cat([p.detach().reshape(-1) for n in ("actor", "reward_critic", "cost_critic") for p in opol.params(n)])
 
 
 def test_update_full_config2_pass_vs_oracle():
@@ -81,6 +82,9 @@ def test_update_full_config2_pass_vs_oracle():
     data_cpu = {"obs": obs, "act": act, "log_prob": logp, "target_value_r": torch.randn(S, generator=g),
                 "target_value_c": torch.randn(S, generator=g).abs(), "adv": torch.randn(S, generator=g)}
     perm = torch.randperm(S, generator=g)
+    # loss_pi = -mean(min(ratio * adv, clip(ratio) * adv)) is a mean of SIGNED terms of magnitude ~|adv| that nearly cancel
+    # (|loss_pi| ~ 0.05 here): the 1e-5 bar applies relative to the mean magnitude of its terms, not to the cancelled sum
+    pi_scale = float(data_cpu["adv"].abs().mean())
     cfg = dict(hidden_sizes=[64, 64], gamma=0.99, target_kl=1e9, batch_size=B, learning_iters=1, max_grad_norm=40.0)
     upd = PolicyGradientUpdate(pol, cfg, L.LOSS_PPO_CLIP, epochs=10 ** 9, host_rng=False, device=dev)
     upd_free = PolicyGradientUpdate(free, cfg, L.LOSS_PPO_CLIP, epochs=10 ** 9, host_rng=False, device=dev)
@@ -100,7 +104,8 @@ def test_update_full_config2_pass_vs_oracle():
             losses.append(O.minibatch_step(opol, opt, {k: v[ii] for k, v in data_cpu.items()}, "ppo"))
         want = torch.tensor(losses, dtype=torch.float64).mean(0)
         got = torch.tensor([res["loss_r"], res["loss_c"], res["loss_pi"]], dtype=torch.float64)
-        loss_rel.append(((got - want).abs() / (want.abs() + 1e-6)).max().item())
+        den = torch.maximum(want.abs(), torch.tensor([0.0, 0.0, pi_scale], dtype=torch.float64))
+        loss_rel.append(((got - want).abs() / den).max().item())
         of = oracle_flat(opol)
         err = (pol.flat.detach().cpu() - of).abs()
         w_abs.append(err.max().item())
@@ -113,8 +118,10 @@ def test_update_full_config2_pass_vs_oracle():
           f"\n  weights after {CHUNK} steps: max |dtheta| median {np.median(w_abs):.2e}  max {w_abs.max():.2e};  ||dtheta||/||theta|| max {w_rel.max():.2e}"
           f"\nfree-running device chain vs oracle: max |dtheta| after 1000 / 4000 / 16000 steps: "
           f"{free_abs[9]:.2e} / {free_abs[39]:.2e} / {free_abs[-1]:.2e}")
-    assert loss_rel.max() < 2e-5, loss_rel.max()                # means over 100 steps of losses whose weights drift at the 1e-5 level
-    assert w_abs.max() < 1.5e-4 and w_rel.max() < 2e-5, (w_abs.max(), w_rel.max())   # 100 Adam steps of lr 3e-4 (each bounded by 3e-4)
+    # measured on B200 (profiles/r02_fullsize_tests.txt): losses median 3.5e-7 / max < 1e-5 once loss_pi is scaled by its terms;
+    # weights median 4.5e-8, max 2.1e-5 (a handful of near-zero-gradient coordinates where Adam's m / sqrt(v) flips), norm-wise 1.9e-6
+    assert loss_rel.max() < 1e-5, loss_rel.max()
+    assert w_abs.max() < 6e-5 and w_rel.max() < 1e-5 and np.median(w_abs) < 1e-6, (w_abs.max(), w_rel.max(), np.median(w_abs))
     assert free_abs[-1] < 0.05, free_abs[-1]                   # sanity only: the chains stay in the same basin
 
 
@@ -139,6 +146,7 @@ def test_update_per_step_error_histogram_config2_shape():
     data_cpu = {"obs": obs, "act": act, "log_prob": logp, "target_value_r": torch.randn(S, generator=g),
                 "target_value_c": torch.randn(S, generator=g).abs(), "adv": torch.randn(S, generator=g)}
     perm = torch.randperm(S, generator=g)
+    pi_scale = float(data_cpu["adv"].abs().mean())     # loss_pi relative to the mean magnitude of its signed terms (see the test above)
     cfg = dict(hidden_sizes=[64, 64], gamma=0.99, target_kl=1e9, batch_size=B, learning_iters=1, max_grad_norm=40.0)
     upd = PolicyGradientUpdate(pol, cfg, L.LOSS_PPO_CLIP, epochs=10 ** 9, host_rng=False, device=dev)
     data = {k: v.to(dev).contiguous() for k, v in data_cpu.items()}
@@ -150,7 +158,7 @@ def test_update_per_step_error_histogram_config2_shape():
         res = upd.run(data, perms=[idx], refresh_old=(s == 0))
         want = O.minibatch_step(opol, opt, {k: v[idx] for k, v in data_cpu.items()}, "ppo")
         got = (res["loss_r"], res["loss_c"], res["loss_pi"])
-        rel.append([abs(a - b) / (abs(b) + 1e-6) for a, b in zip(got, want)])
+        rel.append([abs(a - b) / max(abs(b), sc) for a, b, sc in zip(got, want, (0.0, 0.0, pi_scale))])
         wstep.append((pol.flat.detach().cpu() - oracle_flat(opol)).abs().max().item())
         load_oracle_state(pol, upd.adam, opol, opt)
     rel = np.array(rel)
@@ -158,9 +166,9 @@ def test_update_per_step_error_histogram_config2_shape():
     print(f"\nper-step loss error at identical weights ({STEPS} steps, batch 64, obs 60): rel error (r, c, pi)"
           f"\n  median {np.median(rel, 0)}  p99 {np.percentile(rel, 99, 0)}  max {rel.max(0)}"
           f"\n  one Adam step: max |dtheta| vs oracle median {np.median(wstep):.2e} max {wstep.max():.2e} (lr 3e-4)")
-    assert rel[:, :2].max() < 1e-5, rel.max(0)        # critic losses: O(1) sums of squares
-    assert rel[:, 2].max() < 1e-5 or np.median(rel[:, 2]) < 1e-5, rel.max(0)   # the policy loss is a mean of signed terms near 0
-    assert wstep.max() < 2e-5, wstep.max()
+    # measured on B200: critic losses max 3.1e-7 / 4.2e-7, one Adam step max |dtheta| 4.5e-8
+    assert rel.max() < 1e-5, rel.max(0)
+    assert wstep.max() < 1e-6, wstep.max()
 
 
 @pytest.mark.parametrize("extra", [0.0, 900.0])
@@ -250,7 +258,7 @@ def test_trust_region_pieces_at_config3_size():
     want_loss = O.surrogate_loss(opol, obs, act, logp, data_cpu["adv_r"])
     want_loss.backward()
     want_g = O.flat_grads(opol)
-    assert abs(float(loss) - float(want_loss)) <= 1e-5 * abs(float(want_loss)) + 1e-7
+    assert abs(float(loss) - float(want_loss.detach())) <= 1e-5 * abs(float(want_loss.detach())) + 1e-7
     eg = float((tr.g.cpu() - want_g).norm() / want_g.norm())
     # FVP
     tr._old_dist(data)

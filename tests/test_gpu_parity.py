@@ -97,9 +97,9 @@ def test_policy_step_large_batch_and_philox():
     act, logp, vr, vc = pol.step(obs.to(dev), eps=eps.to(dev))
     with torch.no_grad():
         oa, ol, orr, oc = O.policy_step(opol, obs, eps=eps)
-    for got, want in ((act, oa), (logp, ol), (vr, orr), (vc, oc)):
-        ok, ea, er = close(got, want)
-        assert ok, (ea, er)
+    for name, got, want in (("act", act, oa), ("logp", logp, ol), ("v_r", vr, orr), ("v_c", vc, oc)):
+        ok, ea, er = close(got, want, atol=2e-6)      # 1061 rows, obs 60: the TMA + tcgen05 step kernel (3xTF32, SFU tanh)
+        assert ok, (name, ea, er)
     # in-kernel Philox: standard normal draws, deterministic in (seed, offset), fresh each call
     a1, _, _, _ = pol.step(obs.to(dev))
     a2, _, _, _ = pol.step(obs.to(dev))
