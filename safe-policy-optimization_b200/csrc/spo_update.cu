@@ -127,6 +127,29 @@ __device__ __forceinline__ float2 ld_dsmem_f2(uint32_t addr) {
   asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
   return v;
 }
+// mbarrier + bulk-copy engine: the two 12 KB activation exchanges of a step (h1 all-gather, dh1 reduce-scatter) are PUSHED
+// as 4 KB cp.async.bulk copies shared -> peer shared that complete_tx on the receiver's mbarrier: 695 cycles from issue to
+// "all three slices landed" measured (tools/dsmem_probe.cu BULK) against ~1000 for 3 x float4 ld.shared::cluster per
+// thread plus the barrier in front of them plus the local stores behind them; and the copy engine, not the LSU, moves the bytes.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_push(uint32_t remote_dst, const void* local_src, uint32_t bytes, uint32_t remote_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(remote_dst), "r"(smem_u32(local_src)), "r"(bytes), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(smem)), "l"(gmem));
 }
@@ -135,12 +158,6 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // cross-GPU words: {value, seq} as one 8-byte access (single-copy atomic), system scope, no caching games
 __device__ __forceinline__ void st_ll(float2* p, float v, unsigned seq) {
   asm volatile("st.relaxed.sys.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(seq) : "memory");
-}
-__device__ __forceinline__ bool ld_ll(const float2* p, unsigned seq, float& v) {
-  unsigned a, b;
-  asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "l"(p) : "memory");
-  v = __uint_as_float(a);
-  return b == seq;
 }
 
 // One Adam step on a scalar in torch's _multi_tensor_adam op order:
@@ -259,9 +276,78 @@ __device__ __forceinline__ void warp_gemm_kk(float (&acc)[1][4], const float* __
   for (int e = 0; e < 4; ++e) acc[0][e] = (c_lh[e] + c_hl[e]) + c_hh[e];
 }
 
+// h1 lives as four slice blocks [quarter][64 rows][16 columns] (each 4 KB contiguous: one bulk copy per peer) with the
+// column index XOR-ed by 8 on rows whose bit 1 is set.  Both access patterns of the mma fragments are then conflict-free:
+// k-pair 64-bit loads of the layer-2 A operand (half-warp rows g = 0..3: banks 16(g&1) + 8((g>>1)^x) + 2t, +1) and the 32-bit
+// loads of the dW2 B operand (rows k0 + t: banks 16(t&1) + 8((t>>1)^x) + g).
+constexpr int H1Q = SPO_ROWS * SL;   // floats per slice block
+// element (row r, unit c): h1[(c >> 4) * H1Q + r * SL + ((c & 15) ^ (((r >> 1) & 1) << 3))]
+
+// layer 2: acc[16 x 8 tile at (m0, n0)] = h1[m0.., :] * W2slice[n0.., :]^T   (A from the swizzled blocks, B = w2s [n][k], k-pair mapping)
+__device__ __forceinline__ void warp_gemm_l2(float (&acc)[1][4], const float* __restrict__ h1, const float* __restrict__ B, int ldb, int m0, int n0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int r0 = m0 + g, sw = ((r0 >> 1) & 1) << 3;          // row r0 + 8 has the same swizzle
+  const float* b_ptr = B + (n0 + g) * ldb + 2 * t;
+  float c_lh[4] = {0.f, 0.f, 0.f, 0.f}, c_hl[4] = {0.f, 0.f, 0.f, 0.f}, c_hh[4] = {0.f, 0.f, 0.f, 0.f};
+  float2 a0[8], a1[8], bb[8];
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const float* blk = h1 + (ks >> 1) * H1Q + ((((ks & 1) << 3) + 2 * t) ^ sw);
+    a0[ks] = *reinterpret_cast<const float2*>(blk + r0 * SL);
+    a1[ks] = *reinterpret_cast<const float2*>(blk + (r0 + 8) * SL);
+    bb[ks] = *reinterpret_cast<const float2*>(b_ptr + ks * 8);
+  }
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    uint32_t ah[4], al[4], bh[2], bl[2];
+    spo_split_tf32(a0[ks].x, ah[0], al[0]);
+    spo_split_tf32(a1[ks].x, ah[1], al[1]);
+    spo_split_tf32(a0[ks].y, ah[2], al[2]);
+    spo_split_tf32(a1[ks].y, ah[3], al[3]);
+    spo_split_tf32(bb[ks].x, bh[0], bl[0]);
+    spo_split_tf32(bb[ks].y, bh[1], bl[1]);
+    spo_mma_tf32(c_lh, al, bh);
+    spo_mma_tf32(c_hl, ah, bl);
+    spo_mma_tf32(c_hh, ah, bh);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) acc[0][e] = (c_lh[e] + c_hl[e]) + c_hh[e];
+}
+
+// dW2 slice: acc[16 (own units j) x 8 columns at n0] += dz2s^T * h1   (A(m = j, k = r) = dz2s[r][j]; B(k = r, n) = h1[r][n] swizzled)
+__device__ __forceinline__ void warp_gemm_dw2(float (&acc)[1][4], const float* __restrict__ dz, int ldz, const float* __restrict__ h1, int n0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const float* a_ptr = dz + t * ldz + g;
+  const int n = n0 + g, sw = ((t >> 1) & 1) << 3;            // rows 8ks + t and 8ks + t + 4 share the swizzle of t
+  const float* b_ptr = h1 + (n >> 4) * H1Q + t * SL + ((n & 15) ^ sw);
+  float c_lh[4] = {0.f, 0.f, 0.f, 0.f}, c_hl[4] = {0.f, 0.f, 0.f, 0.f}, c_hh[4] = {0.f, 0.f, 0.f, 0.f};
+  float af[8][4], bf[8][2];
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const float* p = a_ptr + ks * 8 * ldz;
+    af[ks][0] = p[0]; af[ks][1] = p[8]; af[ks][2] = p[4 * ldz]; af[ks][3] = p[4 * ldz + 8];
+    const float* pb = b_ptr + ks * 8 * SL;
+    bf[ks][0] = pb[0]; bf[ks][1] = pb[4 * SL];
+  }
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) spo_split_tf32(af[ks][i], ah[i], al[i]);
+    spo_split_tf32(bf[ks][0], bh[0], bl[0]);
+    spo_split_tf32(bf[ks][1], bh[1], bl[1]);
+    spo_mma_tf32(c_lh, al, bh);
+    spo_mma_tf32(c_hl, ah, bl);
+    spo_mma_tf32(c_hh, ah, bh);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) acc[0][e] += (c_lh[e] + c_hl[e]) + c_hh[e];
+}
+
 template <int NT1>
 __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ __align__(8) uint64_t bar_h1, bar_dh;   // complete_tx targets of the two pushed exchanges
   __shared__ int comm_dead;   // a peer GPU never showed up: stop waiting (ctrl->stop = 2 tells the host)
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
@@ -292,14 +378,15 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   float* gsmall = p; p += SPN;                    // their gradients
   float* x = p;   p += SPO_ROWS * ldx;            // observation tile (the next one is staged in registers)
   float* aux = p; p += SPO_ROWS * AUXW;           // per-row side data
-  float* h1 = p;  p += SPO_ROWS * LDA;            // all 64 units: own slice + the three received ones
+  float* h1 = p;  p += NQ * H1Q;                  // all 64 units as four swizzled slice blocks: own + the three pushed by the peers
   float* h2s = p; p += SPO_ROWS * LDS;            // own slice; becomes dz1 slice during backward
   float* dz2s = p; p += SPO_ROWS * LDS;
   float* ypo = p; p += SPO_ROWS * SPO_MAX_ACT;    // own partial of the output layer (read by the three peers)
   float* y = p;   p += SPO_ROWS * SPO_MAX_ACT;
   float* dy = p;  p += SPO_ROWS * SPO_MAX_ACT;
   float* dls = p; p += SPO_ROWS * SPO_MAX_ACT;    // per-row d loss / d log_std
-  float* dh1f = p; p += SPO_ROWS * LDA;           // own partial of dh1, all 64 columns (each peer reads its quarter)
+  float* dh1b = p; p += NQ * H1Q;                 // own partial of dh1 as [destination quarter][64][16]: block d is pushed to CTA d
+  float* dh1in = p; p += NQ * H1Q;                // [source quarter][64][16]: the partials the three peers pushed for the own columns
   float* red = p; p += 64;                        // block-reduction scratch
   float* xchg = p; p += 4;                        // [parity]{sum g^2, sum theta^2} of this CTA (read by all peers)
   float* dz1s = h2s;
@@ -309,7 +396,13 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   const int64_t n_steps = (a.perm_len + a.batch - 1) / a.batch;
   const int64_t n_tiles = n_steps * tps;
 
-  if (tid == 0) comm_dead = 0;
+  if (tid == 0) {
+    comm_dead = 0;
+    mbar_init(&bar_h1, 1);
+    mbar_init(&bar_dh, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (active) { mbar_expect_tx(&bar_h1, (NQ - 1) * H1Q * 4); mbar_expect_tx(&bar_dh, (NQ - 1) * H1Q * 4); }
+  }
 
   // ---- small-parameter entry of this thread ----
   bool sp_valid = false, sp_counted = false;
@@ -517,13 +610,10 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   }
 
   // shared::cluster addresses of the buffers this CTA pulls from: the four CTAs of its net, all CTAs for the norm
-  uint32_t r_h1[NQ], r_yp[NQ], r_dh[NQ];
+  uint32_t r_yp[NQ];
 #pragma unroll
-  for (int d = 0; d < NQ; ++d) {
-    r_h1[d] = mapa(smem_u32(h1), grp0 + d);
-    r_yp[d] = mapa(smem_u32(ypo), grp0 + d);
-    r_dh[d] = mapa(smem_u32(dh1f), grp0 + d);
-  }
+  for (int d = 0; d < NQ; ++d) r_yp[d] = mapa(smem_u32(ypo), grp0 + d);
+  uint32_t ph_x = 0;     // phase parity of bar_h1 / bar_dh (one phase per tile)
   const uint32_t r_xchg = mapa(smem_u32(xchg), lane < NCTA ? lane : 0);
 
   // gradient accumulators = accumulator fragments of the dW products (persist across the tiles of a step)
@@ -578,34 +668,58 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         for (int i = 0; i < n; ++i) st_ll(dst + (w0 + i) * UT + tid, vals[i], seq);
       }
     };
-    // rank-ordered sum of `n` values with the words received from every peer GPU, scaled by 1/world
-    auto dp_sum = [&](float* vals, auto n_c, int w0) {
-      constexpr int n = decltype(n_c)::value;
+    // rank-ordered sum of ALL of this thread's gradient words (4 of dW2, 4 per block of dW1, one small entry for
+    // tid < SPN) with the words received from every peer GPU, scaled by 1/world.  The words of a peer are requested
+    // together and tested afterwards: a sys-scope load is an L2 round trip (~0.35 us), nine of them one after the other
+    // were most of the +3.9 us per step of the first version at 2 GPUs.
+    auto dp_sum_all = [&](float (&g2)[4], float (&g1)[NT1][4], float& gs) {
+      constexpr int NW = 4 * (1 + NT1) + 1;
       const unsigned limit = a.comm.spin_limit ? a.comm.spin_limit : 400000000u;
-      float acc[n];
+      const unsigned need = (tid < SPN) ? ((1u << NW) - 1u) : ((1u << (NW - 1)) - 1u);
+      float acc[NW];
 #pragma unroll
-      for (int i = 0; i < n; ++i) acc[i] = 0.f;
+      for (int i = 0; i < NW; ++i) acc[i] = 0.f;
       for (int r = 0; r < world; ++r) {
         if (r == me) {
 #pragma unroll
-          for (int i = 0; i < n; ++i) acc[i] += vals[i];
+          for (int e = 0; e < 4; ++e) {
+            acc[e] += g2[e];
+#pragma unroll
+            for (int i = 0; i < NT1; ++i) acc[4 * (1 + i) + e] += g1[i][e];
+          }
+          acc[NW - 1] += gs;
           continue;
         }
-        const float2* src = reinterpret_cast<const float2*>(a.comm.grad_bufs[me]) + ((static_cast<size_t>(seq & 1u) * world + r) * NCTA + rank) * DPW;
+        const float2* src = reinterpret_cast<const float2*>(a.comm.grad_bufs[me]) + ((static_cast<size_t>(seq & 1u) * world + r) * NCTA + rank) * DPW + tid;
+        unsigned got = 0, polls = 0;
+        float v[NW];
 #pragma unroll
-        for (int i = 0; i < n; ++i) {
-          float v = 0.f;
-          unsigned polls = 0;
-          while (!ld_ll(src + (w0 + i) * UT + tid, seq, v)) {
-            if (*reinterpret_cast<volatile int*>(&comm_dead)) { v = 0.f; break; }
-            if (++polls > limit) { comm_dead = 1; atomicExch(&ctrl->stop, 2); v = 0.f; break; }
+        for (int i = 0; i < NW; ++i) v[i] = 0.f;
+        while (got != need) {
+          unsigned wa[NW], wb[NW];
+#pragma unroll
+          for (int i = 0; i < NW; ++i)
+            if (!((got >> i) & 1u) && ((need >> i) & 1u))
+              asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(wa[i]), "=r"(wb[i]) : "l"(src + i * UT) : "memory");
+#pragma unroll
+          for (int i = 0; i < NW; ++i)
+            if (!((got >> i) & 1u) && ((need >> i) & 1u) && wb[i] == seq) { v[i] = __uint_as_float(wa[i]); got |= 1u << i; }
+          if (got != need) {
+            if (*reinterpret_cast<volatile int*>(&comm_dead)) break;
+            if (++polls > limit) { comm_dead = 1; atomicExch(&ctrl->stop, 2); break; }
           }
-          acc[i] += v;
         }
+#pragma unroll
+        for (int i = 0; i < NW; ++i) acc[i] += v[i];
       }
       const float inv_w = __fdiv_rn(1.f, static_cast<float>(world));
 #pragma unroll
-      for (int i = 0; i < n; ++i) vals[i] = __fmul_rn(acc[i], inv_w);
+      for (int e = 0; e < 4; ++e) {
+        g2[e] = __fmul_rn(acc[e], inv_w);
+#pragma unroll
+        for (int i = 0; i < NT1; ++i) g1[i][e] = __fmul_rn(acc[4 * (1 + i) + e], inv_w);
+      }
+      gs = __fmul_rn(acc[NW - 1], inv_w);
     };
 
     store_next();      // tile qt: registers -> shared memory (every warp left tile qt-1 before the last barrier)
@@ -625,8 +739,10 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       float acc[1][4];
       warp_gemm_kk<8 * NT1>(acc, x, ldx, w1s, ldx, mt * 16, ntl * 8);
       const float2 bb = *reinterpret_cast<const float2*>(b1s + cA);
-      *reinterpret_cast<float2*>(h1 + rA * LDA + SL * q + cA) = make_float2(spo_tanh_fast(acc[0][0] + bb.x), spo_tanh_fast(acc[0][1] + bb.y));
-      *reinterpret_cast<float2*>(h1 + (rA + 8) * LDA + SL * q + cA) = make_float2(spo_tanh_fast(acc[0][2] + bb.x), spo_tanh_fast(acc[0][3] + bb.y));
+      const int cs = cA ^ (((rA >> 1) & 1) << 3);     // swizzled column inside the own slice block (rows rA and rA + 8 alike)
+      *reinterpret_cast<float2*>(h1 + q * H1Q + rA * SL + cs) = make_float2(spo_tanh_fast(acc[0][0] + bb.x), spo_tanh_fast(acc[0][1] + bb.y));
+      *reinterpret_cast<float2*>(h1 + q * H1Q + (rA + 8) * SL + cs) = make_float2(spo_tanh_fast(acc[0][2] + bb.x), spo_tanh_fast(acc[0][3] + bb.y));
+      fence_proxy_async();                            // the slice is read by the bulk-copy engine next
       if (tid == 0 && last_tile) {
         // Adam scalars of this step (fp64 like torch's Python floats); the barriers of the step publish them
         b1pow *= static_cast<double>(a.hp.beta1);
@@ -640,26 +756,18 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       }
     }
     PHASE_MARK(1);   // layer-1 product + epilogue
-    __syncthreads();
-    cluster_arrive();
-    cluster_wait();                                   // ---- barrier 1: every h1 slice of the cluster is in place
-    PHASE_MARK(2);
     float yv[SPO_MAX_ACT];                            // output-layer rows of this thread's row r4 (after the y exchange)
     if (active) {
-      // all-gather of h1: one float4 per peer, thread (row r4, chunk k4)
-      float4 v[NQ];
-#pragma unroll
-      for (int d = 0; d < NQ; ++d)
-        if (d != q) v[d] = ld_dsmem_f4(r_h1[d] + static_cast<uint32_t>((r4 * LDA + SL * d + 4 * k4) * 4));
-#pragma unroll
-      for (int d = 0; d < NQ; ++d)
-        if (d != q) *reinterpret_cast<float4*>(h1 + r4 * LDA + SL * d + 4 * k4) = v[d];
-      __syncthreads();
-      PHASE_MARK(3);   // h1 pull
+      __syncthreads();                                // own slice complete (and fenced towards the async proxy)
+      if (tid < NQ && tid != q)                       // all-gather of h1: the own 4 KB block goes to the three peers of the net
+        bulk_push(mapa(smem_u32(h1 + q * H1Q), grp0 + tid), h1 + q * H1Q, H1Q * 4, mapa(smem_u32(&bar_h1), grp0 + tid));
+      mbar_wait(&bar_h1, ph_x);                       // ... and theirs have landed here
+      if (tid == 0) mbar_expect_tx(&bar_h1, (NQ - 1) * H1Q * 4);
+      PHASE_MARK(3);   // h1 all-gather (pushed)
       // ---------------- forward, layer 2 + partial output layer ----------------
       {
         float acc[1][4];
-        warp_gemm_kk<8>(acc, h1, LDA, w2s, LDA, mt * 16, ntl * 8);
+        warp_gemm_l2(acc, h1, w2s, LDA, mt * 16, ntl * 8);
         const float2 bb = *reinterpret_cast<const float2*>(b2s + cA);
         *reinterpret_cast<float2*>(h2s + rA * LDS + cA) = make_float2(spo_tanh_fast(acc[0][0] + bb.x), spo_tanh_fast(acc[0][1] + bb.y));
         *reinterpret_cast<float2*>(h2s + (rA + 8) * LDS + cA) = make_float2(spo_tanh_fast(acc[0][2] + bb.x), spo_tanh_fast(acc[0][3] + bb.y));
@@ -871,34 +979,28 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       }
       __syncthreads();
       PHASE_MARK(7);   // small grads + dz2
-      // (c) dh1 partial [64 x 64] = dz2[:, slice] W2[slice, :] -> own buffer; each peer pulls its 16 columns
+      // (c) dh1 partial [64 x 64] = dz2[:, slice] W2[slice, :], stored by destination quarter; block d is pushed to CTA d
       {
         float acc[4][4];
         warp_gemm<4, 2, false>(acc, dz2s, LDS, 1, w2s, LDA, 1, mt * 16, (wid >> 2) * 32);
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int c = (wid >> 2) * 32 + nt * 8 + 2 * t4;
-          *reinterpret_cast<float2*>(dh1f + rA * LDA + c) = make_float2(acc[nt][0], acc[nt][1]);
-          *reinterpret_cast<float2*>(dh1f + (rA + 8) * LDA + c) = make_float2(acc[nt][2], acc[nt][3]);
+          float* blk = dh1b + (c >> 4) * H1Q + (c & 15);
+          *reinterpret_cast<float2*>(blk + rA * SL) = make_float2(acc[nt][0], acc[nt][1]);
+          *reinterpret_cast<float2*>(blk + (rA + 8) * SL) = make_float2(acc[nt][2], acc[nt][3]);
         }
+        fence_proxy_async();
       }
-      PHASE_MARK(8);   // dh1 partial product
-    }
-    __syncthreads();
-    cluster_arrive();
-    cluster_wait();                                   // ---- barrier 3: dh1 partials in place
-    PHASE_MARK(9);
-    if (active) {
-      // the three remote quarters of dh1 are requested now and consumed after the dW2 product (DSMEM moves ~12 B/clk per
-      // SM -- 12 KB take ~1000 cycles, profiles/r02_dsmem_probe.txt -- so the pull hides behind the next GEMM)
-      float4 v[NQ];
-#pragma unroll
-      for (int d = 0; d < NQ; ++d)
-        if (d != q) v[d] = ld_dsmem_f4(r_dh[d] + static_cast<uint32_t>((r4 * LDA + SL * q + 4 * k4) * 4));
+      __syncthreads();
+      if (tid < NQ && tid != q)                       // reduce-scatter of dh1: the partial for CTA d's columns goes to its slot [q]
+        bulk_push(mapa(smem_u32(dh1in + q * H1Q), grp0 + tid), dh1b + tid * H1Q, H1Q * 4, mapa(smem_u32(&bar_dh), grp0 + tid));
+      PHASE_MARK(8);   // dh1 partial product + push
       // (d) dW2[slice j][k] += sum_r dz2[r][j] * h1[r][k] (warp w: columns 8w..8w+7);  db2[j] += sum_r dz2[r][j]
-      warp_gemm<1, 8, true>(gW2, dz2s, 1, LDS, h1, LDA, 1, 0, wid * 8);
+      //     -- runs while the 12 KB of dh1 partials travel
+      warp_gemm_dw2(gW2, dz2s, LDS, h1, wid * 8);
       colsum_into(dz2s, gsmall + SP_B2);
-      PHASE_MARK(10);  // dW2 + db2 (dh1 quarters in flight)
+      PHASE_MARK(10);  // dW2 + db2 (dh1 partials in flight)
       if (world > 1 && last_tile) {
         // data-parallel ranks: dW2 / db2 / dW3 / db3 / dlog_std leave for the peer GPUs now, ahead of the dW1 product
         __syncthreads();                                   // gsmall[b2, w3, b3, log_std] complete
@@ -906,16 +1008,20 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         dp_push(gW2[0], IC<4>{}, 0);
         if (tid >= SP_B2 && tid < SPN) dp_push(&sv, IC<1>{}, 4 * (1 + NT1));
       }
+      mbar_wait(&bar_dh, ph_x);
+      if (tid == 0) mbar_expect_tx(&bar_dh, (NQ - 1) * H1Q * 4);
       // (e) dz1[r][jj] = (sum over the four partials, quarter order) * (1 - h1[r][16q + jj]^2)   -> overwrites h2s
       {
-        const float4 own = *reinterpret_cast<const float4*>(dh1f + r4 * LDA + SL * q + 4 * k4);
+        float4 v[NQ];
 #pragma unroll
-        for (int d = 0; d < NQ; ++d)
-          if (d == q) v[d] = own;
+        for (int d = 0; d < NQ; ++d) {
+          const float* src = (d == q) ? dh1b + q * H1Q : dh1in + d * H1Q;
+          v[d] = *reinterpret_cast<const float4*>(src + r4 * SL + 4 * k4);
+        }
         float4 s4 = v[0];
 #pragma unroll
         for (int d = 1; d < NQ; ++d) { s4.x += v[d].x; s4.y += v[d].y; s4.z += v[d].z; s4.w += v[d].w; }
-        const float4 h = *reinterpret_cast<const float4*>(h1 + r4 * LDA + SL * q + 4 * k4);
+        const float4 h = *reinterpret_cast<const float4*>(h1 + q * H1Q + r4 * SL + ((4 * k4) ^ (((r4 >> 1) & 1) << 3)));
         s4.x *= (1.f - h.x * h.x); s4.y *= (1.f - h.y * h.y); s4.z *= (1.f - h.z * h.z); s4.w *= (1.f - h.w * h.w);
         *reinterpret_cast<float4*>(dz1s + r4 * LDS + 4 * k4) = s4;
       }
@@ -931,6 +1037,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
 
     cp_async_wait_all();   // indices of tile qt+1 (requested a step ago); the barriers below publish them
     __syncthreads();       // gsmall complete
+    ph_x ^= active ? 1u : 0u;   // both pushed exchanges of this tile are consumed
     if (!last_tile) {
       // more tiles of the same step follow: barrier 4 only orders the buffer reuse
       cluster_arrive();
@@ -945,10 +1052,9 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       if (tid < SP_B2) { sv = gsmall[tid]; dp_push(&sv, IC<1>{}, 4 * (1 + NT1)); }
 #pragma unroll
       for (int i = 0; i < NT1; ++i) dp_push(gW1[i], IC<4>{}, 4 * (1 + i));
-      dp_sum(gW2[0], IC<4>{}, 0);
-#pragma unroll
-      for (int i = 0; i < NT1; ++i) dp_sum(gW1[i], IC<4>{}, 4 * (1 + i));
-      if (tid < SPN) { sv = gsmall[tid]; dp_sum(&sv, IC<1>{}, 4 * (1 + NT1)); gsmall[tid] = sv; }
+      sv = (tid < SPN) ? gsmall[tid] : 0.f;
+      dp_sum_all(gW2[0], gW1, sv);
+      if (tid < SPN) gsmall[tid] = sv;
     }
     PHASE_MARK(13);  // cross-GPU gradient exchange
 
@@ -1134,8 +1240,8 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
 
 size_t update_smem_bytes(int nt1) {
   const int ldx = upd_ldx(nt1);
-  size_t f = 4 * SPO_ROWS + 4 * SPO_MAX_ACT + 8 + SL * ldx + SL * LDA + 2 * SPN + SPO_ROWS * ldx + SPO_ROWS * AUXW + SPO_ROWS * LDA +
-             2 * SPO_ROWS * LDS + 4 * SPO_ROWS * SPO_MAX_ACT + SPO_ROWS * LDA + 64 + 4;
+  size_t f = 4 * SPO_ROWS + 4 * SPO_MAX_ACT + 8 + SL * ldx + SL * LDA + 2 * SPN + SPO_ROWS * ldx + SPO_ROWS * AUXW + NQ * SPO_ROWS * SL +
+             2 * SPO_ROWS * LDS + 4 * SPO_ROWS * SPO_MAX_ACT + 2 * NQ * SPO_ROWS * SL + 64 + 4;
   return f * sizeof(float);
 }
 

@@ -33,9 +33,10 @@ lib.spo_debug_phase_cycles(buf, 1)
 upd.run(data, perms=[perm])
 torch.cuda.synchronize()
 lib.spo_debug_phase_cycles(buf, 1)
-names = ["top (stage-in+sync)", "L1 GEMM+tanh", "barrier 1", "h1 pull", "L2+ypartial", "barrier 2", "y pull+loss rows", "small grads+dz2",
-         "dh1 partial", "barrier 3", "dW2+db2 (dh1 in flight)", "dh1 reduce+dz1", "dW1+db1", "dp exchange", "reg+sumsq", "barrier 4", "Adam"]
+names = {0: "top (stage-in+sync)", 1: "L1 GEMM+tanh", 3: "h1 push+wait", 4: "L2+ypartial", 5: "barrier 2", 6: "y pull+loss rows", 7: "small grads+dz2",
+         8: "dh1 partial+push", 10: "dW2+db2", 11: "dh1 wait+reduce+dz1", 12: "dW1+db1", 13: "dp exchange", 14: "reg+sumsq", 15: "barrier 4", 16: "Adam"}
 for rank in range(12):
     row = [buf[rank * 24 + i] / steps for i in range(17)]
+    row_n = [(names[i], row[i]) for i in sorted(names)]
     net = ("actor", "reward critic", "cost critic")[rank // 4]
-    print(f"{net:13s} q{rank % 4} total {sum(row):7.0f} cyc/step | " + " ".join(f"{n}={v:.0f}" for n, v in zip(names, row)))
+    print(f"{net:13s} q{rank % 4} total {sum(row):7.0f} cyc/step | " + " ".join(f"{n}={v:.0f}" for n, v in row_n))
