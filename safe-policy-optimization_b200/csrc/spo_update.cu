@@ -1,6 +1,7 @@
 // The minibatch update loop as one persistent launch per pass -- round-2 design: every net is spread over FOUR
-// SMs of one 12-CTA thread-block cluster; the CTAs exchange activations by reading each other's shared memory
-// (ld.shared::cluster) behind relaxed hardware cluster barriers.
+// SMs of one 12-CTA thread-block cluster; the CTAs exchange activations by pushing 2-4 KB blocks into each other's
+// shared memory with the bulk-copy engine (cp.async.bulk shared -> peer shared, complete_tx on the receiver's mbarrier).
+// There is no cluster barrier inside the loop.
 //
 // Reference: safepo/single_agent/ppo_lag.py:297-336 (PPO-Lag), focops.py:309-357 (FOCOPS), cpo.py:543-571 /
 // trpo_lag.py:466-494 (critic regression).  Per minibatch: forward of the three nets, losses, backward, critic L2
@@ -14,33 +15,37 @@
 // their biases, the matching columns of W3, and the Adam moments of exactly those parameters (in registers).  Nothing
 // is replicated except b3 / log_std (<= 16 floats), no weight ever moves; what moves per step is activations:
 //
-//   forward   h1[:, slice] = tanh(x W1[slice]^T)          -> all-gather of the 64x16 slices inside the net (16 KB per CTA)
+//   forward   h1[:, slice] = tanh(x W1[slice]^T)          -> all-gather of the 64x16 slices inside the net (3 x 4 KB in)
 //             h2[:, slice] = tanh(h1 W2[slice]^T)         (needs all of h1, local afterwards)
-//             y partial    = h2[:, slice] W3[:, slice]^T  -> all-gather of 64 x O partial sums (tiny)
+//             y partial    = h2[:, slice] W3[:, slice]^T  -> all-gather of the 64 x O partial sums (3 x 2 KB in)
 //   loss rows              (replicated in the four CTAs of a net: every CTA holds all 64 rows of y)
 //   backward  dz2[:, slice], dW3[:, slice], dW2[slice, :] = dz2[:, slice]^T h1       (local)
-//             dh1 partial  = dz2[:, slice] W2[slice, :]   -> reduce-scatter by column quarter (16 KB per CTA)
+//             dh1 partial  = dz2[:, slice] W2[slice, :]   -> reduce-scatter by column quarter (3 x 4 KB in), hidden
+//                                                            behind the dW2 product
 //             dz1[:, slice], dW1[slice, :] = dz1[:, slice]^T x                       (local)
-//   clip      (sum g^2, sum theta^2) of the slice         -> all-to-all of one float2 between the 12 CTAs
+//   clip      (sum g^2, sum theta^2) of the slice         -> all-to-all of 16 bytes between the 12 CTAs = the step barrier
 //   Adam      on the slice, weights rewritten in place in shared memory
 //
-// Each exchange is a PULL: the producer stores into its own shared memory, the cluster passes a hardware barrier
-// (one thread fences at cluster scope, all arrive relaxed: 100-125 cycles measured for 12 CTAs), the consumers load
-// what they need straight from the producers' shared memory (one ld.shared::cluster round trip, the loads of a thread
-// are independent).  Pushing with st.async + mbarrier complete_tx was measured first and rejected: ~1.1-1.4 k cycles
-// of fixed latency per exchange (tools/cluster_probe.cu, profiles/r02_cluster_probe.txt).  Buffer reuse is safe
-// because every consumer finishes its loads before it arrives at the NEXT barrier, and a producer overwrites a buffer
-// only after that barrier (four barriers per step).
+// How the CTAs talk was decided by measurement (tools/cluster_probe.cu, tools/dsmem_probe.cu, profiles/r02_*probe*.txt;
+// 12-CTA cluster): ld.shared::cluster moves ~12 B/clk per SM (12 KB: ~1000 cycles, plus a cluster barrier in front and
+// local stores behind); st.async + mbarrier has 1.1-1.4 k cycles of fixed latency; a cluster-scope fence costs ~380;
+// three 4 KB cp.async.bulk pushes land in 695 cycles, are issued by one thread and leave the LSU alone.  So every
+// exchange is: producers write their block (fence.proxy.async + __syncthreads), one elected thread per destination
+// pushes it, consumers wait on their own mbarrier (armed with the byte count).  Buffer reuse is safe because a CTA
+// pushes its 16 bytes of the step barrier only after its last read of any exchanged buffer, and nothing of the next
+// step is pushed before all 12 of them arrived; the step barrier alternates between two mbarriers so that a CTA a whole
+// step ahead cannot complete_tx into a phase that is still open at a slower one.
 //
 // GEMMs: warp-level mma.sync.m16n8k8 TF32 with the 3xTF32 split in registers (csrc/spo_mma.cuh); every product of
 // the step is now 64x16x64 (or its transposes), 385 cycles at the measured 510 FMA/clk/SM.  tcgen05 was evaluated
 // for this kernel and rejected on latency, not throughput: one M=64,N=64 3xTF32 product measured 1 378 cycles from
-// first issue to completion (profiles/r01_tc64_test.txt) against ~400 for the same work split over four SMs, and
-// the operands here change every step (each is produced by the previous phase), so there is nothing for TMA to
-// prefetch.  The full-batch kernels (csrc/spo_tc_forward.cu), where tiles are independent, are the tcgen05 ones.
+// first issue to completion (profiles/r01_tc64_test.txt), and the operands here change every step (each is produced
+// by the previous phase), so there is nothing for TMA to prefetch.  The full-batch and rollout kernels
+// (csrc/spo_tc_forward.cu), where tiles are independent, are the tcgen05 ones.
 //
-// Shared-memory leading dimensions are all == 8 (mod 32): with the mma fragment pattern (g = lane/4, t = lane%4) both
-// the [m][k] reads (8g + t) and the transposed [k][m] reads (8t + g) are bank-conflict free (round 1 had 30 %).
+// Shared-memory tiles use leading dimensions == 8 (mod 32): k-pair 64-bit loads for [m][k] x [n][k] products and 32-bit
+// loads for transposed operands are then bank-conflict free; h1 lives in four XOR-swizzled [64][16] slice blocks (one
+// block = one contiguous 4 KB push) with the same property for both of its uses.
 //
 // Data-parallel ranks (spo_pg_update_dp): every CTA pushes its slice of the gradient to the same CTA of every peer
 // GPU as 8-byte {value, sequence} words (posted NVLink stores into peer-mapped staging memory), dW2 / dW3 / db2 as soon
@@ -109,23 +114,6 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
-}
-// Hardware cluster barrier, relaxed arrive.  The caller has just passed a __syncthreads: every st.shared of the CTA has
-// been performed on this SM's shared memory (which has no cache in front of it), and a peer's ld.shared::cluster can
-// only be issued after the barrier completed, i.e. after every thread of this CTA arrived.  A release arrive (or a
-// cluster-scope fence by one thread) is a MEMBAR.ALL.GPU in SASS: +290..380 cycles per barrier measured
-// (tools/dsmem_probe.cu, profiles/r02_dsmem_probe.txt: S3 vs S1), four times per step.
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ float2 ld_dsmem_f2(uint32_t addr) {
-  float2 v;
-  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
-  return v;
 }
 // mbarrier + bulk-copy engine: the two 12 KB activation exchanges of a step (h1 all-gather, dh1 reduce-scatter) are PUSHED
 // as 4 KB cp.async.bulk copies shared -> peer shared that complete_tx on the receiver's mbarrier: 695 cycles from issue to
@@ -281,6 +269,7 @@ __device__ __forceinline__ void warp_gemm_kk(float (&acc)[1][4], const float* __
 // k-pair 64-bit loads of the layer-2 A operand (half-warp rows g = 0..3: banks 16(g&1) + 8((g>>1)^x) + 2t, +1) and the 32-bit
 // loads of the dW2 B operand (rows k0 + t: banks 16(t&1) + 8((t>>1)^x) + g).
 constexpr int H1Q = SPO_ROWS * SL;   // floats per slice block
+constexpr int YQ = SPO_ROWS * SPO_MAX_ACT;   // floats per partial-output block
 // element (row r, unit c): h1[(c >> 4) * H1Q + r * SL + ((c & 15) ^ (((r >> 1) & 1) << 3))]
 
 // layer 2: acc[16 x 8 tile at (m0, n0)] = h1[m0.., :] * W2slice[n0.., :]^T   (A from the swizzled blocks, B = w2s [n][k], k-pair mapping)
@@ -347,7 +336,7 @@ __device__ __forceinline__ void warp_gemm_dw2(float (&acc)[1][4], const float* _
 template <int NT1>
 __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   extern __shared__ __align__(16) float smem[];
-  __shared__ __align__(8) uint64_t bar_h1, bar_dh;   // complete_tx targets of the two pushed exchanges
+  __shared__ __align__(8) uint64_t bar_h1, bar_dh, bar_y, bar_ss[2];   // complete_tx targets of the four pushed exchanges
   __shared__ int comm_dead;   // a peer GPU never showed up: stop waiting (ctrl->stop = 2 tells the host)
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
@@ -381,14 +370,14 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   float* h1 = p;  p += NQ * H1Q;                  // all 64 units as four swizzled slice blocks: own + the three pushed by the peers
   float* h2s = p; p += SPO_ROWS * LDS;            // own slice; becomes dz1 slice during backward
   float* dz2s = p; p += SPO_ROWS * LDS;
-  float* ypo = p; p += SPO_ROWS * SPO_MAX_ACT;    // own partial of the output layer (read by the three peers)
+  float* yblk = p; p += NQ * YQ;                  // [quarter][64][8] partial outputs: own block written here, the other three pushed in
   float* y = p;   p += SPO_ROWS * SPO_MAX_ACT;
   float* dy = p;  p += SPO_ROWS * SPO_MAX_ACT;
   float* dls = p; p += SPO_ROWS * SPO_MAX_ACT;    // per-row d loss / d log_std
   float* dh1b = p; p += NQ * H1Q;                 // own partial of dh1 as [destination quarter][64][16]: block d is pushed to CTA d
   float* dh1in = p; p += NQ * H1Q;                // [source quarter][64][16]: the partials the three peers pushed for the own columns
   float* red = p; p += 64;                        // block-reduction scratch
-  float* xchg = p; p += 4;                        // [parity]{sum g^2, sum theta^2} of this CTA (read by all peers)
+  float* xin = p; p += 2 * 16 * 4;                // [parity][source CTA]{sum g^2, sum theta^2, -, -}: own entry written here, 11 pushed in
   float* dz1s = h2s;
   float* b1s = sp + SP_B1; float* b2s = sp + SP_B2; float* w3s = sp + SP_W3; float* b3 = sp + SP_B3; float* log_std = sp + SP_LS;
 
@@ -400,8 +389,16 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     comm_dead = 0;
     mbar_init(&bar_h1, 1);
     mbar_init(&bar_dh, 1);
+    mbar_init(&bar_y, 1);
+    mbar_init(&bar_ss[0], 1);
+    mbar_init(&bar_ss[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (active) { mbar_expect_tx(&bar_h1, (NQ - 1) * H1Q * 4); mbar_expect_tx(&bar_dh, (NQ - 1) * H1Q * 4); }
+    if (!idle) { mbar_expect_tx(&bar_ss[0], (NCTA - 1) * 16); mbar_expect_tx(&bar_ss[1], (NCTA - 1) * 16); }
+    if (active) {
+      mbar_expect_tx(&bar_h1, (NQ - 1) * H1Q * 4);
+      mbar_expect_tx(&bar_dh, (NQ - 1) * H1Q * 4);
+      mbar_expect_tx(&bar_y, (NQ - 1) * YQ * 4);
+    }
   }
 
   // ---- small-parameter entry of this thread ----
@@ -610,11 +607,9 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   }
 
   // shared::cluster addresses of the buffers this CTA pulls from: the four CTAs of its net, all CTAs for the norm
-  uint32_t r_yp[NQ];
-#pragma unroll
-  for (int d = 0; d < NQ; ++d) r_yp[d] = mapa(smem_u32(ypo), grp0 + d);
-  uint32_t ph_x = 0;     // phase parity of bar_h1 / bar_dh (one phase per tile)
-  const uint32_t r_xchg = mapa(smem_u32(xchg), lane < NCTA ? lane : 0);
+  uint32_t ph_x = 0;     // phase parity of bar_h1 / bar_y / bar_dh (one phase per tile of an active net)
+  uint32_t tcount = 0;   // tiles done: the step barrier of tile n uses bar_ss[n & 1], phase parity (n >> 1) & 1 -- two barriers in
+                         // alternation, so that a peer that is a whole step ahead can never complete_tx into a phase still open here
 
   // gradient accumulators = accumulator fragments of the dW products (persist across the tiles of a step)
   float gW2[1][4], gW1[NT1][4];
@@ -634,7 +629,11 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   const int rA = mt * 16 + g8, cA = ntl * 8 + 2 * t4;
   const int r4 = tid >> 2, k4 = tid & 3;      // (row, quarter-of-a-slice) mapping of the element-wise phases
 
-  cluster.sync();   // nobody reads a peer's shared memory before every CTA of the cluster runs
+  cluster.sync();   // nobody pushes into a peer's shared memory before every CTA of the cluster has armed its mbarriers
+  if (idle) {       // fallback cluster of 16: the last four CTAs only keep the cluster alive
+    cluster.sync();
+    return;
+  }
 
   int64_t step = 0;
   int sub = 0;
@@ -781,24 +780,24 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
           float sacc = fmaf(hv.x, wv.x, hv.y * wv.y) + fmaf(hv.z, wv.z, hv.w * wv.w);
           sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
           sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-          if (k4 == (o & 3)) ypo[r4 * SPO_MAX_ACT + o] = sacc;
+          if (k4 == (o & 3)) yblk[q * YQ + r4 * SPO_MAX_ACT + o] = sacc;
         }
+        fence_proxy_async();
       }
-    }
-    PHASE_MARK(4);   // layer 2 + partial output layer
-    __syncthreads();
-    cluster_arrive();
-    cluster_wait();                                   // ---- barrier 2: partial outputs in place
-    PHASE_MARK(5);
-    if (active) {
-      // y[r][o] = b3[o] + sum over the four quarters: lane k4 of a row pulls quarter k4's partial (two float4),
-      // a butterfly over the four lanes finishes the sum (fixed order (p0 + p1) + (p2 + p3) in every CTA)
+      __syncthreads();
+      if (tid < NQ && tid != q)                       // all-gather of the partial outputs: 2 KB to each peer of the net
+        bulk_push(mapa(smem_u32(yblk + q * YQ), grp0 + tid), yblk + q * YQ, YQ * 4, mapa(smem_u32(&bar_y), grp0 + tid));
+      PHASE_MARK(4);   // layer 2 + partial output layer
+      mbar_wait(&bar_y, ph_x);
+      if (tid == 0) mbar_expect_tx(&bar_y, (NQ - 1) * YQ * 4);
+      PHASE_MARK(5);   // y all-gather (pushed)
+      // y[r][o] = b3[o] + sum over the four quarters: lane k4 of a row reads quarter k4's partial, a butterfly over the
+      // four lanes finishes the sum (fixed order (p0 + p1) + (p2 + p3) in every CTA)
       {
-        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = make_float4(0.f, 0.f, 0.f, 0.f);
-        const uint32_t ya = r_yp[k4] + static_cast<uint32_t>(r4 * SPO_MAX_ACT * 4);
-        if (O <= 2) { const float2 t2 = ld_dsmem_f2(ya); lo.x = t2.x; lo.y = t2.y; }   // no more bytes than needed: DSMEM is the narrow pipe
-        else lo = ld_dsmem_f4(ya);
-        if (O > 4) hi = ld_dsmem_f4(ya + 16);
+        const float4* yp = reinterpret_cast<const float4*>(yblk + k4 * YQ + r4 * SPO_MAX_ACT);
+        const float4 lo = yp[0];
+        float4 hi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (O > 4) hi = yp[1];
         yv[0] = lo.x; yv[1] = lo.y; yv[2] = lo.z; yv[3] = lo.w; yv[4] = hi.x; yv[5] = hi.y; yv[6] = hi.z; yv[7] = hi.w;
 #pragma unroll
         for (int o = 0; o < SPO_MAX_ACT; ++o) {
@@ -1038,11 +1037,26 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     cp_async_wait_all();   // indices of tile qt+1 (requested a step ago); the barriers below publish them
     __syncthreads();       // gsmall complete
     ph_x ^= active ? 1u : 0u;   // both pushed exchanges of this tile are consumed
+    // The step barrier = the all-to-all of (sum g^2, sum theta^2): every CTA pushes 16 bytes to each of the other 11 and waits
+    // for 11 x 16 bytes on its own mbarrier.  A CTA pushes only after its last read of any exchanged buffer, so nobody can
+    // overwrite h1 / the partial-output blocks / the dh1 slots of a CTA that still reads them.
+    auto step_barrier_push = [&](float ssq, float t2) {
+      float* mine = xin + (par * 16 + static_cast<int>(rank)) * 4;
+      if (tid == 0) { *reinterpret_cast<float4*>(mine) = make_float4(ssq, t2, 0.f, 0.f); fence_proxy_async(); }
+      __syncthreads();
+      if (tid < NCTA && tid != static_cast<int>(rank)) bulk_push(mapa(smem_u32(mine), tid), mine, 16, mapa(smem_u32(&bar_ss[tcount & 1u]), tid));
+    };
+    auto step_barrier_wait = [&]() {
+      uint64_t* bar = &bar_ss[tcount & 1u];
+      mbar_wait(bar, (tcount >> 1) & 1u);
+      if (tid == 0) mbar_expect_tx(bar, (NCTA - 1) * 16);
+      ++tcount;
+    };
     if (!last_tile) {
-      // more tiles of the same step follow: barrier 4 only orders the buffer reuse
-      cluster_arrive();
+      // more tiles of the same step follow: the exchange only orders the buffer reuse
+      step_barrier_push(0.f, 0.f);
       stage_next();
-      cluster_wait();
+      step_barrier_wait();
       continue;
     }
 
@@ -1097,35 +1111,28 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       if (lane == 0) *reinterpret_cast<float2*>(red + 16 + 2 * wid) = make_float2(ss, th2);
       __syncthreads();
     }
-    if (tid == 0) {
+    {
       float s = 0.f, t2 = 0.f;
-      if (active) {
+      if (tid == 0 && active) {
 #pragma unroll
         for (int w = 0; w < UT / 32; w += 2) {
           const float4 v = *reinterpret_cast<const float4*>(red + 16 + 2 * w);
           s += v.x + v.z; t2 += v.y + v.w;
         }
       }
-      *reinterpret_cast<float2*>(xchg + 2 * par) = make_float2(s + extra_sumsq, t2);
+      PHASE_MARK(14);  // regulariser + sum of squares
+      step_barrier_push(s + extra_sumsq, t2);
     }
-    PHASE_MARK(14);  // regulariser + sum of squares
-    __syncthreads();
-    cluster_arrive();
-    stage_next();    // rows of the next tile are requested while the barrier completes
-    cluster_wait();                                   // ---- barrier 4: every CTA's (sum g^2, sum theta^2) in place
-    PHASE_MARK(15);
-    // every warp pulls the 12 pairs itself (lane b from CTA b) and reduces them with the same shuffle tree
-    float total, t2net;
-    {
-      float2 v = make_float2(0.f, 0.f);
-      if (lane < NCTA) v = ld_dsmem_f2(r_xchg + static_cast<uint32_t>(2 * par * 4));
-      float s = v.x, t2 = v.y;
-      t2 += __shfl_xor_sync(0xffffffffu, t2, 1);
-      t2 += __shfl_xor_sync(0xffffffffu, t2, 2);       // lanes 4n..4n+3: sum theta^2 of net n
+    stage_next();    // rows of the next tile are requested while the 16-byte pushes travel
+    step_barrier_wait();
+    PHASE_MARK(15);  // step barrier (all-to-all of the norms)
+    // every thread reads the 12 pairs from its own shared memory and adds them in CTA order
+    float total = 0.f, t2net = 0.f;
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      total = __shfl_sync(0xffffffffu, s, 0);
-      t2net = __shfl_sync(0xffffffffu, t2, net * NQ);
+    for (int b = 0; b < NCTA; ++b) {
+      const float2 v = *reinterpret_cast<const float2*>(xin + (par * 16 + b) * 4);
+      total += v.x;
+      if (b / NQ == net) t2net += v.y;
     }
     if (tid == 0 && q == 0 && active) {
       // logged loss of this step (ppo_lag.py:330-336): critics include the L2 term over the whole net
@@ -1241,7 +1248,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
 size_t update_smem_bytes(int nt1) {
   const int ldx = upd_ldx(nt1);
   size_t f = 4 * SPO_ROWS + 4 * SPO_MAX_ACT + 8 + SL * ldx + SL * LDA + 2 * SPN + SPO_ROWS * ldx + SPO_ROWS * AUXW + NQ * SPO_ROWS * SL +
-             2 * SPO_ROWS * LDS + 4 * SPO_ROWS * SPO_MAX_ACT + 2 * NQ * SPO_ROWS * SL + 64 + 4;
+             2 * SPO_ROWS * LDS + (3 + NQ) * SPO_ROWS * SPO_MAX_ACT + 2 * NQ * SPO_ROWS * SL + 64 + 128;
   return f * sizeof(float);
 }
 
