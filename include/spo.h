@@ -209,14 +209,13 @@ int spo_pg_update(const spo_dims* d, float* params, float* adam_m, float* adam_v
 /* ---- data-parallel variant: ranks own disjoint env shards and hold
  * identical replicas of the weights; every minibatch step each net's gradient is summed
  * over the ranks INSIDE the persistent kernel through peer-mapped memory over
- * NVLink/NVSwitch (no NCCL call, no extra launch): a CTA pushes its gradient into a
- * staging slot of every peer (posted remote stores), fences, raises the peer's sequence flag
- * (release.sys), then waits on its own flags (acquire.sys) and accumulates the slots it
- * received in rank order, so all ranks obtain bit-identical sums and the replicas never
- * diverge.  The result is scaled by 1/world (global minibatch = world * batch).
- *   grad_bufs[r] : rank r's staging memory, 2 * world * 3 * slot floats, indexed
- *                  [parity][source rank][net][slot] (slot from spo_comm_slot_floats)
- *   flags[r]     : rank r's world*3 uint32 sequence flags [source rank][net] (zero-initialised)
+ * NVLink/NVSwitch (no NCCL call, no extra launch): a CTA pushes its slice of the gradient into
+ * peer-mapped staging memory of every peer as 8-byte {value, sequence} words (posted remote stores) and polls the
+ * words it is owed -- no fence, no flag, no barrier; sums run in rank order, so all ranks obtain bit-identical
+ * results and the replicas never diverge.  The result is scaled by 1/world (global minibatch = world * batch).
+ *   grad_bufs[r] : rank r's staging memory, 2 * world * 3 * slot floats (slot from spo_comm_slot_floats):
+ *                  [parity][source rank][net][slot] 8-byte {value, sequence} words
+ *   flags[r]     : unused since round 2 (the sequence number inside every word is the flag); may be NULL
  *   seq_base     : number of minibatch steps all ranks have completed in earlier launches
  * Both pointer tables live in DEVICE memory (world entries each). */
 typedef struct spo_comm {

@@ -333,7 +333,9 @@ __device__ __forceinline__ void warp_gemm_dw2(float (&acc)[1][4], const float* _
   for (int e = 0; e < 4; ++e) acc[0][e] += (c_lh[e] + c_hl[e]) + c_hh[e];
 }
 
-template <int NT1>
+// DP = false: the single-GPU instantiation carries none of the cross-GPU code (its 24-register polling buffers would sit
+// on top of an already full register file)
+template <int NT1, bool DP>
 __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ __align__(8) uint64_t bar_h1, bar_dh, bar_y, bar_ss[2];   // complete_tx targets of the four pushed exchanges
@@ -623,7 +625,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   float step_loss = 0.f, step_aux0 = 0.f, step_aux1 = 0.f;   // thread 0: loss numerators of the current step
 
   // cross-GPU staging of this CTA: [parity][source rank][cta][dp_slot_words] 8-byte words
-  const int world = a.comm.world, me = a.comm.rank;
+  const int world = DP ? a.comm.world : 1, me = DP ? a.comm.rank : 0;
   constexpr int DPW = dp_slot_words(NT1);
   const int mt = wid & 3, ntl = wid >> 2;     // 16 x 8 tile of the 64 x 16 slice products
   const int rA = mt * 16 + g8, cA = ntl * 8 + 2 * t4;
@@ -656,6 +658,10 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       fetch_idx(qt + 2, st, sb);
       cp_async_commit();
     };
+    // Cross-GPU exchange: every word goes to every peer (one NVLink hop), each rank sums all copies itself in rank order.
+    // (A two-hop variant -- every word reduced by one owner rank and redistributed, 3.6x less NVLink traffic at 8 GPUs --
+    // was built and measured: 15.6 us per step at 4 GPUs against ~12 for this one; the second hop costs more than the
+    // bytes it saves.  profiles/r02_dp_check_4gpu_twohop.log)
     // push `n` of this thread's gradient values (words (w0 + i) * UT + tid of the CTA slot) to every peer GPU
     auto dp_push = [&](const float* vals, auto n_c, int w0) {
       constexpr int n = decltype(n_c)::value;
@@ -666,6 +672,69 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
 #pragma unroll
         for (int i = 0; i < n; ++i) st_ll(dst + (w0 + i) * UT + tid, vals[i], seq);
       }
+    };
+    // the receive for 4..8 ranks: three words of ALL peers per round (up to 21 requests in flight) instead of all words of one
+    // peer per round: 3 L2 round trips at 8 GPUs instead of 7
+    auto dp_sum_wide = [&](float (&g2)[4], float (&g1)[NT1][4], float& gs) {
+      constexpr int NW = 4 * (1 + NT1) + 1, G = 3;
+      const unsigned limit = a.comm.spin_limit ? a.comm.spin_limit : 400000000u;
+      const float inv_w = __fdiv_rn(1.f, static_cast<float>(world));
+      float val[NW];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        val[e] = g2[e];
+#pragma unroll
+        for (int i = 0; i < NT1; ++i) val[4 * (1 + i) + e] = g1[i][e];
+      }
+      val[NW - 1] = gs;
+      const float2* slot0 = reinterpret_cast<const float2*>(a.comm.grad_bufs[me]) + (static_cast<size_t>(seq & 1u) * world * NCTA + rank) * DPW + tid;
+      const size_t rstride = static_cast<size_t>(NCTA) * DPW;
+#pragma unroll
+      for (int i0 = 0; i0 < NW; i0 += G) {
+        unsigned need = 0;
+#pragma unroll
+        for (int j = 0; j < G; ++j)
+          if (i0 + j < NW && ((i0 + j < NW - 1) || tid < SPN))
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+              if (r < world && r != me) need |= 1u << (r * G + j);
+        unsigned got = 0, polls = 0;
+        float v[8][G];
+        while (got != need) {
+          unsigned wa[8][G], wb[8][G];
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+              if (((need & ~got) >> (r * G + j)) & 1u)
+                asm volatile("ld.relaxed.sys.global.v2.b32 {%0, %1}, [%2];" : "=r"(wa[r][j]), "=r"(wb[r][j]) : "l"(slot0 + r * rstride + (i0 + j) * UT) : "memory");
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int j = 0; j < G; ++j)
+              if ((((need & ~got) >> (r * G + j)) & 1u) && wb[r][j] == seq) { v[r][j] = __uint_as_float(wa[r][j]); got |= 1u << (r * G + j); }
+          if (got != need) {
+            if (*reinterpret_cast<volatile int*>(&comm_dead)) break;
+            if (++polls > limit) { comm_dead = 1; atomicExch(&ctrl->stop, 2); break; }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < G; ++j)
+          if (i0 + j < NW) {
+            float acc = 0.f;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+              if (r < world) acc += (r == me) ? val[i0 + j] : (((got >> (r * G + j)) & 1u) ? v[r][j] : 0.f);
+            val[i0 + j] = __fmul_rn(acc, inv_w);
+          }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        g2[e] = val[e];
+#pragma unroll
+        for (int i = 0; i < NT1; ++i) g1[i][e] = val[4 * (1 + i) + e];
+      }
+      gs = val[NW - 1];
     };
     // rank-ordered sum of ALL of this thread's gradient words (4 of dW2, 4 per block of dW1, one small entry for
     // tid < SPN) with the words received from every peer GPU, scaled by 1/world.  The words of a peer are requested
@@ -1000,7 +1069,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       warp_gemm_dw2(gW2, dz2s, LDS, h1, wid * 8);
       colsum_into(dz2s, gsmall + SP_B2);
       PHASE_MARK(10);  // dW2 + db2 (dh1 partials in flight)
-      if (world > 1 && last_tile) {
+      if (DP && world > 1 && last_tile) {
         // data-parallel ranks: dW2 / db2 / dW3 / db3 / dlog_std leave for the peer GPUs now, ahead of the dW1 product
         __syncthreads();                                   // gsmall[b2, w3, b3, log_std] complete
         float sv = (tid >= SP_B2 && tid < SPN) ? gsmall[tid] : 0.f;
@@ -1061,13 +1130,14 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     }
 
     // ---------------- cross-GPU gradient sum (data-parallel ranks), in rank order ----------------
-    if (world > 1 && active) {
+    if (DP && world > 1 && active) {
       float sv = 0.f;
       if (tid < SP_B2) { sv = gsmall[tid]; dp_push(&sv, IC<1>{}, 4 * (1 + NT1)); }
 #pragma unroll
       for (int i = 0; i < NT1; ++i) dp_push(gW1[i], IC<4>{}, 4 * (1 + i));
       sv = (tid < SPN) ? gsmall[tid] : 0.f;
-      dp_sum_all(gW2[0], gW1, sv);
+      if (world >= 4 && world <= 8) dp_sum_wide(gW2[0], gW1, sv);
+      else dp_sum_all(gW2[0], gW1, sv);
       if (tid < SPN) gsmall[tid] = sv;
     }
     PHASE_MARK(13);  // cross-GPU gradient exchange
@@ -1252,15 +1322,15 @@ size_t update_smem_bytes(int nt1) {
   return f * sizeof(float);
 }
 
-template <int NT1>
+template <int NT1, bool DP>
 int launch_update(const UpdArgs& a, cudaStream_t stream) {
   const size_t smem = update_smem_bytes(NT1);
   SPO_REQUIRE(smem <= 227 * 1024, SPO_ERR_UNSUPPORTED, "spo_pg_update: obs_dim=%d needs %zu B of shared memory (> 227 KB)", a.D, smem);
   // 12 CTAs are needed; clusters above 8 are "non-portable" sizes: 12 is tried first, 16 (four CTAs idle) second.
   // The choice is cached per process: one process drives one GPU (torchrun-style data parallelism).
   static int cluster_size = 0;
-  SPO_CUDA_TRY(cudaFuncSetAttribute(spo_update_kernel<NT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  SPO_CUDA_TRY(cudaFuncSetAttribute(spo_update_kernel<NT1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  SPO_CUDA_TRY(cudaFuncSetAttribute(spo_update_kernel<NT1, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  SPO_CUDA_TRY(cudaFuncSetAttribute(spo_update_kernel<NT1, DP>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   if (!cluster_size) {
     const char* env = getenv("SPO_CLUSTER");   // debugging aid: pin the cluster size (12 or 16)
     if (env && atoi(env) >= NCTA && atoi(env) <= 16) cluster_size = atoi(env);
@@ -1279,7 +1349,7 @@ int launch_update(const UpdArgs& a, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, spo_update_kernel<NT1>, a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, spo_update_kernel<NT1, DP>, a);
     if (e == cudaSuccess) { cluster_size = cs; return SPO_OK; }
     if (cluster_size || attempt == 1) {
       spo_set_error("spo_pg_update: launch failed (cluster=%d): %s", cs, cudaGetErrorString(e));
@@ -1365,13 +1435,14 @@ extern "C" int spo_pg_update_dp(const spo_dims* d, float* params, float* adam_m,
     a.hp.clip_hi = INFINITY;
   }
   if (comm && comm->world > 1) {
-    SPO_REQUIRE(comm->rank >= 0 && comm->rank < comm->world && comm->world <= 32 && comm->grad_bufs,
+    SPO_REQUIRE(comm->rank >= 0 && comm->rank < comm->world && comm->world <= 16 && comm->grad_bufs,
                 SPO_ERR_INVALID_ARG, "spo_pg_update_dp: bad spo_comm (world=%d rank=%d)", comm->world, comm->rank);
     a.comm = *comm;
   } else {
     a.comm.world = 1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (d->obs_dim <= 64) return launch_update<1>(a, st);
-  return launch_update<2>(a, st);
+  const bool dp = a.comm.world > 1;
+  if (d->obs_dim <= 64) return dp ? launch_update<1, true>(a, st) : launch_update<1, false>(a, st);
+  return dp ? launch_update<2, true>(a, st) : launch_update<2, false>(a, st);
 }

@@ -72,7 +72,7 @@ class DataParallel:
         lib = L.lib()
         slot = C.c_int()
         L.check(lib.spo_comm_slot_floats(C.byref(dims), C.byref(slot)), "spo_comm_slot_floats")
-        nbytes_grad = 2 * self.world * 3 * slot.value * 4      # [parity][source rank][net][slot]
+        nbytes_grad = 2 * self.world * 3 * slot.value * 4      # [parity][source rank][net][slot] 8-byte {value, sequence} words
         own = []
         for nbytes in (nbytes_grad, max(256, 4 * 3 * self.world)):
             ptr = C.c_void_p()

@@ -233,3 +233,31 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_device():
     assert lib.spo_gae_masked(None, None, None, 0.0, 1.0, 0.96, 0.9, None, 4, 8, None) != OK and b"spo_gae_masked" in lib.spo_last_error()
     assert lib.spo_actor_forward(C.byref(d), None, None, 0, None, None) != OK
     assert lib.spo_fvp(C.byref(d), None, None, 0, None, 0.1, None, None) != OK
+
+
+def test_env_factory_imports_and_fails_loudly_without_safety_gymnasium():
+    """`--env mujoco` must resolve to a real factory (safepo/common/env.py), not to a missing module."""
+    import importlib.util
+    from safepo import _lib as L
+    from safepo.common.env import make_sa_mujoco_env
+    if importlib.util.find_spec("safety_gymnasium") is None:
+        with pytest.raises(L.SpoError, match="safety_gymnasium"):
+            make_sa_mujoco_env(num_envs=2, env_id="SafetyPointGoal1-v0", seed=0)
+
+
+def test_checkpoint_normalizer_object_has_gymnasium_surface():
+    """the checkpointed "Normalizer" must be an object evaluate.py:56-57 can assign to eval_env.obs_rms:
+    picklable, with numpy mean / var, count and update() (the pooled-moments merge of gymnasium's RunningMeanStd)."""
+    import pickle
+    import numpy as np
+    from oracle import envio
+    from safepo.common.normalizer import HostRunningMeanStd
+    rng = np.random.default_rng(0)
+    h, o = HostRunningMeanStd((5,)), envio.RunningMeanStd(shape=(5,))
+    for _ in range(4):
+        x = rng.normal(size=(7, 5)) * 3 + 1
+        h.update(x); o.update(x)
+    h2 = pickle.loads(pickle.dumps(h))
+    assert np.array_equal(h2.mean, o.mean) and np.array_equal(h2.var, o.var) and h2.count == o.count
+    h2.update(rng.normal(size=(3, 5)))
+    assert h2.count == o.count + 3 and h2.mean.shape == (5,)

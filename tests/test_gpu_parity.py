@@ -200,6 +200,37 @@ def test_tensor_core_rollout_step_and_store(N, D, A):
         assert close(dact, da, atol=2e-6)[0] and close(dlogp, dl, atol=2e-6)[0]
 
 
+def test_buffer_two_epochs_store_finish_get_vs_oracle():
+    """with the reference-compatible store() / finish_path() / get() loop, path boundaries and bootstrap values of
+    one epoch must not leak into the next (get() clears them).  Two epochs with different cut points against the oracle's
+    PathBuffer (itself pinned to the reference's VectorizedOnPolicyBuffer), sequential-GAE mode: targets bit-exact."""
+    dev = _cuda()
+    from safepo.common.buffer import VectorizedOnPolicyBuffer
+    N, T, D, A = 3, 12, 4, 2
+    buf = VectorizedOnPolicyBuffer(Sp(D), Sp(A), size=T, device=dev, num_envs=N, gae_mode="exact")
+    obuf = TR.PathBuffer(N, T, D, A, 0.99)
+    g = torch.Generator().manual_seed(3)
+    for epoch, cuts in enumerate(({0: [4, 11], 1: [11], 2: [2, 7, 11]}, {0: [11], 1: [5, 11], 2: [9, 11]})):
+        for t in range(T):
+            obs, act = torch.randn(N, D, generator=g), torch.randn(N, A, generator=g)
+            rew, cost = torch.randn(N, generator=g), torch.rand(N, generator=g)
+            vr, vc, lp = torch.randn(N, generator=g), torch.randn(N, generator=g), torch.randn(N, generator=g)
+            buf.store(obs=obs, act=act, reward=rew, cost=cost, value_r=vr, value_c=vc, log_prob=lp)
+            obuf.store(t, obs, act, rew, cost, vr, vc, lp)
+            for idx in range(N):
+                if t in cuts[idx]:
+                    lr_, lc_ = torch.randn(1, generator=g), torch.randn(1, generator=g)
+                    buf.finish_path(lr_, lc_, idx=idx)
+                    obuf.finish_path(lr_, lc_, idx)
+        data, want = buf.get(), obuf.get()
+        for k in ("target_value_r", "target_value_c"):
+            assert torch.equal(data[k].cpu(), want[k]), (epoch, k, float((data[k].cpu() - want[k]).abs().max()))
+        for k in ("adv_r", "adv_c"):
+            ok, ea, er = close(data[k], want[k], rtol=RTOL, atol=2e-6)
+            assert ok, (epoch, k, ea, er)
+        assert int(buf.seg_end.sum()) == 0 and float(buf.boot_r.abs().sum()) == 0.0
+
+
 # ---------------------------------------------------------------------------------------
 # G1 / G3
 # ---------------------------------------------------------------------------------------
