@@ -146,6 +146,44 @@ class Rollout:
         if self.obs_norm is not None:
             self.obs_norm.normalize(self.obs_d, out=self.obs_d)
 
+    WINDOW = 50     # the reference's deque(maxlen=50) of finished episodes (ppo_lag.py:142-147)
+
+    def _account_finished(self, finished):
+        """Episode bookkeeping of ppo_lag.py:216-230 for the envs that finished in this step (ascending env index): every
+        finished episode is appended to the three 50-episode deques and the running means of the deques are logged once
+        per episode.  Vectorised: once the deques are full, the k running means of a step are the row means of a
+        (k x 50) sliding window over [old deque | new values] -- np.mean along the contiguous last axis uses the same
+        pairwise summation as np.mean of the deque, so the logged numbers are bit-identical to the reference's per-env
+        loop; no Python iteration over envs (1024 of them finish in the same step at config 2).  While a deque is still
+        filling (the first 50 episodes of a run) the windows have different lengths and the plain loop runs.
+        The returns are accumulated on the host in float64 like the reference does with the env's float64 rewards
+        (ep_ret += reward, ppo_lag.py:179-181): the device only ever sees their fp32 copies."""
+        k = len(finished)
+        if k == 0:
+            return
+        logger, W = self.logger, self.WINDOW
+        if len(self.rew_deque) < W:
+            for idx in finished:               # ascending env index, ppo_lag.py:199,216-230
+                self.rew_deque.append(self.ep_ret[idx])
+                self.cost_deque.append(self.ep_cost[idx])
+                self.len_deque.append(self.ep_len[idx])
+                logger.store(**{"Metrics/EpRet": np.mean(self.rew_deque), "Metrics/EpCost": np.mean(self.cost_deque),
+                                "Metrics/EpLen": np.mean(self.len_deque)})
+        else:
+            means = []
+            for dq, vals in ((self.rew_deque, self.ep_ret), (self.cost_deque, self.ep_cost), (self.len_deque, self.ep_len)):
+                seq = np.concatenate([np.fromiter(dq, dtype=np.float64, count=W), vals[finished]])
+                means.append(np.lib.stride_tricks.sliding_window_view(seq, W)[1:].mean(axis=1))
+                dq.extend(seq[-min(k, W):])
+            ed = logger.epoch_dict
+            ed.setdefault("Metrics/EpRet", []).extend(means[0])
+            ed.setdefault("Metrics/EpCost", []).extend(means[1])
+            ed.setdefault("Metrics/EpLen", []).extend(means[2])
+        self.ep_ret[finished] = 0.0
+        self.ep_cost[finished] = 0.0
+        self.ep_len[finished] = 0.0
+        logger.logged = False
+
     def _burn_bootstrap_draws(self, terminated, truncated, epoch_end):
         """The reference obtains bootstrap values with policy.step(..., deterministic=False)
         (ppo_lag.py:204-213): every such call discards one [A] normal draw."""
@@ -208,15 +246,7 @@ class Rollout:
             self.obs_d.copy_(obs_view)
             if self.host_rng and (epoch_end or terminated.any() or any_trunc):
                 self._burn_bootstrap_draws(terminated, truncated, epoch_end)
-            finished = np.nonzero(terminated | truncated)[0]
-            for idx in finished:               # ascending env index, ppo_lag.py:199,216-230
-                self.rew_deque.append(self.ep_ret[idx])
-                self.cost_deque.append(self.ep_cost[idx])
-                self.len_deque.append(self.ep_len[idx])
-                logger.store(**{"Metrics/EpRet": np.mean(self.rew_deque), "Metrics/EpCost": np.mean(self.cost_deque),
-                                "Metrics/EpLen": np.mean(self.len_deque)})
-                self.ep_ret[idx] = self.ep_cost[idx] = self.ep_len[idx] = 0.0
-                logger.logged = False
+            self._account_finished(np.nonzero(terminated | truncated)[0])
         torch.cuda.current_stream().synchronize()
         return time.time() - t0
 
@@ -267,15 +297,7 @@ class DeviceTapeRollout(Rollout):
             self.k = k
             if self.host_rng and (epoch_end or terminated.any() or any_trunc):
                 self._burn_bootstrap_draws(terminated, truncated, epoch_end)
-            finished = np.nonzero(terminated | truncated)[0]
-            for idx in finished:
-                self.rew_deque.append(self.ep_ret[idx])
-                self.cost_deque.append(self.ep_cost[idx])
-                self.len_deque.append(self.ep_len[idx])
-                logger.store(**{"Metrics/EpRet": np.mean(self.rew_deque), "Metrics/EpCost": np.mean(self.cost_deque),
-                                "Metrics/EpLen": np.mean(self.len_deque)})
-                self.ep_ret[idx] = self.ep_cost[idx] = self.ep_len[idx] = 0.0
-                logger.logged = False
+            self._account_finished(np.nonzero(terminated | truncated)[0])
         return time.time() - t0
 
 

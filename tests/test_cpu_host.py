@@ -261,3 +261,46 @@ def test_checkpoint_normalizer_object_has_gymnasium_surface():
     assert np.array_equal(h2.mean, o.mean) and np.array_equal(h2.var, o.var) and h2.count == o.count
     h2.update(rng.normal(size=(3, 5)))
     assert h2.count == o.count + 3 and h2.mean.shape == (5,)
+
+
+def test_vectorised_episode_accounting_is_bit_identical_to_the_per_env_loop():
+    """the per-step bookkeeping of finished episodes (50-episode deques, one logged running mean per finished
+    episode, ascending env index) without a Python loop over envs -- same numbers, bit for bit, as the reference-style loop."""
+    from collections import deque
+    import numpy as np
+    from safepo.single_agent._engine import Rollout
+
+    class Log:
+        def __init__(self):
+            self.epoch_dict, self.logged = {}, True
+
+        def store(self, **kw):
+            for k, v in kw.items():
+                self.epoch_dict.setdefault(k, []).append(v)
+
+    rng = np.random.default_rng(0)
+    N = 300
+    fast = Rollout.__new__(Rollout)            # only the accounting state, no device objects
+    fast.logger = Log()
+    fast.ep_ret, fast.ep_cost, fast.ep_len = rng.normal(size=N) * 10, rng.random(N) * 50, rng.integers(1, 1000, N).astype(float)
+    fast.rew_deque, fast.cost_deque, fast.len_deque = deque(maxlen=50), deque(maxlen=50), deque(maxlen=50)
+    ref_ret, ref_cost, ref_len = fast.ep_ret.copy(), fast.ep_cost.copy(), fast.ep_len.copy()
+    rd, cd, ld = deque(maxlen=50), deque(maxlen=50), deque(maxlen=50)
+    want = {"Metrics/EpRet": [], "Metrics/EpCost": [], "Metrics/EpLen": []}
+    for step in range(12):
+        k = [3, 40, 9, 120, 300, 1, 0, 64, 300, 2, 51, 299][step]
+        finished = np.sort(rng.choice(N, size=k, replace=False))
+        for idx in finished:                    # the reference's loop, ppo_lag.py:216-230
+            rd.append(ref_ret[idx]); cd.append(ref_cost[idx]); ld.append(ref_len[idx])
+            want["Metrics/EpRet"].append(np.mean(rd)); want["Metrics/EpCost"].append(np.mean(cd)); want["Metrics/EpLen"].append(np.mean(ld))
+            ref_ret[idx] = ref_cost[idx] = ref_len[idx] = 0.0
+        fast._account_finished(finished)
+        bump = rng.normal(size=N)
+        fast.ep_ret += bump; ref_ret += bump
+        fast.ep_cost += np.abs(bump); ref_cost += np.abs(bump)
+        fast.ep_len += 1; ref_len += 1
+    for key in want:
+        got = np.asarray(fast.logger.epoch_dict[key], dtype=np.float64)
+        assert got.shape == (len(want[key]),) and np.array_equal(got, np.asarray(want[key])), key
+    assert list(fast.rew_deque) == list(rd) and list(fast.len_deque) == list(ld)
+    assert np.array_equal(fast.ep_ret, ref_ret) and not fast.logger.logged
