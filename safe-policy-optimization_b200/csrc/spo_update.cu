@@ -462,16 +462,11 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   const float reg = is_actor ? 0.f : __fmul_rn(vcoef, __fmul_rn(a.hp.critic_l2, 2.f));
 
   // ---- staging of the next tile in registers (requested at the end of a step, stored at the top of the next) ----
+  // Thread (row r4s = tid >> 2, lane q4s = tid & 3) stages chunks q4s, q4s + 4, ... of ITS row: one index load and one
+  // 32 x 32 -> 64 multiply-add per tile give the row address, every chunk is an immediate offset from it (the first version
+  // spread the chunks of a row over the CTA: a divide / index load / address multiply per item, 140 instructions per warp).
   constexpr int PF_MAX = 4 * NT1;
   const bool vec_rows = (D & 3) == 0;
-  int pf_rc[PF_MAX];
-  int pf_n = 0;
-#pragma unroll
-  for (int it = 0; it < PF_MAX; ++it) {
-    const int i = tid + it * UT, per_row = D >> 2;
-    pf_rc[it] = 0xFF;
-    if (vec_rows && i < SPO_ROWS * per_row) { pf_rc[it] = (i / per_row) | ((i % per_row) << 8); pf_n = it + 1; }
-  }
   float xr[4 * PF_MAX];
 #pragma unroll
   for (int i = 0; i < 4 * PF_MAX; ++i) xr[i] = 0.f;
@@ -524,23 +519,24 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     // multiply-add per address
     const uint32_t* ridx = reinterpret_cast<const uint32_t*>(idxbuf + (qt & 1) * SPO_ROWS);
     const uint32_t Du = static_cast<uint32_t>(D);
+    const bool rv = r4s < rows;
+    const uint32_t g = rv ? ridx[2 * r4s] : 0u;
+    const float* rowp = a.data.obs + static_cast<size_t>(g) * Du;
     if (vec_rows) {
 #pragma unroll
       for (int it = 0; it < PF_MAX; ++it) {
-        const int r = pf_rc[it] & 0xFF, c = pf_rc[it] >> 8;
+        const int c = q4s + 4 * it;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (it < pf_n && r < rows) v = __ldg(reinterpret_cast<const float4*>(a.data.obs + static_cast<size_t>(ridx[2 * r]) * Du) + c);
+        if (rv && 4 * c < D) v = __ldg(reinterpret_cast<const float4*>(rowp) + c);
         xr[4 * it] = v.x; xr[4 * it + 1] = v.y; xr[4 * it + 2] = v.z; xr[4 * it + 3] = v.w;
       }
     } else {
 #pragma unroll
       for (int it = 0; it < 4 * PF_MAX; ++it) {
-        const int i = tid + it * UT, r = i / D, c = i - r * D;
-        xr[it] = (r < rows) ? __ldg(a.data.obs + static_cast<size_t>(ridx[2 * r]) * Du + c) : 0.f;
+        const int c = q4s + 4 * it;
+        xr[it] = (rv && c < D) ? __ldg(rowp + c) : 0.f;
       }
     }
-    const bool rv = r4s < rows;
-    const uint32_t g = rv ? ridx[2 * r4s] : 0u;
     auxr[0] = (rv && q4s < aux_per) ? __ldg(aux_src0 + static_cast<size_t>(g) * static_cast<uint32_t>(aux_mul0)) : 0.f;
     if (aux_per > 4) {
 #pragma unroll
@@ -557,14 +553,14 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     if (vec_rows) {
 #pragma unroll
       for (int it = 0; it < PF_MAX; ++it) {
-        const int r = pf_rc[it] & 0xFF, c = pf_rc[it] >> 8;
-        if (it < pf_n) *reinterpret_cast<float4*>(x + r * ldx + 4 * c) = make_float4(xr[4 * it], xr[4 * it + 1], xr[4 * it + 2], xr[4 * it + 3]);
+        const int c = q4s + 4 * it;
+        if (4 * c < D) *reinterpret_cast<float4*>(x + r4s * ldx + 4 * c) = make_float4(xr[4 * it], xr[4 * it + 1], xr[4 * it + 2], xr[4 * it + 3]);
       }
     } else {
 #pragma unroll
       for (int it = 0; it < 4 * PF_MAX; ++it) {
-        const int i = tid + it * UT, r = i / D, c = i - r * D;
-        if (r < SPO_ROWS) x[r * ldx + c] = xr[it];
+        const int c = q4s + 4 * it;
+        if (c < D) x[r4s * ldx + c] = xr[it];
       }
     }
     if (q4s < aux_per) aux[r4s * AUXW + aux_slot0] = auxr[0];

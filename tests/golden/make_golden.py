@@ -364,12 +364,66 @@ def gen_ma_gae(ref, out):
     out["ma_gae"] = cases
 
 
+def gen_ma_update(ref, out):
+    """MAPPO-Lag networks and two consecutive ppo_update calls through the reference's own MAPPO_L_Policy /
+    MAPPO_L_Trainer (safepo/multi_agent/mappolag.py:46-199) at small dimensions (obs 10, share_obs 14, act 3, hidden 32,
+    the yaml's layer_N = 2): initial state dicts, get_actions outputs (deterministic and sampled under a fixed seed), the
+    sample, and after each update the returned scalars, lamda_lagr, the PopArt state and all three state dicts."""
+    import yaml
+    m = importlib.import_module("safepo.multi_agent.mappolag")
+    cfg = yaml.safe_load(open(os.path.join(REF, "safepo", "multi_agent", "marl_cfg", "mappolag", "config.yaml")))
+    cfg.update(device="cpu", algorithm_name="mappolag", n_rollout_threads=4, hidden_size=32)
+
+    class Sp:
+        def __init__(self, d):
+            self.shape = (d,)
+
+    torch.manual_seed(11)
+    D, DS, A, N = 10, 14, 3, 24
+    pol = m.MAPPO_L_Policy(cfg, Sp(D), Sp(DS), Sp(A))
+    with torch.no_grad():       # move the LayerNorm affine parameters and biases off their trivial initial values
+        for net in (pol.actor, pol.critic, pol.cost_critic):
+            for k, v in net.state_dict().items():
+                if k.endswith("bias") or ".2.weight" in k or "feature_norm" in k or k.endswith("log_std"):
+                    v.add_(0.1 * torch.randn_like(v))
+    tr = m.MAPPO_L_Trainer(cfg, pol)
+    g = torch.Generator().manual_seed(12)
+    obs, share = torch.randn(N, D, generator=g) * 2 + 0.5, torch.randn(N, DS, generator=g) * 3
+    rnn, masks = np.zeros((N, 1, 32), dtype=np.float32), np.ones((N, 1), dtype=np.float32)
+    init_state = {n: {k: v.clone() for k, v in getattr(pol, n).state_dict().items()} for n in ("actor", "critic", "cost_critic")}
+    with torch.no_grad():
+        det = pol.get_actions(share, obs, rnn, rnn, masks, deterministic=True, rnn_states_cost=rnn)
+        torch.manual_seed(99)
+        smp = pol.get_actions(share, obs, rnn, rnn, masks, deterministic=False, rnn_states_cost=rnn)
+    acts = {"det": dict(values=det[0], actions=det[1], logp=det[2], cost=det[5]),
+            "sampled": dict(values=smp[0], actions=smp[1], logp=smp[2], cost=smp[5], seed=99)}
+    sample = dict(share_obs=share, obs=obs, actions=smp[1].clone(), value_preds=det[0].clone() + 0.1 * torch.randn(N, 1, generator=g),
+                  returns=torch.randn(N, 1, generator=g) * 4 + 1, old_action_log_probs=smp[2].clone() + 0.05 * torch.randn(N, A, generator=g),
+                  adv_targ=torch.randn(N, 1, generator=g), factor=torch.rand(N, 1, generator=g) + 0.5,
+                  cost_preds=det[5].clone() + 0.1 * torch.randn(N, 1, generator=g), cost_returns=torch.randn(N, 1, generator=g).abs() * 30,
+                  cost_adv_targ=torch.randn(N, 1, generator=g), aver_episode_costs=torch.rand(N, 1, generator=g) * 60)
+    steps = []
+    for _ in range(2):
+        tup = (sample["share_obs"].numpy(), sample["obs"].numpy(), rnn, rnn, sample["actions"].numpy(), sample["value_preds"],
+               sample["returns"], masks, masks, sample["old_action_log_probs"], sample["adv_targ"], None, sample["factor"],
+               sample["cost_preds"], sample["cost_returns"], rnn, sample["cost_adv_targ"], sample["aver_episode_costs"])
+        r = tr.ppo_update(tup)
+        names = ("value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "imp_weights", "cost_loss", "cost_grad_norm")
+        vn = tr.value_normalizer
+        steps.append(dict(out={k: v.detach().clone() for k, v in zip(names, r)}, lamda_lagr=torch.as_tensor(tr.lamda_lagr).clone(),
+                          popart=(vn.running_mean.clone(), vn.running_mean_sq.clone(), vn.debiasing_term.clone()),
+                          state={n: {k: v.clone() for k, v in getattr(pol, n).state_dict().items()} for n in ("actor", "critic", "cost_critic")}))
+    keep = ("actor_lr", "critic_lr", "opti_eps", "weight_decay", "clip_param", "huber_delta", "entropy_coef", "max_grad_norm", "cost_limit",
+            "gamma", "lagrangian_coef_rate", "value_loss_coef", "lamda_lagr", "layer_N", "std_x_coef", "std_y_coef")
+    out["ma_update"] = dict(cfg={k: cfg[k] for k in keep}, dims=(D, DS, A, N), init=init_state, actions=acts, sample=sample, steps=steps)
+
+
 def main():
     sys.path.insert(0, ROOT)
     ref = import_reference()
     only = set(sys.argv[1:])      # e.g. `python make_golden.py siblings` regenerates one fixture
     for name, fn in (("forward", gen_forward), ("gae", gen_gae), ("lagrange", gen_lagrange), ("update", gen_update_chain),
-                     ("dataloader", gen_dataloader), ("trust", gen_trust), ("main_runs", gen_main_runs), ("siblings", gen_siblings), ("ma_gae", gen_ma_gae)):
+                     ("dataloader", gen_dataloader), ("trust", gen_trust), ("main_runs", gen_main_runs), ("siblings", gen_siblings), ("ma_gae", gen_ma_gae), ("ma_update", gen_ma_update)):
         if only and name not in only:
             continue
         out = {}

@@ -211,3 +211,31 @@ def test_masked_gae_with_popart_matches_reference(golden):
         cret = MA.masked_gae(c["costs"], c["cost_preds"], c["masks"], pop, c["gamma"], c["lam"])
         assert torch.equal(ret, c["returns"][:-1]) and torch.equal(cret, c["cost_returns"][:-1]), (c["T"], c["N"])
         assert float(c["returns"][-1].abs().max()) == 0.0      # the reference's extra row stays zero
+
+
+def test_ma_networks_and_ppo_update_match_reference(golden):
+    """SURVEY 8f rank 3 (config 5, first slice): the oracle's MAPPO-Lag networks and ppo_update against the reference's
+    own MAPPO_L_Policy / MAPPO_L_Trainer (mappolag.py:46-199): get_actions (deterministic and sampled under the same seed)
+    and two consecutive updates -- every returned scalar, lamda_lagr, the PopArt state and all weights, bit for bit."""
+    from oracle import ma_oracle as MA
+    c = golden("ma_update")["ma_update"]
+    cfg, s = c["cfg"], c["sample"]
+    nets = {n: MA.OracleMANet(c["init"][n], layer_N=cfg["layer_N"]) for n in ("actor", "critic", "cost_critic")}
+    v, a, lp, k = MA.ma_get_actions(nets["actor"], nets["critic"], nets["cost_critic"], s["share_obs"], s["obs"], deterministic=True)
+    d = c["actions"]["det"]
+    assert torch.equal(v, d["values"]) and torch.equal(a, d["actions"]) and torch.equal(lp, d["logp"]) and torch.equal(k, d["cost"])
+    torch.manual_seed(c["actions"]["sampled"]["seed"])
+    v, a, lp, k = MA.ma_get_actions(nets["actor"], nets["critic"], nets["cost_critic"], s["share_obs"], s["obs"])
+    d = c["actions"]["sampled"]
+    assert torch.equal(a, d["actions"]) and torch.equal(lp, d["logp"]) and lp.shape == (c["dims"][3], c["dims"][2])   # per-dimension log-probs
+    tr = MA.OracleMATrainer(nets["actor"], nets["critic"], nets["cost_critic"], cfg)
+    for step in c["steps"]:
+        out = tr.ppo_update(s)
+        for name, want in step["out"].items():
+            assert torch.equal(torch.as_tensor(out[name]), want), (name, out[name], want)
+        assert torch.equal(torch.as_tensor(tr.lamda_lagr), step["lamda_lagr"])
+        for got, want in zip((tr.popart.running_mean, tr.popart.running_mean_sq, tr.popart.debiasing_term), step["popart"]):
+            assert torch.equal(got, want)
+        for n in ("actor", "critic", "cost_critic"):
+            for key, want in step["state"][n].items():
+                assert torch.equal(nets[n].p[key].detach(), want), (n, key)
