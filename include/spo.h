@@ -288,6 +288,19 @@ int spo_conjugate_gradient(const spo_dims* d, const float* params, const float* 
 int spo_cg_begin(const spo_dims* d, const float* b, float* x, float* work, void* stream);
 int spo_cg_update(const spo_dims* d, float* x, float* work, float residual_tol, float eps, void* stream);
 
+/* ---- multi-agent nets (MAPPO-Lag, BASELINE config 5; SURVEY section 8f rank 3, first slice: FORWARD only) ----
+ * spo_ma_mlp_layer: one [Linear -> ELU -> LayerNorm] block of MLPLayer (safepo/utils/mlp.py:18-27), optionally preceded by
+ *   the input LayerNorm of MLPBase (feature_norm, mlp.py:46-47,57-58): out[n][H] = LN_out(ELU(LN_in?(in)[n][K] W[H][K]^T + b)).
+ *   K even, H a multiple of 128 up to 512; all pointers device fp32 (in / W 8-byte, out 16-byte aligned).
+ * spo_ma_head: the output layer on the features, one warp per row.  log_std == NULL: plain Linear (v_out of
+ *   MultiAgentCritic, model.py:330,361).  Otherwise the DiagGaussian head (distributions.py:38-42, act.py:37-43):
+ *   std = sigmoid(log_std / std_x_coef) * std_y_coef, action = mean + std * eps (eps [n][O] device, NULL = the mode), and the
+ *   per-dimension log-probabilities logp [n][O] (may be NULL). */
+int spo_ma_mlp_layer(const float* in, int n, int K, const float* W, const float* b, const float* ln_w, const float* ln_b, int H,
+                     const float* ln_in_w, const float* ln_in_b, float* out, void* stream);
+int spo_ma_head(const float* feat, int n, int H, const float* W, const float* b, int O, const float* log_std, float std_x_coef,
+                float std_y_coef, const float* eps, float* out, float* logp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

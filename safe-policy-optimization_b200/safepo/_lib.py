@@ -104,6 +104,8 @@ def _declare(L):
         "spo_fvp": [PD, p, p, i64, p, f, p, p],
         "spo_linesearch_eval": [PD, p, p, p, p, p, p, p, p, i64, p, p],
         "spo_conjugate_gradient": [PD, p, p, i64, p, i, f, f, f, p, p, p],
+        "spo_ma_mlp_layer": [p, i, i, p, p, p, p, i, p, p, p, p],
+        "spo_ma_head": [p, i, i, p, p, i, p, f, f, p, p, p, p],
         "spo_cg_begin": [PD, p, p, p, p],
         "spo_cg_update": [PD, p, p, f, f, p],
         "spo_obs_normalize": [p, i, i, p, p, d, p, i, d, p, p],
@@ -121,7 +123,7 @@ EXPORTS = ("spo_version", "spo_last_error", "spo_sync_check", "spo_param_count",
            "spo_adv_apply", "spo_pg_update", "spo_actor_forward", "spo_actor_kl", "spo_surrogate_grad", "spo_fvp",
            "spo_linesearch_eval", "spo_conjugate_gradient", "spo_comm_slot_floats", "spo_pg_update_dp", "spo_comm_alloc",
            "spo_comm_free", "spo_comm_export", "spo_comm_import", "spo_comm_close", "spo_actor_kl_accumulate", "spo_kl_finalize",
-           "spo_obs_normalize", "spo_action_rescale", "spo_gae_masked", "spo_cg_begin", "spo_cg_update")
+           "spo_obs_normalize", "spo_action_rescale", "spo_gae_masked", "spo_cg_begin", "spo_cg_update", "spo_ma_mlp_layer", "spo_ma_head")
 
 
 # number of libspo kernels launched so far (bench.py reports the delta over its timed region)
@@ -129,7 +131,7 @@ LAUNCHES = {"n": 0}
 _KERNEL_CALLS = {"spo_policy_step", "spo_critic_values", "spo_store_transition", "spo_gae_dual", "spo_adv_stats",
                  "spo_adv_apply", "spo_pg_update", "spo_actor_forward", "spo_actor_kl", "spo_surrogate_grad", "spo_fvp",
                  "spo_linesearch_eval", "spo_pg_update_dp", "spo_actor_kl_accumulate", "spo_kl_finalize", "spo_obs_normalize",
-                 "spo_action_rescale", "spo_gae_masked", "spo_cg_begin", "spo_cg_update"}
+                 "spo_action_rescale", "spo_gae_masked", "spo_cg_begin", "spo_cg_update", "spo_ma_mlp_layer", "spo_ma_head"}
 
 
 def check(rc, what):

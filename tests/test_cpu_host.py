@@ -231,6 +231,9 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_device():
     assert lib.spo_obs_normalize(None, 4, 3, None, None, 1.0, None, 1, 1e-8, None, None) != OK
     assert lib.spo_action_rescale(None, 4, 3, None, None, -1.0, 1.0, None, None) != OK
     assert lib.spo_gae_masked(None, None, None, 0.0, 1.0, 0.96, 0.9, None, 4, 8, None) != OK and b"spo_gae_masked" in lib.spo_last_error()
+    assert lib.spo_ma_mlp_layer(None, 4, 10, None, None, None, None, 128, None, None, None, None) != OK and b"spo_ma_mlp_layer" in lib.spo_last_error()
+    assert lib.spo_ma_head(None, 4, 128, None, None, 3, None, 1.0, 0.5, None, None, None, None) != OK
+    assert lib.spo_cg_begin(C.byref(d), None, None, None, None) != OK and lib.spo_cg_update(C.byref(d), None, None, 1e-10, 1e-6, None) != OK
     assert lib.spo_actor_forward(C.byref(d), None, None, 0, None, None) != OK
     assert lib.spo_fvp(C.byref(d), None, None, 0, None, 0.1, None, None) != OK
 

@@ -771,3 +771,56 @@ def test_masked_gae_bit_exact_vs_oracle(T, N):
     want = MA.masked_gae(rew, vp, masks, pop, 0.96, 0.95)
     got = masked_gae_returns(rew.to(dev), vp.to(dev), masks.to(dev), float(mean), float(sqrt_var), 0.96, 0.95).cpu()
     assert torch.equal(got, want), float((got - want).abs().max())
+
+
+# ---- SURVEY 8f rank 3, first slice: multi-agent nets, forward (MAPPO_L_Policy.get_actions) against the pinned oracle
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,D,DS,A,H", [(24, 10, 14, 3, 128), (8192, 398, 398, 20, 512), (77, 66, 130, 5, 256)])
+def test_ma_get_actions_vs_oracle(N, D, DS, A, H):
+    """spo_ma_mlp_layer / spo_ma_head through safepo.common.ma_model.MultiAgentNets against oracle/ma_oracle.py (pinned bit for
+    bit to the reference's MAPPO_L_Policy, tests/golden/ma_update.pt); the middle case is config 5's shape
+    (ShadowHandOver: obs 398, act 20, hidden 512, 8192 envs).  1e-5 relative on values / actions / per-dimension log-probs."""
+    from oracle import ma_oracle as MA
+    from safepo.common.ma_model import MultiAgentNets
+    dev = _cuda()
+    g = torch.Generator().manual_seed(N + D)
+
+    def make(din, head):
+        st = {"base.feature_norm.weight": 1 + 0.1 * torch.randn(din, generator=g), "base.feature_norm.bias": 0.1 * torch.randn(din, generator=g)}
+        dims = [din, H, H, H]
+        for li, name in enumerate(("fc1", "fc2.0", "fc2.1")):
+            st[f"base.mlp.{name}.0.weight"] = torch.randn(H, dims[li], generator=g) * (1.4 / dims[li] ** 0.5)
+            st[f"base.mlp.{name}.0.bias"] = 0.1 * torch.randn(H, generator=g)
+            st[f"base.mlp.{name}.2.weight"] = 1 + 0.1 * torch.randn(H, generator=g)
+            st[f"base.mlp.{name}.2.bias"] = 0.1 * torch.randn(H, generator=g)
+        if head == "actor":
+            st["act.action_out.log_std"] = torch.ones(A) + 0.3 * torch.randn(A, generator=g)
+            st["act.action_out.fc_mean.weight"] = torch.randn(A, H, generator=g) * 0.05
+            st["act.action_out.fc_mean.bias"] = 0.1 * torch.randn(A, generator=g)
+        else:
+            st["v_out.weight"] = torch.randn(1, H, generator=g) * 0.1
+            st["v_out.bias"] = 0.1 * torch.randn(1, generator=g)
+        return st
+
+    sa, sc, sk = make(D, "actor"), make(DS, "critic"), make(DS, "critic")
+    obs, cent = torch.randn(N, D, generator=g) * 2 + 0.3, torch.randn(N, DS, generator=g) * 3
+    eps = torch.randn(N, A, generator=g)
+    nets = MultiAgentNets(sa, sc, sk, dev)
+    oa, oc, ok_ = MA.OracleMANet(sa), MA.OracleMANet(sc), MA.OracleMANet(sk)
+    with torch.no_grad():
+        dist = MA.ma_actor_dist(oa, obs)
+        want_act = dist.mean + dist.stddev * eps
+        want = (MA.ma_critic_value(oc, cent), want_act, dist.log_prob(want_act), MA.ma_critic_value(ok_, cent))
+        want_det = (dist.mean, dist.log_prob(dist.mean))
+    got = nets.get_actions(cent.to(dev), obs.to(dev), eps=eps.to(dev))
+    # three 398/512-wide fp32 layers, each followed by a LayerNorm: the reordering noise of two fp32 implementations is ~1e-6
+    # per element and a few 1e-6 at the maximum over N x 512 activations (printed; measured on B200 in profiles/r02_ma_forward.txt)
+    worst = {}
+    for name, a_, b_ in zip(("values", "actions", "logp", "cost"), got, want):
+        ok, ea, er = close(a_, b_, rtol=2e-5, atol=1e-5)
+        worst[name] = (ea, float((a_.cpu() - b_).abs().mean()))
+        assert ok, (name, N, D, H, ea, er)
+    print(f"\nMA get_actions N={N} D={D} H={H}: max / mean |err| " + ", ".join(f"{k} {v[0]:.2e} / {v[1]:.2e}" for k, v in worst.items()))
+    gd = nets.get_actions(cent.to(dev), obs.to(dev), deterministic=True)
+    assert close(gd[1], want_det[0], rtol=2e-5, atol=1e-5)[0] and close(gd[2], want_det[1], rtol=2e-5, atol=1e-5)[0]
+    assert gd[2].shape == (N, A)          # log-probs stay per action dimension (distributions.py:8-9)
