@@ -220,6 +220,8 @@ def test_ma_networks_and_ppo_update_match_reference(golden):
     from oracle import ma_oracle as MA
     c = golden("ma_update")["ma_update"]
     cfg, s = c["cfg"], c["sample"]
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)        # like the fixture: LayerNorm's backward reductions depend on the intra-op thread count in the last bit
     nets = {n: MA.OracleMANet(c["init"][n], layer_N=cfg["layer_N"]) for n in ("actor", "critic", "cost_critic")}
     v, a, lp, k = MA.ma_get_actions(nets["actor"], nets["critic"], nets["cost_critic"], s["share_obs"], s["obs"], deterministic=True)
     d = c["actions"]["det"]
@@ -239,3 +241,4 @@ def test_ma_networks_and_ppo_update_match_reference(golden):
         for n in ("actor", "critic", "cost_critic"):
             for key, want in step["state"][n].items():
                 assert torch.equal(nets[n].p[key].detach(), want), (n, key)
+    torch.set_num_threads(threads)
