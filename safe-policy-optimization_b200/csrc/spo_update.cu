@@ -1369,11 +1369,6 @@ extern "C" int spo_debug_phase_cycles(unsigned long long* out_16x24, int reset) 
 }
 #endif
 
-extern "C" int spo_pg_update_v1_dp(const spo_dims* d, float* params, float* adam_m, float* adam_v, int* adam_t,
-                                   const spo_batch* data, const int64_t* perm, int64_t perm_len, int batch,
-                                   spo_loss_kind kind, const spo_hparams* hp, spo_update_ctrl* ctrl,
-                                   const spo_comm* comm, void* stream);
-
 extern "C" int spo_comm_slot_floats(const spo_dims* d, int* slot_floats) {
   int rc = spo_check_dims(d);
   if (rc) return rc;
@@ -1406,10 +1401,6 @@ extern "C" int spo_pg_update_dp(const spo_dims* d, float* params, float* adam_m,
   if (kind == SPO_LOSS_FOCOPS || kind == SPO_LOSS_CUP_PROJECTION) {
     SPO_REQUIRE(data->old_mean && data->old_std, SPO_ERR_INVALID_ARG, "spo_pg_update: FOCOPS needs old_mean/old_std");
     SPO_REQUIRE(batch <= SPO_ROWS, SPO_ERR_UNSUPPORTED, "spo_pg_update: FOCOPS supports batch <= %d (got %d)", SPO_ROWS, batch);
-  }
-  {
-    const char* v1 = getenv("SPO_UPDATE_V1");   // development only: the round-1 kernel (one CTA per net), for A/B runs
-    if (v1 && v1[0] == '1') return spo_pg_update_v1_dp(d, params, adam_m, adam_v, adam_t, data, perm, perm_len, batch, kind, hp, ctrl, comm, stream);
   }
   UpdArgs a{};
   a.params = params; a.adam_m = adam_m; a.adam_v = adam_v; a.adam_t = adam_t;
