@@ -379,6 +379,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
   float* dh1b = p; p += NQ * H1Q;                 // own partial of dh1 as [destination quarter][64][16]: block d is pushed to CTA d
   float* dh1in = p; p += NQ * H1Q;                // [source quarter][64][16]: the partials the three peers pushed for the own columns
   float* red = p; p += 64;                        // block-reduction scratch
+  float* bk = p;  p += 3 * (4 * (1 + NT1) + 1) * UT;   // (theta, m, v) of this thread's parameters before a speculative Adam step
   float* xin = p; p += 2 * 16 * 4;                // [parity][source CTA]{sum g^2, sum theta^2, -, -}: own entry written here, 11 pushed in
   float* dz1s = h2s;
   float* b1s = sp + SP_B1; float* b2s = sp + SP_B2; float* w3s = sp + SP_W3; float* b3 = sp + SP_B3; float* log_std = sp + SP_LS;
@@ -633,6 +634,164 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     return;
   }
 
+  // ---- pieces of the step that run at two places (speculative Adam, see the end of the step) ----
+  bool pending = false;      // the norms of the last finished step have been pushed but not yet checked
+  int pend_par = 0;
+  float pend_inv_b = 0.f;
+  // The step barrier = the all-to-all of (sum g^2, sum theta^2): every CTA pushes 16 bytes to each of the other 11 and waits
+  // for 11 x 16 bytes on its own mbarrier.  A CTA pushes only after its last read of any exchanged buffer and checks the norms
+  // before it pushes anything of the next step, so nobody can overwrite h1 / the partial-output blocks / the dh1 slots of a
+  // CTA that still reads them.
+  auto step_barrier_push = [&](int par, float ssq, float t2) {
+    float* mine = xin + (par * 16 + static_cast<int>(rank)) * 4;
+    if (tid == 0) { *reinterpret_cast<float4*>(mine) = make_float4(ssq, t2, 0.f, 0.f); fence_proxy_async(); }
+    __syncthreads();
+    // one lane of every warp issues (a bulk copy is a uniform-datapath instruction: eleven from one warp go one after the other)
+    if (lane == 0)
+      for (int p = wid; p < NCTA; p += UT / 32)
+        if (p != static_cast<int>(rank)) bulk_push(mapa(smem_u32(mine), p), mine, 16, mapa(smem_u32(&bar_ss[tcount & 1u]), p));
+  };
+  auto step_barrier_wait = [&]() {
+    uint64_t* bar = &bar_ss[tcount & 1u];
+    mbar_wait(bar, (tcount >> 1) & 1u);
+    if (tid == 0) mbar_expect_tx(bar, (NCTA - 1) * 16);
+    ++tcount;
+  };
+  // layer 1 of the forward: own 16 units of h1 into the own (swizzled) slice block
+  auto layer1 = [&]() {
+    float acc[1][4];
+    warp_gemm_kk<8 * NT1>(acc, x, ldx, w1s, ldx, mt * 16, ntl * 8);
+    const float2 bb = *reinterpret_cast<const float2*>(b1s + cA);
+    const int cs = cA ^ (((rA >> 1) & 1) << 3);     // swizzled column inside the own slice block (rows rA and rA + 8 alike)
+    *reinterpret_cast<float2*>(h1 + q * H1Q + rA * SL + cs) = make_float2(spo_tanh_fast(acc[0][0] + bb.x), spo_tanh_fast(acc[0][1] + bb.y));
+    *reinterpret_cast<float2*>(h1 + q * H1Q + (rA + 8) * SL + cs) = make_float2(spo_tanh_fast(acc[0][2] + bb.x), spo_tanh_fast(acc[0][3] + bb.y));
+    fence_proxy_async();                            // the slice is read by the bulk-copy engine next
+  };
+  // the twelve (sum g^2, sum theta^2) pairs of a finished step -> logged loss (thread 0 of quarter 0) and the clip coefficient
+  auto resolve_norms = [&](int par, float inv_b) -> float {
+    float total = 0.f, t2net = 0.f;
+#pragma unroll
+    for (int b = 0; b < NCTA; ++b) {      // every thread adds them in CTA order from its own shared memory
+      const float2 v = *reinterpret_cast<const float2*>(xin + (par * 16 + b) * 4);
+      total += v.x;
+      if (b / NQ == net) t2net += v.y;
+    }
+    if (tid == 0 && q == 0 && active) {
+      // logged loss of the step (ppo_lag.py:330-336): critics include the L2 term over the whole net
+      float L;
+      if (!is_actor) L = fmaf(a.hp.critic_l2, t2net, __fmul_rn(step_loss, inv_b));
+      else if (a.kind == SPO_LOSS_PPO_CLIP) L = __fmul_rn(step_loss, inv_b);
+      else L = __fsub_rn(__fmul_rn(step_loss, inv_b),
+                         __fmul_rn(__fmul_rn(__fdiv_rn(1.f, a.hp.focops_lam), __fmul_rn(step_aux0, inv_b)), __fmul_rn(step_aux1, inv_b)));
+      acc_loss += static_cast<double>(L);
+    }
+    if (tid == 0) { step_loss = 0.f; step_aux0 = 0.f; step_aux1 = 0.f; }
+    // clip coefficient max_norm / (norm + 1e-6), capped at 1 (SFU sqrt and division: <= 2 ulp, exactly 1 below the limit)
+    return fminf(__fdividef(a.hp.max_grad_norm, __fadd_rn(sqrt_approx(total), 1e-6f)), 1.f);
+  };
+  constexpr int NWB = 4 * (1 + NT1) + 1;     // parameters per thread: 4 of W2, 4 per block of W1, one small
+  // Adam on this thread's parameters.  All loads first, then the arithmetic, then all stores: shared-memory loads cannot be moved
+  // across possibly aliasing stores by the compiler, which would serialise twelve load -> sqrt -> rcp -> store chains per thread.
+  // save: (theta, m, v) go to the backup area first (speculative step).
+  auto adam_apply = [&](float clip, bool save) {
+    AdamK k;
+    k.w1 = adk[0]; k.b2 = adk[1]; k.w2 = adk[2]; k.ibc2s = adk[3]; k.eps = adk[4]; k.ss = adk[5];
+    float2 w2v[2];
+    float w1v[NT1][4];
+    float spv = 0.f, spg = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; e += 2) {
+      int j, kc;
+      frag_jk(e, wid, j, kc);
+      w2v[e >> 1] = *reinterpret_cast<const float2*>(w2s + j * LDA + kc);
+#pragma unroll
+      for (int i = 0; i < NT1; ++i) {
+        frag_jk(e, wid + 8 * i, j, kc);
+        const float2 t = *reinterpret_cast<const float2*>(w1s + j * ldx + kc);   // columns >= D are zero padding
+        w1v[i][e] = t.x; w1v[i][e + 1] = t.y;
+      }
+    }
+    if (tid < SPN) { spv = sp[tid]; spg = gsmall[tid]; }
+    if (save) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        bk[(0 * NWB + e) * UT + tid] = (e & 1) ? w2v[e >> 1].y : w2v[e >> 1].x;
+        bk[(1 * NWB + e) * UT + tid] = mW2[e];
+        bk[(2 * NWB + e) * UT + tid] = vW2[e];
+#pragma unroll
+        for (int i = 0; i < NT1; ++i) {
+          bk[(0 * NWB + 4 * (1 + i) + e) * UT + tid] = w1v[i][e];
+          bk[(1 * NWB + 4 * (1 + i) + e) * UT + tid] = mW1[i][e];
+          bk[(2 * NWB + 4 * (1 + i) + e) * UT + tid] = vW1[i][e];
+        }
+      }
+      bk[(0 * NWB + NWB - 1) * UT + tid] = spv;
+      bk[(1 * NWB + NWB - 1) * UT + tid] = sp_m;
+      bk[(2 * NWB + NWB - 1) * UT + tid] = sp_v;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e += 2) {
+      w2v[e >> 1].x = adam_update(w2v[e >> 1].x, __fmul_rn(gW2[0][e], clip), mW2[e], vW2[e], k);
+      w2v[e >> 1].y = adam_update(w2v[e >> 1].y, __fmul_rn(gW2[0][e + 1], clip), mW2[e + 1], vW2[e + 1], k);
+#pragma unroll
+      for (int i = 0; i < NT1; ++i) {
+        // padded columns (kc >= D): gradient 0, moments 0 -> the update is exactly 0, the padding stays 0
+        w1v[i][e] = adam_update(w1v[i][e], __fmul_rn(gW1[i][e], clip), mW1[i][e], vW1[i][e], k);
+        w1v[i][e + 1] = adam_update(w1v[i][e + 1], __fmul_rn(gW1[i][e + 1], clip), mW1[i][e + 1], vW1[i][e + 1], k);
+      }
+    }
+    if (tid < SPN && sp_valid) spv = adam_update(spv, __fmul_rn(spg, clip), sp_m, sp_v, k);
+#pragma unroll
+    for (int e = 0; e < 4; e += 2) {
+      int j, kc;
+      frag_jk(e, wid, j, kc);
+      *reinterpret_cast<float2*>(w2s + j * LDA + kc) = w2v[e >> 1];
+#pragma unroll
+      for (int i = 0; i < NT1; ++i) {
+        frag_jk(e, wid + 8 * i, j, kc);
+        *reinterpret_cast<float2*>(w1s + j * ldx + kc) = make_float2(w1v[i][e], w1v[i][e + 1]);
+      }
+    }
+    if (tid < SPN) sp[tid] = spv;
+  };
+  // undo a speculative step: weights back into shared memory, moments back into the registers
+  auto adam_restore = [&]() {
+#pragma unroll
+    for (int e = 0; e < 4; e += 2) {
+      int j, kc;
+      frag_jk(e, wid, j, kc);
+      *reinterpret_cast<float2*>(w2s + j * LDA + kc) = make_float2(bk[(0 * NWB + e) * UT + tid], bk[(0 * NWB + e + 1) * UT + tid]);
+#pragma unroll
+      for (int i = 0; i < NT1; ++i) {
+        frag_jk(e, wid + 8 * i, j, kc);
+        *reinterpret_cast<float2*>(w1s + j * ldx + kc) =
+            make_float2(bk[(0 * NWB + 4 * (1 + i) + e) * UT + tid], bk[(0 * NWB + 4 * (1 + i) + e + 1) * UT + tid]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      mW2[e] = bk[(1 * NWB + e) * UT + tid];
+      vW2[e] = bk[(2 * NWB + e) * UT + tid];
+#pragma unroll
+      for (int i = 0; i < NT1; ++i) {
+        mW1[i][e] = bk[(1 * NWB + 4 * (1 + i) + e) * UT + tid];
+        vW1[i][e] = bk[(2 * NWB + 4 * (1 + i) + e) * UT + tid];
+      }
+    }
+    if (tid < SPN) sp[tid] = bk[(0 * NWB + NWB - 1) * UT + tid];
+    sp_m = bk[(1 * NWB + NWB - 1) * UT + tid];
+    sp_v = bk[(2 * NWB + NWB - 1) * UT + tid];
+  };
+  auto clear_grads = [&]() {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      gW2[0][e] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NT1; ++i) gW1[i][e] = 0.f;
+    }
+    if (tid < SPN) gsmall[tid] = 0.f;
+  };
+
   int64_t step = 0;
   int sub = 0;
   auto next_tile = [&]() { if (++sub == tps) { sub = 0; ++step; } };
@@ -788,25 +947,44 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
 
     store_next();      // tile qt: registers -> shared memory (every warp left tile qt-1 before the last barrier)
     __syncthreads();   // tile qt in place; Adam's weight writes visible
-    if (is_actor && active && tid >= UT - 32 && tid - (UT - 32) < A) {
-      // row-independent pieces of the Gaussian log-density (log_std changed in the last Adam step)
-      const int j = tid - (UT - 32);
-      const float sd = expf(log_std[j]);
-      lsc[4 * j + 0] = sd;
-      lsc[4 * j + 1] = __fdiv_rn(1.f, __fmul_rn(sd, sd));
-      lsc[4 * j + 2] = logf(sd);
-    }
     PHASE_MARK(0);   // top of the step: stage-in + barrier
 
     // ---------------- forward, layer 1: own 16 units ----------------
+    if (active) layer1();
+    PHASE_MARK(2);   // layer-1 product + tanh
+    // The norms of the PREVIOUS step have been travelling since its end (SPECULATION, see the end of the step): Adam already
+    // ran with clip = 1.  Now, before anything of this step leaves the CTA, check them.
+    if (pending) {
+      pending = false;
+      step_barrier_wait();
+      PHASE_MARK(9);   // wait for the previous step's norms
+      const float clip = resolve_norms(pend_par, pend_inv_b);
+      if (active) {
+        if (clip < 1.f) {          // rare: the joint norm exceeded max_grad_norm -- undo, redo with the clip, redo layer 1
+          __syncthreads();
+          adam_restore();
+          adam_apply(clip, false);
+          __syncthreads();
+          layer1();
+        }
+        clear_grads();
+      }
+    }
+    PHASE_MARK(1);   // layer-1 product + epilogue
+    float yv[SPO_MAX_ACT];                            // output-layer rows of this thread's row r4 (after the y exchange)
     if (active) {
-      float acc[1][4];
-      warp_gemm_kk<8 * NT1>(acc, x, ldx, w1s, ldx, mt * 16, ntl * 8);
-      const float2 bb = *reinterpret_cast<const float2*>(b1s + cA);
-      const int cs = cA ^ (((rA >> 1) & 1) << 3);     // swizzled column inside the own slice block (rows rA and rA + 8 alike)
-      *reinterpret_cast<float2*>(h1 + q * H1Q + rA * SL + cs) = make_float2(spo_tanh_fast(acc[0][0] + bb.x), spo_tanh_fast(acc[0][1] + bb.y));
-      *reinterpret_cast<float2*>(h1 + q * H1Q + (rA + 8) * SL + cs) = make_float2(spo_tanh_fast(acc[0][2] + bb.x), spo_tanh_fast(acc[0][3] + bb.y));
-      fence_proxy_async();                            // the slice is read by the bulk-copy engine next
+      __syncthreads();                                // own slice complete (and fenced towards the async proxy)
+      if (lane == 0 && wid < NQ && wid != q)          // all-gather of h1: the own 4 KB block goes to the three peers of the net
+        bulk_push(mapa(smem_u32(h1 + q * H1Q), grp0 + wid), h1 + q * H1Q, H1Q * 4, mapa(smem_u32(&bar_h1), grp0 + wid));
+      // while the blocks travel: per-step scalars nobody needs before the loss rows / Adam
+      if (is_actor && tid >= UT - 32 && tid - (UT - 32) < A) {
+        // row-independent pieces of the Gaussian log-density (log_std is final now)
+        const int j = tid - (UT - 32);
+        const float sd = expf(log_std[j]);
+        lsc[4 * j + 0] = sd;
+        lsc[4 * j + 1] = __fdiv_rn(1.f, __fmul_rn(sd, sd));
+        lsc[4 * j + 2] = logf(sd);
+      }
       if (tid == 0 && last_tile) {
         // Adam scalars of this step (fp64 like torch's Python floats); the barriers of the step publish them
         b1pow *= static_cast<double>(a.hp.beta1);
@@ -818,13 +996,6 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         adk[4] = a.hp.adam_eps;
         adk[5] = -__fdiv_rn(lr, static_cast<float>(1.0 - b1pow));
       }
-    }
-    PHASE_MARK(1);   // layer-1 product + epilogue
-    float yv[SPO_MAX_ACT];                            // output-layer rows of this thread's row r4 (after the y exchange)
-    if (active) {
-      __syncthreads();                                // own slice complete (and fenced towards the async proxy)
-      if (tid < NQ && tid != q)                       // all-gather of h1: the own 4 KB block goes to the three peers of the net
-        bulk_push(mapa(smem_u32(h1 + q * H1Q), grp0 + tid), h1 + q * H1Q, H1Q * 4, mapa(smem_u32(&bar_h1), grp0 + tid));
       mbar_wait(&bar_h1, ph_x);                       // ... and theirs have landed here
       if (tid == 0) mbar_expect_tx(&bar_h1, (NQ - 1) * H1Q * 4);
       PHASE_MARK(3);   // h1 all-gather (pushed)
@@ -840,19 +1011,40 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
       // output layer, partial over the own 16 hidden units: thread (row r4, quarter of the slice k4), two shuffles
       {
         const float4 hv = *reinterpret_cast<const float4*>(h2s + r4 * LDS + 4 * k4);
-        for (int o = 0; o < O; ++o) {
-          const float4 wv = *reinterpret_cast<const float4*>(w3s + o * SL + 4 * k4);
-          float sacc = fmaf(hv.x, wv.x, hv.y * wv.y) + fmaf(hv.z, wv.z, hv.w * wv.w);
-          sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-          sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-          if (k4 == (o & 3)) yblk[q * YQ + r4 * SPO_MAX_ACT + o] = sacc;
+        for (int o = 0; o < O; o += 2) {     // two outputs per trip: their shuffle chains overlap (rows >= O of w3 are allocated)
+          const float4 wa = *reinterpret_cast<const float4*>(w3s + o * SL + 4 * k4);
+          const float4 wb = *reinterpret_cast<const float4*>(w3s + (o + 1) * SL + 4 * k4);
+          float sa = fmaf(hv.x, wa.x, hv.y * wa.y) + fmaf(hv.z, wa.z, hv.w * wa.w);
+          float sb = fmaf(hv.x, wb.x, hv.y * wb.y) + fmaf(hv.z, wb.z, hv.w * wb.w);
+          sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+          sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+          sa += __shfl_xor_sync(0xffffffffu, sa, 2);
+          sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+          if (k4 == (o & 3)) yblk[q * YQ + r4 * SPO_MAX_ACT + o] = sa;
+          if (k4 == ((o + 1) & 3) && o + 1 < O) yblk[q * YQ + r4 * SPO_MAX_ACT + o + 1] = sb;
         }
         fence_proxy_async();
       }
       __syncthreads();
-      if (tid < NQ && tid != q)                       // all-gather of the partial outputs: 2 KB to each peer of the net
-        bulk_push(mapa(smem_u32(yblk + q * YQ), grp0 + tid), yblk + q * YQ, YQ * 4, mapa(smem_u32(&bar_y), grp0 + tid));
+      if (lane == 0 && wid < NQ && wid != q)          // all-gather of the partial outputs: 2 KB to each peer of the net
+        bulk_push(mapa(smem_u32(yblk + q * YQ), grp0 + wid), yblk + q * YQ, YQ * 4, mapa(smem_u32(&bar_y), grp0 + wid));
       PHASE_MARK(4);   // layer 2 + partial output layer
+      // the row's side data, read while the partial outputs travel
+      float pa[2] = {0.f, 0.f}, psd[2] = {1.f, 1.f}, piv[2] = {1.f, 1.f}, pls[2] = {0.f, 0.f}, plogp = 0.f, padv = 0.f, ptgt = 0.f;
+      {
+        const float* axp = aux + r4 * AUXW;
+        if (is_actor) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int j = k4 + 4 * h;
+            if (j < A) { pa[h] = axp[j]; psd[h] = lsc[4 * j]; piv[h] = lsc[4 * j + 1]; pls[h] = lsc[4 * j + 2]; }
+          }
+          plogp = axp[AUX_LOGP];
+          padv = axp[AUX_ADV];
+        } else if (k4 == 0) {
+          ptgt = axp[AUX_TGT];
+        }
+      }
       mbar_wait(&bar_y, ph_x);
       if (tid == 0) mbar_expect_tx(&bar_y, (NQ - 1) * YQ * 4);
       PHASE_MARK(5);   // y all-gather (pushed)
@@ -881,7 +1073,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         float* ax = aux + r * AUXW;
         if (!is_actor) {
           if (k4 == 0) {
-            const float dv = __fsub_rn(yv[0], ax[AUX_TGT]);
+            const float dv = __fsub_rn(yv[0], ptgt);
             part0 = valid ? __fmul_rn(dv, dv) : 0.f;
             dy[r * SPO_MAX_ACT] = valid ? __fmul_rn(__fmul_rn(__fmul_rn(2.f, dv), inv_b), vcoef) : 0.f;
           }
@@ -896,11 +1088,11 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
               const float m_lo = (k4 == 0) ? yv[0] : (k4 == 1) ? yv[1] : (k4 == 2) ? yv[2] : yv[3];
               const float m_hi = (k4 == 0) ? yv[4] : (k4 == 1) ? yv[5] : (k4 == 2) ? yv[6] : yv[7];
               const float mean = h ? m_hi : m_lo;
-              const float std = lsc[4 * j], inv_var = lsc[4 * j + 1];
-              const float diff = __fsub_rn(ax[j], mean);
+              const float std = psd[h], inv_var = piv[h];
+              const float diff = __fsub_rn(pa[h], mean);
               const float d2 = __fmul_rn(diff, diff);
               const float q2 = __fmul_rn(d2, inv_var);           // (a - mu)^2 / var
-              term[h] = __fsub_rn(__fsub_rn(__fmul_rn(-0.5f, q2), lsc[4 * j + 2]), kLogSqrt2Pi);
+              term[h] = __fsub_rn(__fsub_rn(__fmul_rn(-0.5f, q2), pls[h]), kLogSqrt2Pi);
               dmu_lp[h] = __fmul_rn(diff, inv_var);
               dls_lp[h] = __fsub_rn(q2, 1.f);
               if (a.kind == SPO_LOSS_FOCOPS) {
@@ -925,8 +1117,8 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
             kl += __shfl_xor_sync(0xffffffffu, kl, 1);
             kl += __shfl_xor_sync(0xffffffffu, kl, 2);
           }
-          const float ratio = expf(__fsub_rn(lp, ax[AUX_LOGP]));
-          const float adv = ax[AUX_ADV];
+          const float ratio = expf(__fsub_rn(lp, plogp));
+          const float adv = padv;
           if (a.kind == SPO_LOSS_PPO_CLIP) {
             const float s1 = __fmul_rn(ratio, adv);
             const float s2 = __fmul_rn(fminf(fmaxf(ratio, a.hp.clip_lo), a.hp.clip_hi), adv);
@@ -1005,29 +1197,35 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         float hv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) hv[i] = h2s[(rg + 16 * i) * LDS + kk];
-        for (int o = 0; o < O; ++o) {
-          float sa = 0.f;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) sa = fmaf(dy[(rg + 16 * i) * SPO_MAX_ACT + o], hv[i], sa);
-          sa += __shfl_xor_sync(0xffffffffu, sa, 1);
-          sa += __shfl_xor_sync(0xffffffffu, sa, 2);
-          sa += __shfl_xor_sync(0xffffffffu, sa, 4);
-          sa += __shfl_xor_sync(0xffffffffu, sa, 8);
-          if (rg == 0) gsmall[SP_W3 + o * SL + kk] += sa;
-        }
+        // the column sum for db3 / dlog_std rides along with the first pair of dW3 sums (independent shuffle chains)
         const int col = kk & 7;                    // kk < 8: dy column (db3), else dls column (dlog_std)
         const bool need = (kk < 8) ? (col < O) : (is_actor && col < A);
         const float* src = (kk < 8) ? dy : dls;
-        float sa = 0.f;
+        float sc = 0.f;
         if (need) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) sa += src[(rg + 16 * i) * SPO_MAX_ACT + col];
+          for (int i = 0; i < 4; ++i) sc += src[(rg + 16 * i) * SPO_MAX_ACT + col];
         }
-        sa += __shfl_xor_sync(0xffffffffu, sa, 1);
-        sa += __shfl_xor_sync(0xffffffffu, sa, 2);
-        sa += __shfl_xor_sync(0xffffffffu, sa, 4);
-        sa += __shfl_xor_sync(0xffffffffu, sa, 8);
-        if (need && rg == 0) gsmall[(kk < 8 ? SP_B3 : SP_LS) + col] += sa;
+        for (int o = 0; o < O; o += 2) {           // column o + 1 of dy exists (SPO_MAX_ACT columns); its sum is dropped when >= O
+          float sa = 0.f, sb = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 d = *reinterpret_cast<const float2*>(dy + (rg + 16 * i) * SPO_MAX_ACT + o);
+            sa = fmaf(d.x, hv[i], sa);
+            sb = fmaf(d.y, hv[i], sb);
+          }
+#pragma unroll
+          for (int m = 1; m < 16; m <<= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, m);
+            sb += __shfl_xor_sync(0xffffffffu, sb, m);
+            if (o == 0) sc += __shfl_xor_sync(0xffffffffu, sc, m);
+          }
+          if (rg == 0) {
+            gsmall[SP_W3 + o * SL + kk] += sa;
+            if (o + 1 < O) gsmall[SP_W3 + (o + 1) * SL + kk] += sb;
+          }
+        }
+        if (need && rg == 0) gsmall[(kk < 8 ? SP_B3 : SP_LS) + col] += sc;
       }
       // (b) dz2[r][kk] = (sum_o dy[r][o] * w3[o][kk]) * (1 - h2[r][kk]^2), own 16 columns
       {
@@ -1057,8 +1255,8 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         fence_proxy_async();
       }
       __syncthreads();
-      if (tid < NQ && tid != q)                       // reduce-scatter of dh1: the partial for CTA d's columns goes to its slot [q]
-        bulk_push(mapa(smem_u32(dh1in + q * H1Q), grp0 + tid), dh1b + tid * H1Q, H1Q * 4, mapa(smem_u32(&bar_dh), grp0 + tid));
+      if (lane == 0 && wid < NQ && wid != q)          // reduce-scatter of dh1: the partial for CTA d's columns goes to its slot [q]
+        bulk_push(mapa(smem_u32(dh1in + q * H1Q), grp0 + wid), dh1b + wid * H1Q, H1Q * 4, mapa(smem_u32(&bar_dh), grp0 + wid));
       PHASE_MARK(8);   // dh1 partial product + push
       // (d) dW2[slice j][k] += sum_r dz2[r][j] * h1[r][k] (warp w: columns 8w..8w+7);  db2[j] += sum_r dz2[r][j]
       //     -- runs while the 12 KB of dh1 partials travel
@@ -1102,24 +1300,9 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
     cp_async_wait_all();   // indices of tile qt+1 (requested a step ago); the barriers below publish them
     __syncthreads();       // gsmall complete
     ph_x ^= active ? 1u : 0u;   // both pushed exchanges of this tile are consumed
-    // The step barrier = the all-to-all of (sum g^2, sum theta^2): every CTA pushes 16 bytes to each of the other 11 and waits
-    // for 11 x 16 bytes on its own mbarrier.  A CTA pushes only after its last read of any exchanged buffer, so nobody can
-    // overwrite h1 / the partial-output blocks / the dh1 slots of a CTA that still reads them.
-    auto step_barrier_push = [&](float ssq, float t2) {
-      float* mine = xin + (par * 16 + static_cast<int>(rank)) * 4;
-      if (tid == 0) { *reinterpret_cast<float4*>(mine) = make_float4(ssq, t2, 0.f, 0.f); fence_proxy_async(); }
-      __syncthreads();
-      if (tid < NCTA && tid != static_cast<int>(rank)) bulk_push(mapa(smem_u32(mine), tid), mine, 16, mapa(smem_u32(&bar_ss[tcount & 1u]), tid));
-    };
-    auto step_barrier_wait = [&]() {
-      uint64_t* bar = &bar_ss[tcount & 1u];
-      mbar_wait(bar, (tcount >> 1) & 1u);
-      if (tid == 0) mbar_expect_tx(bar, (NCTA - 1) * 16);
-      ++tcount;
-    };
     if (!last_tile) {
       // more tiles of the same step follow: the exchange only orders the buffer reuse
-      step_barrier_push(0.f, 0.f);
+      step_barrier_push(par, 0.f, 0.f);
       stage_next();
       step_barrier_wait();
       continue;
@@ -1132,6 +1315,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
 #pragma unroll
       for (int i = 0; i < NT1; ++i) dp_push(gW1[i], IC<4>{}, 4 * (1 + i));
       sv = (tid < SPN) ? gsmall[tid] : 0.f;
+      stage_next();    // the next tile's rows are requested while the last words cross NVLink
       if (world >= 4 && world <= 8) dp_sum_wide(gW2[0], gW1, sv);
       else dp_sum_all(gW2[0], gW1, sv);
       if (tid < SPN) gsmall[tid] = sv;
@@ -1187,85 +1371,31 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
         }
       }
       PHASE_MARK(14);  // regulariser + sum of squares
-      step_barrier_push(s + extra_sumsq, t2);
+      step_barrier_push(par, s + extra_sumsq, t2);
+      PHASE_MARK(17);  // norms pushed
     }
-    stage_next();    // rows of the next tile are requested while the 16-byte pushes travel
-    step_barrier_wait();
-    PHASE_MARK(15);  // step barrier (all-to-all of the norms)
-    // every thread reads the 12 pairs from its own shared memory and adds them in CTA order
-    float total = 0.f, t2net = 0.f;
-#pragma unroll
-    for (int b = 0; b < NCTA; ++b) {
-      const float2 v = *reinterpret_cast<const float2*>(xin + (par * 16 + b) * 4);
-      total += v.x;
-      if (b / NQ == net) t2net += v.y;
-    }
-    if (tid == 0 && q == 0 && active) {
-      // logged loss of this step (ppo_lag.py:330-336): critics include the L2 term over the whole net
-      float L;
-      if (!is_actor) L = fmaf(a.hp.critic_l2, t2net, __fmul_rn(step_loss, inv_b));
-      else if (a.kind == SPO_LOSS_PPO_CLIP) L = __fmul_rn(step_loss, inv_b);
-      else L = __fsub_rn(__fmul_rn(step_loss, inv_b),
-                         __fmul_rn(__fmul_rn(__fdiv_rn(1.f, a.hp.focops_lam), __fmul_rn(step_aux0, inv_b)), __fmul_rn(step_aux1, inv_b)));
-      acc_loss += static_cast<double>(L);
-    }
-    if (tid == 0) { step_loss = 0.f; step_aux0 = 0.f; step_aux1 = 0.f; }
-    // clip coefficient max_norm / (norm + 1e-6), capped at 1 (SFU sqrt and division: <= 2 ulp, exactly 1 below the limit)
-    const float clip = fminf(__fdividef(a.hp.max_grad_norm, __fadd_rn(sqrt_approx(total), 1e-6f)), 1.f);
-
-    if (active) {
-      AdamK k;
-      k.w1 = adk[0]; k.b2 = adk[1]; k.w2 = adk[2]; k.ibc2s = adk[3]; k.eps = adk[4]; k.ss = adk[5];
-      // all loads first, then the arithmetic, then all stores: shared-memory loads cannot be moved across possibly
-      // aliasing stores by the compiler, which would serialise twelve load -> sqrt -> rcp -> store chains per thread
-      float2 w2v[2];
-      float w1v[NT1][4];
-      float spv = 0.f, spg = 0.f;
-#pragma unroll
-      for (int e = 0; e < 4; e += 2) {
-        int j, kc;
-        frag_jk(e, wid, j, kc);
-        w2v[e >> 1] = *reinterpret_cast<const float2*>(w2s + j * LDA + kc);
-#pragma unroll
-        for (int i = 0; i < NT1; ++i) {
-          frag_jk(e, wid + 8 * i, j, kc);
-          const float2 t = *reinterpret_cast<const float2*>(w1s + j * ldx + kc);   // columns >= D are zero padding
-          w1v[i][e] = t.x; w1v[i][e + 1] = t.y;
-        }
-      }
-      if (tid < SPN) { spv = sp[tid]; spg = gsmall[tid]; }
-#pragma unroll
-      for (int e = 0; e < 4; e += 2) {
-        w2v[e >> 1].x = adam_update(w2v[e >> 1].x, __fmul_rn(gW2[0][e], clip), mW2[e], vW2[e], k);
-        w2v[e >> 1].y = adam_update(w2v[e >> 1].y, __fmul_rn(gW2[0][e + 1], clip), mW2[e + 1], vW2[e + 1], k);
-        gW2[0][e] = 0.f; gW2[0][e + 1] = 0.f;
-#pragma unroll
-        for (int i = 0; i < NT1; ++i) {
-          int j, kc;
-          frag_jk(e, wid + 8 * i, j, kc);
-          // padded columns (kc >= D): gradient 0, moments 0 -> the update is exactly 0, the padding stays 0
-          w1v[i][e] = adam_update(w1v[i][e], __fmul_rn(gW1[i][e], clip), mW1[i][e], vW1[i][e], k);
-          w1v[i][e + 1] = adam_update(w1v[i][e + 1], __fmul_rn(gW1[i][e + 1], clip), mW1[i][e + 1], vW1[i][e + 1], k);
-          gW1[i][e] = 0.f; gW1[i][e + 1] = 0.f;
-        }
-      }
-      if (tid < SPN && sp_valid) spv = adam_update(spv, __fmul_rn(spg, clip), sp_m, sp_v, k);
-#pragma unroll
-      for (int e = 0; e < 4; e += 2) {
-        int j, kc;
-        frag_jk(e, wid, j, kc);
-        *reinterpret_cast<float2*>(w2s + j * LDA + kc) = w2v[e >> 1];
-#pragma unroll
-        for (int i = 0; i < NT1; ++i) {
-          frag_jk(e, wid + 8 * i, j, kc);
-          *reinterpret_cast<float2*>(w1s + j * ldx + kc) = make_float2(w1v[i][e], w1v[i][e + 1]);
-        }
-      }
-      if (tid < SPN) { sp[tid] = spv; gsmall[tid] = 0.f; }
-    }
+    if (!(DP && world > 1 && active)) stage_next();    // rows of the next tile are requested while the 16-byte pushes travel
+    PHASE_MARK(15);  // norms pushed, next tile requested
+    // SPECULATION: the joint norm almost never exceeds max_grad_norm (clip = min(max_norm / (norm + 1e-6), 1) is exactly 1 then),
+    // so Adam runs NOW with clip = 1 -- (theta, m, v) saved first -- and the next step's stage-in and layer-1 product follow while
+    // the twelve 16-byte pushes travel; the norms are checked before that step pushes anything (top of the loop).  A step
+    // whose norm does exceed the limit is undone and redone there: results are bit-identical either way.
+    if (active) adam_apply(1.f, true);
+    pending = true;
+    pend_par = par;
+    pend_inv_b = inv_b;
     PHASE_MARK(16);  // Adam
     ++step_idx;
     // the __syncthreads at the top of the next iteration orders these weight writes before the next forward
+  }
+  if (pending) {         // the last step of the launch
+    step_barrier_wait();
+    const float clip = resolve_norms(pend_par, pend_inv_b);
+    if (active && clip < 1.f) {
+      __syncthreads();
+      adam_restore();
+      adam_apply(clip, false);
+    }
   }
   cp_async_wait_all();
   __syncthreads();
@@ -1314,7 +1444,7 @@ __global__ void __launch_bounds__(UT, 1) spo_update_kernel(const UpdArgs a) {
 size_t update_smem_bytes(int nt1) {
   const int ldx = upd_ldx(nt1);
   size_t f = 4 * SPO_ROWS + 4 * SPO_MAX_ACT + 8 + SL * ldx + SL * LDA + 2 * SPN + SPO_ROWS * ldx + SPO_ROWS * AUXW + NQ * SPO_ROWS * SL +
-             2 * SPO_ROWS * LDS + (3 + NQ) * SPO_ROWS * SPO_MAX_ACT + 2 * NQ * SPO_ROWS * SL + 64 + 128;
+             2 * SPO_ROWS * LDS + (3 + NQ) * SPO_ROWS * SPO_MAX_ACT + 2 * NQ * SPO_ROWS * SL + 64 + 128 + 3 * (4 * (1 + nt1) + 1) * UT;
   return f * sizeof(float);
 }
 

@@ -33,10 +33,10 @@ lib.spo_debug_phase_cycles(buf, 1)
 upd.run(data, perms=[perm])
 torch.cuda.synchronize()
 lib.spo_debug_phase_cycles(buf, 1)
-names = {0: "top (stage-in+sync)", 1: "L1 GEMM+tanh", 3: "h1 push+wait", 4: "L2+ypartial", 5: "barrier 2", 6: "y pull+loss rows", 7: "small grads+dz2",
-         8: "dh1 partial+push", 10: "dW2+db2", 11: "dh1 wait+reduce+dz1", 12: "dW1+db1", 13: "dp exchange", 14: "reg+sumsq", 15: "barrier 4", 16: "Adam"}
+names = {0: "top (stage-in+sync)", 2: "L1 GEMM+tanh", 9: "norm wait", 1: "resolve+lsc+adk", 17: "norm push",  3: "h1 push+wait", 4: "L2+ypartial", 5: "barrier 2", 6: "y pull+loss rows", 7: "small grads+dz2",
+         8: "dh1 partial+push", 10: "dW2+db2", 11: "dh1 wait+reduce+dz1", 12: "dW1+db1", 13: "dp exchange", 14: "reg+sumsq", 15: "stage next", 16: "Adam+save"}
 for rank in range(12):
-    row = [buf[rank * 24 + i] / steps for i in range(17)]
-    row_n = [(names[i], row[i]) for i in sorted(names)]
+    row = [buf[rank * 24 + i] / steps for i in range(24)]
+    row_n = [(names[i], row[i]) for i in names]
     net = ("actor", "reward critic", "cost critic")[rank // 4]
     print(f"{net:13s} q{rank % 4} total {sum(row):7.0f} cyc/step | " + " ".join(f"{n}={v:.0f}" for n, v in row_n))

@@ -34,3 +34,30 @@ if os.environ.get("TIME"):
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     print(f"update kernel: {best * 1e3 / steps:.2f} us per minibatch step ({steps} steps, best of 5)")
+if os.environ.get("FILLER"):
+    # experiment: the same timing while a filler kernel keeps the other SMs busy (tools/filler.cu)
+    import ctypes as C
+    fl = C.CDLL(os.path.join(ROOT, "tools", "libfiller.so"))
+    fl.filler_launch.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
+    assert fl.filler_prepare() == 0
+    side, flagst = torch.cuda.Stream(), torch.cuda.Stream()
+    sink = torch.zeros(1, device=dev)
+    for mode in (0, 1, 2):
+        for ctas in (64, 132):
+            for threads in (32, 256):
+                stop = torch.zeros(1, dtype=torch.int32, device=dev)
+                torch.cuda.synchronize()
+                rc = fl.filler_launch(ctas, threads, mode, stop.data_ptr(), int(0.25 * 1.9e9), sink.data_ptr(), side.cuda_stream)
+                assert rc == 0, rc
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                best = 1e9
+                for _ in range(3):
+                    e0.record()
+                    upd.run(data, perms=[perm])
+                    e1.record()
+                    e1.synchronize()
+                    best = min(best, e0.elapsed_time(e1))
+                with torch.cuda.stream(flagst):
+                    stop.fill_(1)
+                torch.cuda.synchronize()
+                print(f"filler mode {mode} ctas {ctas} threads {threads}: {best * 1e3 / steps:.2f} us per step")
