@@ -481,6 +481,68 @@ def test_update_other_shapes_vs_oracle(kind, D, A, batch):
             assert err < 5e-5, (kind, D, A, batch, net, k, err)    # 6 Adam steps of lr 3e-4
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,D,batch,max_norm", [
+    ("ppo", 60, 64, 0.05),     # every step clipped: every speculative Adam step is undone and redone
+    ("ppo", 60, 64, 2.5),      # around the typical joint norm (2.0 .. 2.8 here): clipped and unclipped steps alternate
+    ("focops", 27, 64, 2.9),   # the same for FOCOPS (2.6 .. 3.3)
+    ("ppo", 104, 100, 0.5),    # two W1 blocks, two tiles per step, ragged tile, clipped
+])
+def test_update_with_active_gradient_clip_vs_oracle(kind, D, batch, max_norm):
+    """clip_grad_norm_ (ppo_lag.py:325) with a limit the joint norm exceeds.  The kernel runs Adam before the
+    cluster-wide norm is known and repeats the step with the clip coefficient when it turns out < 1: weights after
+    12 steps and the pass-mean losses against the oracle; the number of clipped steps is counted on the oracle side."""
+    from safepo import _lib as L
+    from safepo.common.model import ActorVCritic
+    from safepo.single_agent._engine import PolicyGradientUpdate
+    dev = _cuda()
+    A = 2 if D != 27 else 8
+    torch.manual_seed(77 + D)
+    pol = ActorVCritic(D, A, [64, 64]).to(dev)
+    state = policy_state(pol)
+    opol = oracle_policy(state, D, A)
+    S = 11 * batch + 29
+    g = torch.Generator().manual_seed(S + D)
+    obs = torch.randn(S, D, generator=g)
+    with torch.no_grad():
+        mean, std = O.actor_mean_std(opol, obs)
+        act = mean + std * torch.randn(S, A, generator=g)
+        logp = O.normal_log_prob(act, mean, std).sum(-1) + 0.05 * torch.randn(S, generator=g)
+        old_mean, old_std = mean.clone(), std.expand_as(mean).clone()
+    data_cpu = {"obs": obs, "act": act, "log_prob": logp, "target_value_r": torch.randn(S, generator=g),
+                "target_value_c": torch.randn(S, generator=g).abs(), "adv": torch.randn(S, generator=g)}
+    perm = torch.randperm(S, generator=g)
+    cfg = dict(hidden_sizes=[64, 64], gamma=0.99, target_kl=1e9, batch_size=batch, learning_iters=1, max_grad_norm=max_norm)
+    upd = PolicyGradientUpdate(pol, cfg, {"ppo": L.LOSS_PPO_CLIP, "focops": L.LOSS_FOCOPS}[kind], epochs=10**9, host_rng=False, device=dev)
+    upd.hp.focops_kl = 0.02
+    data = {k: v.to(dev).contiguous() for k, v in data_cpu.items()}
+    res = upd.run(data, perms=[perm], refresh_old=True)
+    opt = O.OracleOptim(opol)
+    losses, clipped = [], 0
+    for s0 in range(0, S, batch):
+        idx = perm[s0:s0 + batch]
+        b = {k: v[idx] for k, v in data_cpu.items()}
+        b["old_mean"], b["old_std"] = old_mean[idx], old_std[idx]
+        losses.append(O.minibatch_step(opol, opt, b, kind, max_grad_norm=max_norm))
+        norm = torch.sqrt(sum((p.grad ** 2).sum() for p in opol.all_params() if p.grad is not None))
+        clipped += int(float(norm) >= max_norm * 0.999)     # grads are the clipped ones here: norm == max_norm when clipped
+    n_steps = (S + batch - 1) // batch
+    assert res["steps"] == n_steps
+    if max_norm <= 0.05:
+        assert clipped == n_steps
+    else:
+        assert 0 < clipped, (clipped, n_steps)
+    want = torch.tensor(losses, dtype=torch.float64).mean(0)
+    for name, got, w in (("loss_r", res["loss_r"], want[0]), ("loss_c", res["loss_c"], want[1]), ("loss_pi", res["loss_pi"], want[2])):
+        ok, ea, er = close(got, w, rtol=5e-5, atol=5e-6)
+        assert ok, (kind, D, batch, max_norm, name, got, float(w), ea, er)
+    final, ofinal = policy_state(pol), opol.state()
+    for net in O.NET_ORDER:
+        for k, v in ofinal[net].items():
+            err = float((final[net][k] - v).abs().max())
+            assert err < 1e-4, (kind, D, batch, max_norm, net, k, err, clipped, n_steps)    # 12 Adam steps of lr 3e-4
+
+
 # ---------------------------------------------------------------------------------------
 # env I/O transforms (SURVEY 8f rank 1; oracle/envio.py restates third-party gymnasium: parity unpinned)
 # ---------------------------------------------------------------------------------------

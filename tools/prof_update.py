@@ -7,6 +7,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "safe-policy-optimization_b200"))
 from safepo import _lib as L  # noqa: E402
+
+if os.environ.get("LIB"):      # A/B runs: another build of the library (e.g. tools/libspo_head.so)
+    L.LIB_PATH = os.path.join(ROOT, os.environ["LIB"])
 from safepo.single_agent._engine import PolicyGradientUpdate  # noqa: E402
 from safepo.common.model import ActorVCritic  # noqa: E402
 
