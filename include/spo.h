@@ -288,7 +288,7 @@ int spo_conjugate_gradient(const spo_dims* d, const float* params, const float* 
 int spo_cg_begin(const spo_dims* d, const float* b, float* x, float* work, void* stream);
 int spo_cg_update(const spo_dims* d, float* x, float* work, float residual_tol, float eps, void* stream);
 
-/* ---- multi-agent nets (MAPPO-Lag, BASELINE config 5; SURVEY section 8f rank 3, first slice: FORWARD only) ----
+/* ---- multi-agent nets (MAPPO-Lag, BASELINE config 5), first slice: the forward ----
  * spo_ma_mlp_layer: one [Linear -> ELU -> LayerNorm] block of MLPLayer (safepo/utils/mlp.py:18-27), optionally preceded by
  *   the input LayerNorm of MLPBase (feature_norm, mlp.py:46-47,57-58): out[n][H] = LN_out(ELU(LN_in?(in)[n][K] W[H][K]^T + b)).
  *   K even, H a multiple of 128 up to 512; all pointers device fp32 (in / W 8-byte, out 16-byte aligned).
@@ -300,6 +300,55 @@ int spo_ma_mlp_layer(const float* in, int n, int K, const float* W, const float*
                      const float* ln_in_w, const float* ln_in_b, float* out, void* stream);
 int spo_ma_head(const float* feat, int n, int H, const float* W, const float* b, int O, const float* log_std, float std_x_coef,
                 float std_y_coef, const float* eps, float* out, float* logp, void* stream);
+
+/* ---- multi-agent nets, second slice: the UPDATE (MAPPO_L_Trainer.ppo_update, safepo/multi_agent/mappolag.py:135-199) ----
+ * The host side (safepo/common/ma_model.py: MultiAgentTrainer) strings these together per net: training forward (activations
+ * kept), loss head, then per layer LayerNorm/ELU backward, dW = dz^T x, dx = dz W, and clip + Adam on the packed parameters.
+ * All pointers are device fp32; every sum over rows is a fixed-order two-stage reduction (per-CTA partials in `part`, then
+ * spo_ma_partial_reduce), so results do not depend on scheduling.
+ *
+ * spo_ma_mlp_layer_train: spo_ma_mlp_layer that also keeps pre[n][H] = ELU(z) (the input of the output LayerNorm; 16-byte
+ *   aligned) and, with the input LayerNorm, xn[n][K] = LN_in(in) (may be NULL otherwise).
+ * spo_ma_ln_elu_bwd: dy[n][H] = d loss / d LN output -> dz[n][H] = d loss / d (x W^T + b) (mlp.py:18-27 backwards);
+ *   part[ceil(n/32)][3][H] = per-CTA column sums {dy * xhat (d ln weight), dy (d ln bias), dz (d bias)}.
+ * spo_ma_ln_in_bwd: parameter gradients of the input LayerNorm (mlp.py:46-47): part[ceil(n/32)][2][K] = {dxn * xhat, dxn}.
+ * spo_ma_partial_reduce: out_s[j] = scale * sum_b part[b * stride + s * len + j], s < nseg <= 3 (out_s NULL = skipped).
+ * spo_ma_gemm_nn: C[M][N] = A[M][Kd] B[Kd][N].   spo_ma_gemm_tn: part[z][M][N] = sum over the z-th slice of the R rows of
+ *   A[r][M] B[r][N]  (follow with spo_ma_partial_reduce(part, slices, M*N, 1, M*N, C, ...)).
+ * spo_ma_actor_loss: DiagGaussian head + clipped surrogate (mappolag.py:147-166, distributions.py:8-9,38-42): per-dimension
+ *   log-probs of `actions` under mean = feat W^T + b, std = sigmoid(log_std / x) * y;  imp[n] = prod_j exp(logp_j - old_logp_j);
+ *   loss_row = -factor * min(imp * adv, clamp(imp, clip_lo, clip_hi) * adv), adv = adv_targ - *lamda * cost_adv_targ (lamda: device
+ *   scalar);  dmean[n][A] = d mean_rows(loss_row) / d mean;  part[ceil(n/32)][66] = {sum loss_row, 0, sum dmean_j (32), sum dstd_j (32)}.
+ * spo_ma_actor_finalize: scalars[0] = policy_loss, scalars[1] = dist_entropy (act.py:57-60); g_b[A] = d / d bias of the mean layer,
+ *   g_log_std[A] = d (policy_loss - entropy_coef * entropy) / d log_std.
+ * spo_ma_value_loss: clipped one-sided-Huber value loss (mappolag.py:121-133, util.py:19-22) on v[n] against the two PopArt
+ *   normalisations of the returns; dv[n] = scale * dL/dv (scale = value_loss_coef / n); part[ceil(n/256)][2] = {sum L_row, sum dv}.
+ * spo_ma_popart_normalize: PopArt.forward on [n] values (popart.py:76-112): updates state = {running_mean, running_mean_sq,
+ *   debiasing_term} with the batch moments (weight beta), then out = (x - mean) / sqrt(var).
+ * spo_ma_lagrange_step: lamda <- relu(lamda - delta * rate), delta = -mean((mean(aver_costs) - cost_limit)(1 - gamma) + imp * cost_adv)
+ *   (mappolag.py:169-172).
+ * spo_ma_clip_adam: clip_grad_norm_(max_grad_norm) over the packed gradient + one torch.optim.Adam step (step >= 1 is the new
+ *   step count); work[>= 1024] scratch, norm_out[0] = the gradient norm before clipping, norm_out[1] = the clip coefficient. */
+int spo_ma_mlp_layer_train(const float* in, int n, int K, const float* W, const float* b, const float* ln_w, const float* ln_b, int H,
+                           const float* ln_in_w, const float* ln_in_b, float* out, float* pre, float* xn, void* stream);
+int spo_ma_ln_elu_bwd(const float* dy, const float* pre, const float* ln_w, int n, int H, float* dz, float* part, void* stream);
+int spo_ma_ln_in_bwd(const float* dxn, const float* x, int n, int K, float* part, void* stream);
+int spo_ma_partial_reduce(const float* part, int nblk, int stride, int nseg, int len, float* out0, float* out1, float* out2, float scale,
+                          void* stream);
+int spo_ma_gemm_nn(const float* A, const float* B, float* C, int M, int N, int Kd, void* stream);
+int spo_ma_gemm_tn(const float* A, const float* B, float* part, int R, int M, int N, int slices, void* stream);
+int spo_ma_actor_loss(const float* feat, int n, int H, const float* W, const float* b, const float* log_std, int A, const float* actions,
+                      const float* old_logp, const float* adv, const float* cost_adv, const float* factor, const float* lamda,
+                      float clip_lo, float clip_hi, float std_x_coef, float std_y_coef, float* dmean, float* imp, float* part, void* stream);
+int spo_ma_actor_finalize(const float* part, int nblk, int n, const float* log_std, int A, float std_x_coef, float std_y_coef, float entropy_coef,
+                          float* g_b, float* g_log_std, float* scalars, void* stream);
+int spo_ma_value_loss(const float* v, const float* value_preds, const float* ret_norm_clipped, const float* ret_norm_orig, int n, float clip,
+                      float huber_delta, float scale, float* dv, float* part, void* stream);
+int spo_ma_popart_normalize(const float* x, int n, float* state, double beta, float epsilon, float* out, void* stream);
+int spo_ma_lagrange_step(const float* imp, const float* cost_adv, const float* aver_episode_costs, int n, float cost_limit, double gamma,
+                         float rate, float* lamda, void* stream);
+int spo_ma_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int count, float max_grad_norm, double lr, double beta1,
+                     double beta2, double eps, double weight_decay, int step, float* work, float* norm_out, void* stream);
 
 #ifdef __cplusplus
 }

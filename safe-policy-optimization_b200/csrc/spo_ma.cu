@@ -27,6 +27,8 @@ struct MaLayerArgs {
   const float *lin_w, *lin_b;         // input LayerNorm over K (feature_norm) or null
   float* out;           // [n][H]
   int n, K, H;
+  float* pre;           // training: ELU(z) before the output LayerNorm [n][H], or null
+  float* xn;            // training: the input after the input LayerNorm [n][K], or null
 };
 
 // HB = H / 128 column blocks per lane (H = 128 * HB)
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(MA_THREADS) spo_ma_layer_kernel(const MaLayerA
           const float mean = stat[2 * r], rstd = stat[2 * r + 1];
           v.x = fmaf((v.x - mean) * rstd, a.lin_w[k0 + kk], a.lin_b[k0 + kk]);
           v.y = fmaf((v.y - mean) * rstd, a.lin_w[k0 + kk + 1], a.lin_b[k0 + kk + 1]);
+          if (a.xn) *reinterpret_cast<float2*>(a.xn + static_cast<size_t>(g) * K + k0 + kk) = v;
         }
       }
       xs[r * (MA_KC + 4) + kk] = v.x;
@@ -142,6 +145,12 @@ __global__ void __launch_bounds__(MA_THREADS) spo_ma_layer_kernel(const MaLayerA
     const float rstd = rsqrtf(q / static_cast<float>(H) + 1e-5f);
     const int g = row0 + 4 * wid + r;
     if (g < a.n) {
+      if (a.pre) {
+#pragma unroll
+        for (int cb = 0; cb < HB; ++cb)
+          *reinterpret_cast<float4*>(a.pre + static_cast<size_t>(g) * H + 128 * cb + 4 * lane) =
+              make_float4(acc[r][4 * cb], acc[r][4 * cb + 1], acc[r][4 * cb + 2], acc[r][4 * cb + 3]);
+      }
 #pragma unroll
       for (int cb = 0; cb < HB; ++cb) {
         const float4 gw = __ldg(reinterpret_cast<const float4*>(a.ln_w + 128 * cb + 4 * lane));
@@ -196,15 +205,18 @@ __global__ void __launch_bounds__(256) spo_ma_head_kernel(const MaHeadArgs a) {
 
 extern "C" {
 
-int spo_ma_mlp_layer(const float* in, int n, int K, const float* W, const float* b, const float* ln_w, const float* ln_b, int H,
-                     const float* ln_in_w, const float* ln_in_b, float* out, void* stream) {
-  SPO_REQUIRE(in && W && b && ln_w && ln_b && out && n > 0, SPO_ERR_INVALID_ARG, "spo_ma_mlp_layer: null argument or n<=0");
-  SPO_REQUIRE((ln_in_w == nullptr) == (ln_in_b == nullptr), SPO_ERR_INVALID_ARG, "spo_ma_mlp_layer: input LayerNorm needs weight and bias");
+static int ma_layer_launch(const float* in, int n, int K, const float* W, const float* b, const float* ln_w, const float* ln_b, int H,
+                           const float* ln_in_w, const float* ln_in_b, float* out, float* pre, float* xn, void* stream, const char* who) {
+  SPO_REQUIRE(in && W && b && ln_w && ln_b && out && n > 0, SPO_ERR_INVALID_ARG, "%s: null argument or n<=0", who);
+  SPO_REQUIRE((ln_in_w == nullptr) == (ln_in_b == nullptr), SPO_ERR_INVALID_ARG, "%s: input LayerNorm needs weight and bias", who);
   SPO_REQUIRE(K >= 2 && (K & 1) == 0 && H >= 128 && H <= MA_MAXH && (H & 127) == 0, SPO_ERR_UNSUPPORTED,
-              "spo_ma_mlp_layer: K=%d must be even, H=%d a multiple of 128 up to %d", K, H, MA_MAXH);
+              "%s: K=%d must be even, H=%d a multiple of 128 up to %d", who, K, H, MA_MAXH);
   SPO_REQUIRE((reinterpret_cast<uintptr_t>(in) & 7) == 0 && (reinterpret_cast<uintptr_t>(W) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
-              SPO_ERR_INVALID_ARG, "spo_ma_mlp_layer: in / W must be 8-byte, out 16-byte aligned");
-  MaLayerArgs a{in, W, b, ln_w, ln_b, ln_in_w, ln_in_b, out, n, K, H};
+              SPO_ERR_INVALID_ARG, "%s: in / W must be 8-byte, out 16-byte aligned", who);
+  SPO_REQUIRE((reinterpret_cast<uintptr_t>(pre) & 15) == 0 && (reinterpret_cast<uintptr_t>(xn) & 7) == 0, SPO_ERR_INVALID_ARG,
+              "%s: pre must be 16-byte, xn 8-byte aligned", who);
+  SPO_REQUIRE(!xn || ln_in_w, SPO_ERR_INVALID_ARG, "%s: xn is the output of the input LayerNorm, which is not requested", who);
+  MaLayerArgs a{in, W, b, ln_w, ln_b, ln_in_w, ln_in_b, out, n, K, H, pre, xn};
   const size_t smem = sizeof(float) * (MA_KC * H + MA_ROWS * (MA_KC + 4) + 2 * MA_ROWS);
   const int grid = (n + MA_ROWS - 1) / MA_ROWS;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -216,6 +228,17 @@ int spo_ma_mlp_layer(const float* in, int n, int K, const float* W, const float*
   }
   SPO_CUDA_TRY(cudaGetLastError());
   return SPO_OK;
+}
+
+int spo_ma_mlp_layer(const float* in, int n, int K, const float* W, const float* b, const float* ln_w, const float* ln_b, int H,
+                     const float* ln_in_w, const float* ln_in_b, float* out, void* stream) {
+  return ma_layer_launch(in, n, K, W, b, ln_w, ln_b, H, ln_in_w, ln_in_b, out, nullptr, nullptr, stream, "spo_ma_mlp_layer");
+}
+
+int spo_ma_mlp_layer_train(const float* in, int n, int K, const float* W, const float* b, const float* ln_w, const float* ln_b, int H,
+                           const float* ln_in_w, const float* ln_in_b, float* out, float* pre, float* xn, void* stream) {
+  SPO_REQUIRE(pre, SPO_ERR_INVALID_ARG, "spo_ma_mlp_layer_train: pre is null");
+  return ma_layer_launch(in, n, K, W, b, ln_w, ln_b, H, ln_in_w, ln_in_b, out, pre, xn, stream, "spo_ma_mlp_layer_train");
 }
 
 int spo_ma_head(const float* feat, int n, int H, const float* W, const float* b, int O, const float* log_std, float std_x_coef,

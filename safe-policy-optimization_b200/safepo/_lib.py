@@ -106,6 +106,18 @@ def _declare(L):
         "spo_conjugate_gradient": [PD, p, p, i64, p, i, f, f, f, p, p, p],
         "spo_ma_mlp_layer": [p, i, i, p, p, p, p, i, p, p, p, p],
         "spo_ma_head": [p, i, i, p, p, i, p, f, f, p, p, p, p],
+        "spo_ma_mlp_layer_train": [p, i, i, p, p, p, p, i, p, p, p, p, p, p],
+        "spo_ma_ln_elu_bwd": [p, p, p, i, i, p, p, p],
+        "spo_ma_ln_in_bwd": [p, p, i, i, p, p],
+        "spo_ma_partial_reduce": [p, i, i, i, i, p, p, p, f, p],
+        "spo_ma_gemm_nn": [p, p, p, i, i, i, p],
+        "spo_ma_gemm_tn": [p, p, p, i, i, i, i, p],
+        "spo_ma_actor_loss": [p, i, i, p, p, p, i, p, p, p, p, p, p, f, f, f, f, p, p, p, p],
+        "spo_ma_actor_finalize": [p, i, i, p, i, f, f, f, p, p, p, p],
+        "spo_ma_value_loss": [p, p, p, p, i, f, f, f, p, p, p],
+        "spo_ma_popart_normalize": [p, i, p, d, f, p, p],
+        "spo_ma_lagrange_step": [p, p, p, i, f, d, f, p, p],
+        "spo_ma_clip_adam": [p, p, p, p, i, f, d, d, d, d, d, i, p, p, p],
         "spo_cg_begin": [PD, p, p, p, p],
         "spo_cg_update": [PD, p, p, f, f, p],
         "spo_obs_normalize": [p, i, i, p, p, d, p, i, d, p, p],
@@ -123,7 +135,8 @@ EXPORTS = ("spo_version", "spo_last_error", "spo_sync_check", "spo_param_count",
            "spo_adv_apply", "spo_pg_update", "spo_actor_forward", "spo_actor_kl", "spo_surrogate_grad", "spo_fvp",
            "spo_linesearch_eval", "spo_conjugate_gradient", "spo_comm_slot_floats", "spo_pg_update_dp", "spo_comm_alloc",
            "spo_comm_free", "spo_comm_export", "spo_comm_import", "spo_comm_close", "spo_actor_kl_accumulate", "spo_kl_finalize",
-           "spo_obs_normalize", "spo_action_rescale", "spo_gae_masked", "spo_cg_begin", "spo_cg_update", "spo_ma_mlp_layer", "spo_ma_head")
+           "spo_obs_normalize", "spo_action_rescale", "spo_gae_masked", "spo_cg_begin", "spo_cg_update", "spo_ma_mlp_layer", "spo_ma_head",
+           "spo_ma_mlp_layer_train", "spo_ma_ln_elu_bwd", "spo_ma_ln_in_bwd", "spo_ma_partial_reduce", "spo_ma_gemm_nn", "spo_ma_gemm_tn", "spo_ma_actor_loss", "spo_ma_actor_finalize", "spo_ma_value_loss", "spo_ma_popart_normalize", "spo_ma_lagrange_step", "spo_ma_clip_adam")
 
 
 # number of libspo kernels launched so far (bench.py reports the delta over its timed region)
@@ -131,7 +144,8 @@ LAUNCHES = {"n": 0}
 _KERNEL_CALLS = {"spo_policy_step", "spo_critic_values", "spo_store_transition", "spo_gae_dual", "spo_adv_stats",
                  "spo_adv_apply", "spo_pg_update", "spo_actor_forward", "spo_actor_kl", "spo_surrogate_grad", "spo_fvp",
                  "spo_linesearch_eval", "spo_pg_update_dp", "spo_actor_kl_accumulate", "spo_kl_finalize", "spo_obs_normalize",
-                 "spo_action_rescale", "spo_gae_masked", "spo_cg_begin", "spo_cg_update", "spo_ma_mlp_layer", "spo_ma_head"}
+                 "spo_action_rescale", "spo_gae_masked", "spo_cg_begin", "spo_cg_update", "spo_ma_mlp_layer", "spo_ma_head",
+                 "spo_ma_mlp_layer_train", "spo_ma_ln_elu_bwd", "spo_ma_ln_in_bwd", "spo_ma_partial_reduce", "spo_ma_gemm_nn", "spo_ma_gemm_tn", "spo_ma_actor_loss", "spo_ma_actor_finalize", "spo_ma_value_loss", "spo_ma_popart_normalize", "spo_ma_lagrange_step", "spo_ma_clip_adam"}
 
 
 def check(rc, what):

@@ -233,6 +233,18 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_device():
     assert lib.spo_gae_masked(None, None, None, 0.0, 1.0, 0.96, 0.9, None, 4, 8, None) != OK and b"spo_gae_masked" in lib.spo_last_error()
     assert lib.spo_ma_mlp_layer(None, 4, 10, None, None, None, None, 128, None, None, None, None) != OK and b"spo_ma_mlp_layer" in lib.spo_last_error()
     assert lib.spo_ma_head(None, 4, 128, None, None, 3, None, 1.0, 0.5, None, None, None, None) != OK
+    # the multi-agent update entry points (second slice of SURVEY 8f rank 3)
+    assert lib.spo_ma_mlp_layer_train(None, 4, 10, None, None, None, None, 128, None, None, None, None, None, None) != OK
+    assert lib.spo_ma_ln_elu_bwd(None, None, None, 4, 128, None, None, None) != OK and b"spo_ma_ln_elu_bwd" in lib.spo_last_error()
+    assert lib.spo_ma_ln_in_bwd(None, None, 4, 10, None, None) != OK
+    assert lib.spo_ma_partial_reduce(None, 1, 4, 1, 4, None, None, None, 1.0, None) != OK
+    assert lib.spo_ma_gemm_nn(None, None, None, 4, 4, 4, None) != OK and lib.spo_ma_gemm_tn(None, None, None, 4, 4, 4, 1, None) != OK
+    assert lib.spo_ma_actor_loss(None, 4, 128, None, None, None, 3, None, None, None, None, None, None, 0.8, 1.2, 1.0, 0.5, None, None, None, None) != OK
+    assert lib.spo_ma_actor_finalize(None, 1, 4, None, 3, 1.0, 0.5, 0.01, None, None, None, None) != OK
+    assert lib.spo_ma_value_loss(None, None, None, None, 4, 0.2, 10.0, 0.25, None, None, None) != OK
+    assert lib.spo_ma_popart_normalize(None, 4, None, 0.99999, 1e-5, None, None) != OK
+    assert lib.spo_ma_lagrange_step(None, None, None, 4, 1.0, 0.96, 1e-5, None, None) != OK
+    assert lib.spo_ma_clip_adam(None, None, None, None, 4, 10.0, 5e-4, 0.9, 0.999, 1e-5, 0.0, 1, None, None, None) != OK and b"spo_ma_clip_adam" in lib.spo_last_error()
     assert lib.spo_cg_begin(C.byref(d), None, None, None, None) != OK and lib.spo_cg_update(C.byref(d), None, None, 1e-10, 1e-6, None) != OK
     assert lib.spo_actor_forward(C.byref(d), None, None, 0, None, None) != OK
     assert lib.spo_fvp(C.byref(d), None, None, 0, None, 0.1, None, None) != OK

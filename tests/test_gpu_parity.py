@@ -835,6 +835,26 @@ def test_masked_gae_bit_exact_vs_oracle(T, N):
     assert torch.equal(got, want), float((got - want).abs().max())
 
 
+def _ma_state(g, din, H, A, head):
+    """A MultiAgentActor / MultiAgentCritic state dict (reference names, model.py:172-363) with non-trivial LayerNorm
+    parameters and biases."""
+    st = {"base.feature_norm.weight": 1 + 0.1 * torch.randn(din, generator=g), "base.feature_norm.bias": 0.1 * torch.randn(din, generator=g)}
+    dims = [din, H, H, H]
+    for li, name in enumerate(("fc1", "fc2.0", "fc2.1")):
+        st[f"base.mlp.{name}.0.weight"] = torch.randn(H, dims[li], generator=g) * (1.4 / dims[li] ** 0.5)
+        st[f"base.mlp.{name}.0.bias"] = 0.1 * torch.randn(H, generator=g)
+        st[f"base.mlp.{name}.2.weight"] = 1 + 0.1 * torch.randn(H, generator=g)
+        st[f"base.mlp.{name}.2.bias"] = 0.1 * torch.randn(H, generator=g)
+    if head == "actor":
+        st["act.action_out.log_std"] = torch.ones(A) + 0.3 * torch.randn(A, generator=g)
+        st["act.action_out.fc_mean.weight"] = torch.randn(A, H, generator=g) * 0.05
+        st["act.action_out.fc_mean.bias"] = 0.1 * torch.randn(A, generator=g)
+    else:
+        st["v_out.weight"] = torch.randn(1, H, generator=g) * 0.1
+        st["v_out.bias"] = 0.1 * torch.randn(1, generator=g)
+    return st
+
+
 # ---- SURVEY 8f rank 3, first slice: multi-agent nets, forward (MAPPO_L_Policy.get_actions) against the pinned oracle
 @pytest.mark.gpu
 @pytest.mark.parametrize("N,D,DS,A,H", [(24, 10, 14, 3, 128), (8192, 398, 398, 20, 512), (77, 66, 130, 5, 256)])
@@ -848,21 +868,7 @@ def test_ma_get_actions_vs_oracle(N, D, DS, A, H):
     g = torch.Generator().manual_seed(N + D)
 
     def make(din, head):
-        st = {"base.feature_norm.weight": 1 + 0.1 * torch.randn(din, generator=g), "base.feature_norm.bias": 0.1 * torch.randn(din, generator=g)}
-        dims = [din, H, H, H]
-        for li, name in enumerate(("fc1", "fc2.0", "fc2.1")):
-            st[f"base.mlp.{name}.0.weight"] = torch.randn(H, dims[li], generator=g) * (1.4 / dims[li] ** 0.5)
-            st[f"base.mlp.{name}.0.bias"] = 0.1 * torch.randn(H, generator=g)
-            st[f"base.mlp.{name}.2.weight"] = 1 + 0.1 * torch.randn(H, generator=g)
-            st[f"base.mlp.{name}.2.bias"] = 0.1 * torch.randn(H, generator=g)
-        if head == "actor":
-            st["act.action_out.log_std"] = torch.ones(A) + 0.3 * torch.randn(A, generator=g)
-            st["act.action_out.fc_mean.weight"] = torch.randn(A, H, generator=g) * 0.05
-            st["act.action_out.fc_mean.bias"] = 0.1 * torch.randn(A, generator=g)
-        else:
-            st["v_out.weight"] = torch.randn(1, H, generator=g) * 0.1
-            st["v_out.bias"] = 0.1 * torch.randn(1, generator=g)
-        return st
+        return _ma_state(g, din, H, A, head)
 
     sa, sc, sk = make(D, "actor"), make(DS, "critic"), make(DS, "critic")
     obs, cent = torch.randn(N, D, generator=g) * 2 + 0.3, torch.randn(N, DS, generator=g) * 3
@@ -886,3 +892,88 @@ def test_ma_get_actions_vs_oracle(N, D, DS, A, H):
     gd = nets.get_actions(cent.to(dev), obs.to(dev), deterministic=True)
     assert close(gd[1], want_det[0], rtol=2e-5, atol=1e-5)[0] and close(gd[2], want_det[1], rtol=2e-5, atol=1e-5)[0]
     assert gd[2].shape == (N, A)          # log-probs stay per action dimension (distributions.py:8-9)
+
+
+# ---- SURVEY 8f rank 3, second slice: the update of the multi-agent nets (MAPPO_L_Trainer.ppo_update)
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,Kd", [(100, 14, 128), (777, 130, 256), (64, 64, 16), (1000, 398, 512), (333, 512, 20), (50, 128, 1)])
+def test_ma_tile_products_vs_float64(M, N, Kd):
+    """spo_ma_gemm_nn (C = A B) and spo_ma_gemm_tn + spo_ma_partial_reduce (C = A^T B over row slices) against float64
+    products of the same fp32 inputs: edges that are not multiples of the 64 x 64 x 16 tile, one-column and one-row operands."""
+    from safepo import _lib as L
+    dev = _cuda()
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A_, B_ = torch.randn(M, Kd, generator=g), torch.randn(Kd, N, generator=g)
+    C = torch.empty(M, N, device=dev)
+    L.check(L.lib().spo_ma_gemm_nn(L.ptr(A_.to(dev)), L.ptr(B_.to(dev)), L.ptr(C), M, N, Kd, L.stream()), "spo_ma_gemm_nn")
+    want = (A_.double() @ B_.double())
+    assert float((C.cpu().double() - want).abs().max()) < 1e-5 * (Kd ** 0.5) * 4
+    # transposed-A product, reduction over the M rows here: [Kd][N] = A^T [Kd][M] ... use A as [R=M][Kd], B2 as [R=M][N]
+    B2 = torch.randn(M, N, generator=g)
+    for slices in (1, 3):
+        if slices > 1 and M < 64:
+            continue
+        part = torch.empty(slices * Kd * N, device=dev)
+        out = torch.empty(Kd, N, device=dev)
+        L.check(L.lib().spo_ma_gemm_tn(L.ptr(A_.to(dev)), L.ptr(B2.to(dev)), L.ptr(part), M, Kd, N, slices, L.stream()), "spo_ma_gemm_tn")
+        L.check(L.lib().spo_ma_partial_reduce(L.ptr(part), slices, Kd * N, 1, Kd * N, L.ptr(out), None, None, 1.0, L.stream()), "spo_ma_partial_reduce")
+        want2 = A_.double().t() @ B2.double()
+        assert float((out.cpu().double() - want2).abs().max()) < 1e-5 * (M ** 0.5) * 4, (slices, M, N, Kd)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,D,DS,A,H", [(100, 10, 14, 3, 128), (777, 66, 130, 5, 256), (2048, 398, 398, 20, 512)])
+def test_ma_ppo_update_vs_oracle(N, D, DS, A, H):
+    """Two consecutive MAPPO_L_Trainer.ppo_update calls (mappolag.py:135-199) through safepo.common.ma_model.MultiAgentTrainer
+    against oracle/ma_oracle.py OracleMATrainer (pinned to the reference's trainer by tests/golden/ma_update.pt): the gradients of
+    every parameter tensor before the clip, the eight returned quantities, lamda_lagr, the PopArt statistics and all weights
+    after each update.  The last case is config 5's layer shape (obs 398, act 20, hidden 512) on a quarter of its rows."""
+    from oracle import ma_oracle as MA
+    from safepo.common.ma_model import MultiAgentNets, MultiAgentTrainer
+    dev = _cuda()
+    cfg = dict(golden("ma_update")["ma_update"]["cfg"])
+    g = torch.Generator().manual_seed(3 * N + D)
+    sa, sc, sk = _ma_state(g, D, H, A, "actor"), _ma_state(g, DS, H, A, "critic"), _ma_state(g, DS, H, A, "critic")
+    oa, oc, ok_ = MA.OracleMANet(sa), MA.OracleMANet(sc), MA.OracleMANet(sk)
+    obs, share = torch.randn(N, D, generator=g) * 2 + 0.5, torch.randn(N, DS, generator=g) * 3
+    with torch.no_grad():
+        dist = MA.ma_actor_dist(oa, obs)
+        actions = dist.mean + dist.stddev * torch.randn(N, A, generator=g)
+        logp = dist.log_prob(actions)
+        v0, k0 = MA.ma_critic_value(oc, share), MA.ma_critic_value(ok_, share)
+    sample = dict(share_obs=share, obs=obs, actions=actions, value_preds=v0 + 0.1 * torch.randn(N, 1, generator=g),
+                  returns=torch.randn(N, 1, generator=g) * 4 + 1, old_action_log_probs=logp + 0.05 * torch.randn(N, A, generator=g),
+                  adv_targ=torch.randn(N, 1, generator=g), factor=torch.rand(N, 1, generator=g) + 0.5,
+                  cost_preds=k0 + 0.1 * torch.randn(N, 1, generator=g), cost_returns=torch.randn(N, 1, generator=g).abs() * 30,
+                  cost_adv_targ=torch.randn(N, 1, generator=g), aver_episode_costs=torch.rand(N, 1, generator=g) * 60)
+    otr = MA.OracleMATrainer(oa, oc, ok_, cfg)
+    nets = MultiAgentNets(sa, sc, sk, dev, layer_N=cfg["layer_N"], std_x_coef=cfg["std_x_coef"], std_y_coef=cfg["std_y_coef"])
+    tr = MultiAgentTrainer(nets, cfg)
+    names = ("value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "imp_weights", "cost_loss", "cost_grad_norm")
+    worst = {}
+    for it in range(2):
+        want = otr.ppo_update(sample)
+        got = dict(zip(names, tr.ppo_update(sample)))
+        torch.cuda.synchronize()
+        for k in names:
+            ok, ea, er = close(got[k].reshape(-1), want[k].reshape(-1), rtol=1e-4, atol=2e-6)
+            assert ok, (it, k, ea, er)
+        # gradients before the clip: the oracle's .grad are the clipped ones
+        for net, onet, nk in ((nets.actor, oa, "actor_grad_norm"), (nets.critic, oc, "critic_grad_norm"), (nets.cost_critic, ok_, "cost_grad_norm")):
+            coef = min(1.0, float(cfg["max_grad_norm"]) / (float(want[nk]) + 1e-6))
+            for k, pt in onet.p.items():
+                wg = pt.grad / coef
+                err = float((net.g[k].cpu() - wg).abs().max())
+                scale = float(wg.abs().max())
+                worst[k] = max(worst.get(k, 0.0), err / (scale + 1e-12))
+                assert err <= 5e-5 * scale + 1e-7, (it, k, err, scale)
+        assert abs(float(tr.lamda_lagr) - float(otr.lamda_lagr)) <= 1e-5 * max(1.0, abs(float(otr.lamda_lagr))), (float(tr.lamda_lagr), float(otr.lamda_lagr))
+        pst = tr.popart_state.cpu()
+        for got_s, want_s in zip(pst, (otr.popart.running_mean, otr.popart.running_mean_sq, otr.popart.debiasing_term)):
+            assert abs(float(got_s) - float(want_s)) <= 1e-5 * abs(float(want_s)) + 1e-12
+        for net, onet in ((nets.actor, oa), (nets.critic, oc), (nets.cost_critic, ok_)):
+            for k, pt in onet.p.items():
+                err = float((net.p[k].cpu() - pt.detach()).abs().max())
+                assert err < 2e-5, (it, k, err)           # Adam steps of lr 5e-4
+    print(f"\nMA ppo_update N={N} D={D} H={H}: worst relative gradient error per tensor {max(worst.values()):.2e}")
+
