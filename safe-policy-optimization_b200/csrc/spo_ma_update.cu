@@ -10,9 +10,10 @@
 // and the loss heads (clipped surrogate on the product of per-dimension ratios with the Lagrangian-mixed advantage;
 // PopArt-normalised, clipped, one-sided-Huber value loss), the joint-norm clip and Adam on the packed parameter buffer.
 // Every reduction over rows is a two-stage sum in a fixed order (per-CTA partials, then one thread per output over the CTAs):
-// results do not depend on scheduling.  The products are fp32 FFMA tiles (64 x 64 x 16, 4 x 4 per thread); moving them to
-// tcgen05 with the 3xTF32 split of spo_tc_forward.cu is the next step for this path.
+// results do not depend on scheduling.  The products run on the tensor pipe as mma.sync 3xTF32 tiles (128 x 64 x 32); moving them to
+// tcgen05 with the 3xTF32 operand copies of spo_tc_forward.cu is the next step for this path.
 #include "spo_common.cuh"
+#include "spo_mma.cuh"
 
 namespace {
 
@@ -174,12 +175,17 @@ __global__ void __launch_bounds__(256) ma_partial_reduce_kernel(const ReduceArgs
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// fp32 tile products.  64 x 64 output tile, 16-deep chunks, thread (ty, tx) of 16 x 16 computes a 4 x 4 block.
+// Tile products on the tensor pipe: mma.sync m16n8k8 TF32 with the 3xTF32 split in registers (spo_mma.cuh: lo*hi + hi*lo + hi*hi,
+// small terms first -- fp32-grade results, ~1e-6 relative).  128 x 64 output tile, 32-deep chunks; warp w of 8 owns a 64 x 16 patch
+// (4 x 2 mma tiles: 20 operand loads per 24 mma).  Both operand tiles are staged k-major with leading dimensions = 8 (mod 32), which
+// makes the fragment loads of both operands bank-conflict free (the same rule as in spo_update.cu).
 //   NN: C[M][N] = A[M][Kd] B[Kd][N]                         (dx = dz W;  d feat = d mean W_out)
 //   TN: C[M][N] = sum_r A[r][M] B[r][N], r in the z-th slice of R rows -> part[z][M][N]   (dW = dz^T x)
 // All operands row-major fp32; edges are guarded element-wise, no alignment requirement beyond 4 bytes.
+// (The first version of these products was a 64 x 64 x 16 FFMA tile, 4 x 4 per thread: 16.5 TFLOP/s for a whole update.)
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int GT = 64, GK = 16;
+constexpr int GTM = 128, GTN = 64, GK = 32;
+constexpr int LDA_S = GTM + 8, LDB_S = GTN + 8;
 
 struct GemmArgs {
   const float *A, *B;
@@ -188,97 +194,93 @@ struct GemmArgs {
   int rows_per_slice;
 };
 
-__device__ __forceinline__ void tile_fma(float (&acc)[4][4], const float (*As)[GT + 4], const float (*Bs)[GT], int ty, int tx) {
+__device__ __forceinline__ void tile_store(const float (&acc)[4][2][4], float* C, int M, int N, int m_base, int n_base) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int kk = 0; kk < GK; ++kk) {
-    const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][4 * ty]);
-    const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][4 * tx]);
-    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+  for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-  }
+      for (int e = 0; e < 4; ++e) {
+        const int gm = m_base + 16 * mt + g + ((e >> 1) << 3), gn = n_base + 8 * nt + 2 * t + (e & 1);
+        if (gm < M && gn < N) C[static_cast<size_t>(gm) * N + gn] = acc[mt][nt][e];
+      }
 }
 
 __global__ void __launch_bounds__(256) ma_gemm_nn_kernel(const GemmArgs a) {
-  __shared__ __align__(16) float As[GK][GT + 4];   // [k][m]
-  __shared__ __align__(16) float Bs[GK][GT];       // [k][n]
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  __shared__ __align__(16) float As[GK * LDA_S];   // [k][m]
+  __shared__ __align__(16) float Bs[GK * LDB_S];   // [k][n]
+  const int tid = threadIdx.x, wid = tid >> 5;
+  const int m0 = blockIdx.y * GTM, n0 = blockIdx.x * GTN;
+  const int wm = (wid & 1) * 64, wn = (wid >> 1) * 16;
+  float acc[4][2][4];
+  spo_mma_zero<4>(acc);
   for (int k0 = 0; k0 < a.Kd; k0 += GK) {
-    {   // A tile: thread -> row tid >> 2, four consecutive k
-      const int r = tid >> 2, kb = (tid & 3) * 4, gm = m0 + r;
+    {   // A tile 128 x 32: thread -> row tid >> 1, sixteen consecutive k
+      const int r = tid >> 1, kb = (tid & 1) * 16, gm = m0 + r;
+      const float* src = a.A + static_cast<size_t>(gm) * a.Kd + k0 + kb;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int gk = k0 + kb + e;
-        As[kb + e][r] = (gm < a.M && gk < a.Kd) ? a.A[static_cast<size_t>(gm) * a.Kd + gk] : 0.f;
-      }
+      for (int e = 0; e < 16; ++e) As[(kb + e) * LDA_S + r] = (gm < a.M && k0 + kb + e < a.Kd) ? src[e] : 0.f;
     }
-    {   // B tile: thread -> k row tid >> 4, four consecutive n
-      const int kk = tid >> 4, cb = (tid & 15) * 4, gk = k0 + kk;
+    {   // B tile 32 x 64: thread -> k rows tid >> 4 and + 16, four consecutive n
+      const int kk = tid >> 4, cb = (tid & 15) * 4;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int gn = n0 + cb + e;
-        Bs[kk][cb + e] = (gk < a.Kd && gn < a.N) ? a.B[static_cast<size_t>(gk) * a.N + gn] : 0.f;
+      for (int h = 0; h < 2; ++h) {
+        const int gk = k0 + kk + 16 * h;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int gn = n0 + cb + e;
+          Bs[(kk + 16 * h) * LDB_S + cb + e] = (gk < a.Kd && gn < a.N) ? a.B[static_cast<size_t>(gk) * a.N + gn] : 0.f;
+        }
       }
     }
     __syncthreads();
-    tile_fma(acc, As, Bs, ty, tx);
+    spo_warp_mma_3xtf32<4>(acc, As, 1, LDA_S, Bs, LDB_S, 1, wm, wn, GK);
     __syncthreads();
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gm = m0 + 4 * ty + i;
-    if (gm >= a.M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gn = n0 + 4 * tx + j;
-      if (gn < a.N) a.C[static_cast<size_t>(gm) * a.N + gn] = acc[i][j];
-    }
-  }
+  tile_store(acc, a.C, a.M, a.N, m0 + wm, n0 + wn);
 }
 
 __global__ void __launch_bounds__(256) ma_gemm_tn_kernel(const GemmArgs a) {
-  __shared__ __align__(16) float As[GK][GT + 4];   // [r][m]
-  __shared__ __align__(16) float Bs[GK][GT];       // [r][n]
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+  __shared__ __align__(16) float As[GK * LDA_S];   // [r][m]
+  __shared__ __align__(16) float Bs[GK * LDB_S];   // [r][n]
+  const int tid = threadIdx.x, wid = tid >> 5;
+  const int m0 = blockIdx.y * GTM, n0 = blockIdx.x * GTN;
+  const int wm = (wid & 1) * 64, wn = (wid >> 1) * 16;
   const int r_begin = blockIdx.z * a.rows_per_slice;
   const int r_end = min(a.Kd, r_begin + a.rows_per_slice);
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float acc[4][2][4];
+  spo_mma_zero<4>(acc);
   for (int r0 = r_begin; r0 < r_end; r0 += GK) {
-    const int kk = tid >> 4, cb = (tid & 15) * 4, gr = r0 + kk;
+    {   // A tile 32 x 128: thread -> rows tid >> 5 + 8 i, four consecutive m
+      const int cb = (tid & 31) * 4;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int gm = m0 + cb + e, gn = n0 + cb + e;
-      As[kk][cb + e] = (gr < r_end && gm < a.M) ? a.A[static_cast<size_t>(gr) * a.M + gm] : 0.f;
-      Bs[kk][cb + e] = (gr < r_end && gn < a.N) ? a.B[static_cast<size_t>(gr) * a.N + gn] : 0.f;
+      for (int i = 0; i < 4; ++i) {
+        const int kk = (tid >> 5) + 8 * i, gr = r0 + kk;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int gm = m0 + cb + e;
+          As[kk * LDA_S + cb + e] = (gr < r_end && gm < a.M) ? a.A[static_cast<size_t>(gr) * a.M + gm] : 0.f;
+        }
+      }
+    }
+    {   // B tile 32 x 64
+      const int kk = tid >> 4, cb = (tid & 15) * 4;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int gr = r0 + kk + 16 * h;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int gn = n0 + cb + e;
+          Bs[(kk + 16 * h) * LDB_S + cb + e] = (gr < r_end && gn < a.N) ? a.B[static_cast<size_t>(gr) * a.N + gn] : 0.f;
+        }
+      }
     }
     __syncthreads();
-    tile_fma(acc, As, Bs, ty, tx);
+    spo_warp_mma_3xtf32<4>(acc, As, 1, LDA_S, Bs, LDB_S, 1, wm, wn, GK);
     __syncthreads();
   }
-  float* C = a.C + static_cast<size_t>(blockIdx.z) * a.M * a.N;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gm = m0 + 4 * ty + i;
-    if (gm >= a.M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gn = n0 + 4 * tx + j;
-      if (gn < a.N) C[static_cast<size_t>(gm) * a.N + gn] = acc[i][j];
-    }
-  }
+  tile_store(acc, a.C + static_cast<size_t>(blockIdx.z) * a.M * a.N, a.M, a.N, m0 + wm, n0 + wn);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -632,7 +634,7 @@ int spo_ma_partial_reduce(const float* part, int nblk, int stride, int nseg, int
 int spo_ma_gemm_nn(const float* A, const float* B, float* C, int M, int N, int Kd, void* stream) {
   SPO_REQUIRE(A && B && C && M > 0 && N > 0 && Kd > 0, SPO_ERR_INVALID_ARG, "spo_ma_gemm_nn: null argument or empty shape");
   GemmArgs a{A, B, C, M, N, Kd, 0};
-  dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT, 1);
+  dim3 grid((N + GTN - 1) / GTN, (M + GTM - 1) / GTM, 1);
   SPO_REQUIRE(grid.y <= 65535, SPO_ERR_UNSUPPORTED, "spo_ma_gemm_nn: M=%d too large", M);
   ma_gemm_nn_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   SPO_CUDA_TRY(cudaGetLastError());
@@ -645,7 +647,7 @@ int spo_ma_gemm_tn(const float* A, const float* B, float* part, int R, int M, in
   const int rps = ((R + slices - 1) / slices + GK - 1) / GK * GK;
   SPO_REQUIRE(static_cast<long long>(rps) * (slices - 1) < R, SPO_ERR_INVALID_ARG, "spo_ma_gemm_tn: %d slices leave an empty slice for R=%d", slices, R);
   GemmArgs a{A, B, part, M, N, R, rps};
-  dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT, slices);
+  dim3 grid((N + GTN - 1) / GTN, (M + GTM - 1) / GTM, slices);
   ma_gemm_tn_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   SPO_CUDA_TRY(cudaGetLastError());
   return SPO_OK;

@@ -163,9 +163,9 @@ class MultiAgentTrainer:
 
     def _gemm_tn(self, A_, B_, out, R, M, N, ws):
         """out[M][N] = A_[R][M]^T B_[R][N] (sum over the R rows in slices, partials reduced in order)."""
-        tiles = ((M + 63) // 64) * ((N + 63) // 64)
+        tiles = ((M + 127) // 128) * ((N + 63) // 64)            # 128 x 64 output tiles, >= 2 CTAs per SM wanted
         slices = max(1, min(32, (296 + tiles - 1) // tiles, R // 256))
-        while slices > 1 and (slices - 1) * (((R + slices - 1) // slices + 15) // 16 * 16) >= R:
+        while slices > 1 and (slices - 1) * (((R + slices - 1) // slices + 31) // 32 * 32) >= R:   # no empty slice (32-row chunks)
             slices -= 1
         _launch("spo_ma_gemm_tn", L.ptr(A_), L.ptr(B_), L.ptr(ws["part"]), R, M, N, slices, L.stream())
         _launch("spo_ma_partial_reduce", L.ptr(ws["part"]), slices, M * N, 1, M * N, L.ptr(out), None, None, 1.0, L.stream())

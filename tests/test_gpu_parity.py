@@ -899,7 +899,7 @@ def test_ma_get_actions_vs_oracle(N, D, DS, A, H):
 @pytest.mark.parametrize("M,N,Kd", [(100, 14, 128), (777, 130, 256), (64, 64, 16), (1000, 398, 512), (333, 512, 20), (50, 128, 1)])
 def test_ma_tile_products_vs_float64(M, N, Kd):
     """spo_ma_gemm_nn (C = A B) and spo_ma_gemm_tn + spo_ma_partial_reduce (C = A^T B over row slices) against float64
-    products of the same fp32 inputs: edges that are not multiples of the 64 x 64 x 16 tile, one-column and one-row operands."""
+    products of the same fp32 inputs: edges that are not multiples of the 128 x 64 x 32 tile, one-column and one-row operands."""
     from safepo import _lib as L
     dev = _cuda()
     g = torch.Generator().manual_seed(M * 7 + N)
@@ -913,7 +913,7 @@ def test_ma_tile_products_vs_float64(M, N, Kd):
     B2 = torch.randn(M, N, generator=g)
     B2d = B2.to(dev)
     for slices in (1, 3):
-        if slices > 1 and M < 100:     # three slices of >= 16 rows each need more rows than that
+        if slices > 1 and M < 200:     # three slices of whole 32-row chunks need more rows than that
             continue
         part = torch.empty(slices * Kd * N, device=dev)
         out = torch.empty(Kd, N, device=dev)
