@@ -38,11 +38,11 @@ for _ in range(3):
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-for _ in range(10):
+for _ in range(int(os.environ.get('REPS', 10))):
     nets.get_actions(cent, obs)
 e1.record()
 torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 10
+ms = e0.elapsed_time(e1) / int(os.environ.get('REPS', 10))
 flops = 3 * N * 2 * (D * H + 2 * H * H) + N * 2 * H * (A + 2)
 print(f"get_actions at N={N}: {ms:.3f} ms per call (3 nets x 3 layers + heads), {flops / ms / 1e9:.1f} TFLOP/s fp32")
 
@@ -61,11 +61,11 @@ for _ in range(2):
     out = tr.ppo_update(sample)
 torch.cuda.synchronize()
 e0.record()
-for _ in range(5):
+for _ in range(int(os.environ.get('UREPS', 5))):
     out = tr.ppo_update(sample)
 e1.record()
 torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 5
+ms = e0.elapsed_time(e1) / int(os.environ.get('UREPS', 5))
 # forward + dW + dx per layer product: 3 x the forward flops (the first layer has no dx into the observations' LayerNorm input... it does: d xn)
 uflops = 3 * flops
 print(f"ppo_update at N={N}: {ms:.3f} ms per update (3 nets: forward, backward, clip + Adam), {uflops / ms / 1e9:.1f} TFLOP/s fp32; "
