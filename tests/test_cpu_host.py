@@ -319,3 +319,36 @@ def test_vectorised_episode_accounting_is_bit_identical_to_the_per_env_loop():
         assert got.shape == (len(want[key]),) and np.array_equal(got, np.asarray(want[key])), key
     assert list(fast.rew_deque) == list(rd) and list(fast.len_deque) == list(ld)
     assert np.array_equal(fast.ep_ret, ref_ret) and not fast.logger.logged
+
+
+def test_multi_agent_net_packing_and_no_cpu_path():
+    """safepo/common/ma_model.py host logic: one packed fp32 buffer per net with every tensor on a 16-byte boundary, parameters and
+    gradients as views under the reference's state_dict names; the nets refuse a CPU device (no fallback)."""
+    from safepo import _lib as L
+    from safepo.common.ma_model import MultiAgentNets, _Net
+    g = torch.Generator().manual_seed(0)
+    D, H, A = 10, 128, 3
+    st = {"base.feature_norm.weight": torch.randn(D, generator=g), "base.feature_norm.bias": torch.randn(D, generator=g)}
+    dims = [D, H, H]
+    for li, name in enumerate(("fc1", "fc2.0")):
+        st[f"base.mlp.{name}.0.weight"] = torch.randn(H, dims[li], generator=g)
+        st[f"base.mlp.{name}.0.bias"] = torch.randn(H, generator=g)
+        st[f"base.mlp.{name}.2.weight"] = torch.randn(H, generator=g)
+        st[f"base.mlp.{name}.2.bias"] = torch.randn(H, generator=g)
+    st["act.action_out.log_std"] = torch.randn(A, generator=g)
+    st["act.action_out.fc_mean.weight"] = torch.randn(A, H, generator=g)
+    st["act.action_out.fc_mean.bias"] = torch.randn(A, generator=g)
+    net = _Net(st, torch.device("cpu"), layer_N=1)
+    assert (net.D, net.H, len(net.blocks)) == (D, H, 2)
+    base = net.flat.data_ptr()
+    for k, v in st.items():
+        assert torch.equal(net.p[k], v) and net.p[k].shape == v.shape
+        assert (net.p[k].data_ptr() - base) % 16 == 0 and (net.g[k].data_ptr() - net.gflat.data_ptr()) == (net.p[k].data_ptr() - base)
+    net.flat.zero_()                                    # the parameters are views of the packed buffer
+    assert all(float(t.abs().sum()) == 0.0 for t in net.p.values())
+    assert net.flat.numel() >= sum(v.numel() for v in st.values()) and net.flat.numel() % 4 == 0
+    sd = net.state_dict()
+    assert list(sd) == list(st)                        # state_dict order and names of the reference
+    with pytest.raises(L.SpoError, match="CUDA"):
+        MultiAgentNets(st, st, st, "cpu")
+
