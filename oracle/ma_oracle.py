@@ -185,3 +185,138 @@ class OracleMATrainer:
         return dict(value_loss=value_loss.detach(), critic_grad_norm=critic_grad_norm, policy_loss=policy_loss.detach(),
                     dist_entropy=dist_entropy.detach(), actor_grad_norm=actor_grad_norm, imp_weights=imp_weights.detach(),
                     cost_loss=cost_loss.detach(), cost_grad_norm=cost_grad_norm)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# MAPPO-Lag replay buffer, trainer.train and the runner's iteration (the callers of ppo_update).
+# Restates safepo/common/buffer.py:209-465 (SeparatedReplayBuffer: insert :281-337, after_update :339-348, compute_returns /
+# compute_cost_returns :356-384 = masked_gae above, feed_forward_generator :386-465), safepo/multi_agent/mappolag.py:200-234
+# (MAPPO_L_Trainer.train) and :402-504,583-597 (Runner.collect / insert / train / compute), same torch ops in the same order and
+# the same draws from torch's global generator (Normal.sample per agent in collect; randperm over the agents and over the batch
+# in train).  Pinned by tests/golden/ma_epoch.pt (two iterations of two agents through the reference's own methods).
+# Reference quirk kept: train() marks inactive entries with NaN and then takes torch.mean / torch.std (not nanmean), so the
+# advantages of a buffer with ANY inactive entry are all NaN; only the all-active case is meaningful (and pinned).
+# ---------------------------------------------------------------------------------------------------------------------
+class OracleMABuffer:
+    def __init__(self, T, N, obs_dim, share_obs_dim, act_dim, gamma, gae_lambda):
+        self.T, self.N, self.gamma, self.gae_lambda = T, N, gamma, gae_lambda
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32)      # noqa: E731
+        self.aver_episode_costs = z(T + 1, N, obs_dim)           # buffer.py:240 (sic: observation-shaped until the first return_aver_insert)
+        self.share_obs, self.obs = z(T + 1, N, share_obs_dim), z(T + 1, N, obs_dim)
+        self.value_preds, self.returns = z(T + 1, N, 1), z(T + 1, N, 1)
+        self.cost_preds, self.cost_returns = z(T + 1, N, 1), z(T + 1, N, 1)
+        self.actions, self.action_log_probs = z(T, N, act_dim), z(T, N, act_dim)
+        self.rewards, self.costs = z(T, N, 1), z(T, N, 1)
+        self.masks, self.active_masks = torch.ones(T + 1, N, 1), torch.ones(T + 1, N, 1)
+        self.factor = torch.ones(T, N, 1)
+        self.step = 0
+
+    def insert(self, share_obs, obs, actions, action_log_probs, value_preds, rewards, masks, active_masks, costs, cost_preds):
+        s = self.step
+        self.share_obs[s + 1].copy_(share_obs)
+        self.obs[s + 1].copy_(obs)
+        self.actions[s].copy_(actions)
+        self.action_log_probs[s].copy_(action_log_probs)
+        self.value_preds[s].copy_(value_preds)
+        self.rewards[s].copy_(rewards)
+        self.masks[s + 1].copy_(masks)
+        self.active_masks[s + 1].copy_(active_masks)
+        self.costs[s].copy_(costs)
+        self.cost_preds[s].copy_(cost_preds)
+        self.step = (s + 1) % self.T
+
+    def after_update(self):
+        for t in (self.share_obs, self.obs, self.masks, self.active_masks):
+            t[0].copy_(t[-1])
+
+    def compute_returns(self, next_value, popart):
+        self.value_preds[-1] = next_value
+        self.returns[:-1] = masked_gae(self.rewards, self.value_preds, self.masks, popart, self.gamma, self.gae_lambda)
+
+    def compute_cost_returns(self, next_cost, popart):
+        self.cost_preds[-1] = next_cost
+        self.cost_returns[:-1] = masked_gae(self.costs, self.cost_preds, self.masks, popart, self.gamma, self.gae_lambda)
+
+    def whole_batch_sample(self, advantages, cost_adv):
+        """feed_forward_generator with num_mini_batch = 1: ONE sample holding every row in a random order (randperm from the
+        global generator)."""
+        idx = torch.randperm(self.T * self.N)
+        flat = lambda t: t.reshape(-1, t.shape[-1])[idx]        # noqa: E731
+        return dict(share_obs=flat(self.share_obs[:-1]), obs=flat(self.obs[:-1]), actions=flat(self.actions),
+                    value_preds=flat(self.value_preds[:-1]), returns=flat(self.returns[:-1]),
+                    old_action_log_probs=flat(self.action_log_probs), adv_targ=flat(advantages), factor=flat(self.factor),
+                    cost_preds=flat(self.cost_preds[:-1]), cost_returns=flat(self.cost_returns[:-1]), cost_adv_targ=flat(cost_adv),
+                    aver_episode_costs=self.aver_episode_costs)
+
+
+def ma_trainer_train(trainer, buf, learning_iters):
+    """MAPPO_L_Trainer.train (mappolag.py:200-234): advantages = returns - denormalised predictions, standardised with the
+    (NaN-propagating, see the header) mean / unbiased std over the active entries; learning_iters whole-batch updates."""
+    def standardise(ret, pred):
+        adv = ret[:-1] - trainer.popart.denormalize(pred[:-1])
+        copy = adv.clone()
+        copy[buf.active_masks[:-1] == 0.0] = float("nan")
+        return (adv - torch.mean(copy)) / (torch.std(copy) + 1e-8)
+    advantages = standardise(buf.returns, buf.value_preds)
+    cost_adv = standardise(buf.cost_returns, buf.cost_preds)
+    out = None
+    for _ in range(learning_iters):
+        out = trainer.ppo_update(buf.whole_batch_sample(advantages, cost_adv))
+    return out
+
+
+class OracleMARunner:
+    """The per-iteration part of Runner (mappolag.py:300-345 without environments and logging): agents = list of
+    (actor, critic, cost_critic) OracleMANets."""
+
+    def __init__(self, nets, cfg, T, N, obs_dim, share_obs_dim, act_dim):
+        self.cfg, self.T, self.N, self.num_agents = cfg, T, N, len(nets)
+        self.nets = nets
+        self.trainer = [OracleMATrainer(a, c, k, cfg) for a, c, k in nets]
+        self.buffer = [OracleMABuffer(T, N, obs_dim, share_obs_dim, act_dim, cfg["gamma"], cfg["gae_lambda"]) for _ in nets]
+
+    def warmup(self, obs, share_obs):
+        for a, b in enumerate(self.buffer):
+            b.share_obs[0].copy_(share_obs[:, a])
+            b.obs[0].copy_(obs[:, a])
+
+    def collect(self, step):
+        values, actions, logps, cost_preds = [], [], [], []
+        for a, (actor, critic, cost_critic) in enumerate(self.nets):
+            b = self.buffer[a]
+            v, act, lp, cp = ma_get_actions(actor, critic, cost_critic, b.share_obs[step], b.obs[step])
+            values.append(v), actions.append(act), logps.append(lp), cost_preds.append(cp)
+        return torch.transpose(torch.stack(values), 1, 0), actions, logps, torch.transpose(torch.stack(cost_preds), 1, 0)
+
+    def insert(self, obs, share_obs, rewards, costs, dones, values, actions, action_log_probs, cost_preds):
+        dones_env = torch.all(dones, dim=1)
+        masks = torch.ones(self.N, self.num_agents, 1)
+        masks[dones_env] = 0.0
+        active_masks = torch.ones(self.N, self.num_agents, 1)
+        active_masks[dones] = 0.0
+        active_masks[dones_env] = 1.0
+        for a, b in enumerate(self.buffer):
+            b.insert(share_obs[:, a], obs[:, a], actions[a], action_log_probs[a], values[:, a], rewards[:, a], masks[:, a], active_masks[:, a],
+                     costs[:, a], cost_preds[:, a])
+
+    def compute(self):
+        with torch.no_grad():
+            for (actor, critic, cost_critic), b, tr in zip(self.nets, self.buffer, self.trainer):
+                b.compute_returns(ma_critic_value(critic, b.share_obs[-1]), tr.popart)
+                b.compute_cost_returns(ma_critic_value(cost_critic, b.share_obs[-1]), tr.popart)
+
+    def train(self):
+        factor = torch.ones(self.T, self.N, 1)
+        for agent_id in torch.randperm(self.num_agents):
+            a = int(agent_id)
+            b, tr, actor = self.buffer[a], self.trainer[a], self.nets[a][0]
+            A = b.actions.shape[-1]
+            b.factor.copy_(factor)
+            flat_obs, flat_act = b.obs[:-1].reshape(-1, b.obs.shape[-1]), b.actions.reshape(-1, A)
+            with torch.no_grad():
+                old_lp = ma_actor_dist(actor, flat_obs).log_prob(flat_act)
+            ma_trainer_train(tr, b, self.cfg["learning_iters"])
+            with torch.no_grad():
+                new_lp = ma_actor_dist(actor, flat_obs).log_prob(flat_act)
+            factor = factor * torch.prod(torch.exp(new_lp - old_lp).reshape(self.T, self.N, A), dim=-1, keepdim=True)
+            b.after_update()

@@ -423,12 +423,101 @@ def gen_ma_update(ref, out):
     out["ma_update"] = dict(cfg={k: cfg[k] for k in keep}, dims=(D, DS, A, N), init=init_state, actions=acts, sample=sample, steps=steps)
 
 
+def gen_ma_epoch(ref, out):
+    """Two whole MAPPO-Lag training iterations of TWO agents through the reference's own Runner methods (collect / insert /
+    compute / train of safepo/multi_agent/mappolag.py:402-504,583-597, called on a stand-in ``self`` that carries the real
+    MAPPO_L_Policy / MAPPO_L_Trainer / SeparatedReplayBuffer objects -- the Runner's constructor needs environments that are not
+    installable here) on a synthetic environment stream: T = 4 steps, 6 envs, hidden 32, learning_iters 2.  Stored: the initial
+    state dicts, the env stream, the global-RNG seed, and after every iteration the buffers' returns / cost returns / factor,
+    lamda_lagr, the PopArt state and every state dict."""
+    import yaml
+    m = importlib.import_module("safepo.multi_agent.mappolag")
+    cfg = yaml.safe_load(open(os.path.join(REF, "safepo", "multi_agent", "marl_cfg", "mappolag", "config.yaml")))
+    T, N, D, DS, A, H, NA = 4, 6, 10, 14, 3, 32, 2
+    cfg.update(device="cpu", algorithm_name="mappolag", n_rollout_threads=N, hidden_size=H, episode_length=T, learning_iters=2,
+               env_name="synthetic", entropy_coef=0.01)
+
+    class Sp:
+        def __init__(self, d):
+            self.shape = (d,)
+
+    class Log:
+        def store(self, **kw):
+            pass
+
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)          # LayerNorm's backward reductions depend on the intra-op thread count (see gen_ma_update)
+    torch.manual_seed(21)
+    policy = [m.MAPPO_L_Policy(cfg, Sp(D), Sp(DS), Sp(A)) for _ in range(NA)]
+    with torch.no_grad():
+        for pol in policy:
+            for net in (pol.actor, pol.critic, pol.cost_critic):
+                for k, v in net.state_dict().items():
+                    if k.endswith("bias") or ".2.weight" in k or "feature_norm" in k or k.endswith("log_std"):
+                        v.add_(0.1 * torch.randn_like(v))
+    init_state = [{n: {k: v.clone() for k, v in getattr(pol, n).state_dict().items()} for n in ("actor", "critic", "cost_critic")} for pol in policy]
+    fake = types.SimpleNamespace(config=cfg, num_agents=NA, logger=Log(), policy=policy,
+                                 trainer=[m.MAPPO_L_Trainer(cfg, pol) for pol in policy],
+                                 buffer=[m.SeparatedReplayBuffer(cfg, Sp(D), Sp(DS), Sp(A)) for _ in range(NA)])
+    g = torch.Generator().manual_seed(22)
+    obs0, share0 = torch.randn(N, NA, D, generator=g) * 2 + 0.5, torch.randn(N, NA, DS, generator=g) * 3
+    for a in range(NA):                                    # Runner.warmup
+        fake.buffer[a].share_obs[0].copy_(share0[:, a])
+        fake.buffer[a].obs[0].copy_(obs0[:, a])
+    stream, iters = [], []
+    seed = 77
+    torch.manual_seed(seed)
+    train_episode_costs = torch.zeros(1, N)
+    for it in range(2):
+        steps = []
+        for step in range(T):
+            values, actions, action_log_probs, rnn_states, rnn_states_critic, cost_preds, rnn_states_cost = m.Runner.collect(fake, step)
+            obs, share_obs = torch.randn(N, NA, D, generator=g) * 2 + 0.5, torch.randn(N, NA, DS, generator=g) * 3
+            rewards, costs = torch.randn(N, NA, 1, generator=g), (torch.rand(N, NA, 1, generator=g) < 0.3).float()
+            done_env = torch.rand(N, generator=g) < 0.2
+            # all agents of an env finish together: an agent finishing alone zeroes its active mask, and MAPPO_L_Trainer.train
+            # (mappolag.py:202-205) then takes torch.mean over a copy with NaNs written into it -- the reference's own update
+            # turns to NaN in that case (it means nanmean), so only the all-or-none case is a usable fixture
+            dones = done_env[:, None].expand(N, NA).clone()
+            train_episode_costs += torch.mean(costs, dim=1).flatten()
+            for t in range(N):
+                if bool(torch.all(dones, dim=1)[t]):
+                    train_episode_costs[:, t] = 0
+            data = (obs, share_obs, rewards, costs, dones, None, values, actions, action_log_probs, rnn_states, rnn_states_critic,
+                    cost_preds, rnn_states_cost, train_episode_costs.mean())
+            m.Runner.insert(fake, data)
+            steps.append(dict(obs=obs, share_obs=share_obs, rewards=rewards, costs=costs, dones=dones,
+                              values=values.clone(), actions=[x.clone() for x in actions], action_log_probs=[x.clone() for x in action_log_probs],
+                              cost_preds=cost_preds.clone()))
+        m.Runner.compute(fake)
+        after_compute = [dict(returns=b.returns.clone(), cost_returns=b.cost_returns.clone(), value_preds=b.value_preds.clone(),
+                              cost_preds=b.cost_preds.clone(), masks=b.masks.clone(), active_masks=b.active_masks.clone()) for b in fake.buffer]
+        m.Runner.train(fake)
+        res = []
+        for a in range(NA):
+            tr, vn = fake.trainer[a], fake.trainer[a].value_normalizer
+            res.append(dict(factor=fake.buffer[a].factor.clone(), lamda_lagr=torch.as_tensor(tr.lamda_lagr).clone(),
+                            popart=(vn.running_mean.clone(), vn.running_mean_sq.clone(), vn.debiasing_term.clone()),
+                            state={n: {k: v.clone() for k, v in getattr(policy[a], n).state_dict().items()} for n in ("actor", "critic", "cost_critic")}))
+        stream.append(steps)
+        iters.append(dict(after_compute=after_compute, agents=res))
+        if it == 0:                                          # Runner.return_aver_cost after an iteration with finished episodes
+            for a in range(NA):
+                fake.buffer[a].return_aver_insert(torch.tensor(31.5))
+    keep = ("actor_lr", "critic_lr", "opti_eps", "weight_decay", "clip_param", "huber_delta", "entropy_coef", "max_grad_norm", "cost_limit",
+            "gamma", "gae_lambda", "lagrangian_coef_rate", "value_loss_coef", "lamda_lagr", "layer_N", "std_x_coef", "std_y_coef", "learning_iters",
+            "num_mini_batch", "episode_length", "n_rollout_threads")
+    torch.set_num_threads(threads)
+    out["ma_epoch"] = dict(cfg={k: cfg[k] for k in keep}, dims=(T, N, D, DS, A, H, NA), init=init_state, obs0=obs0, share_obs0=share0, seed=seed,
+                           stream=stream, iters=iters, aver_cost_after_first=31.5)
+
+
 def main():
     sys.path.insert(0, ROOT)
     ref = import_reference()
     only = set(sys.argv[1:])      # e.g. `python make_golden.py siblings` regenerates one fixture
     for name, fn in (("forward", gen_forward), ("gae", gen_gae), ("lagrange", gen_lagrange), ("update", gen_update_chain),
-                     ("dataloader", gen_dataloader), ("trust", gen_trust), ("main_runs", gen_main_runs), ("siblings", gen_siblings), ("ma_gae", gen_ma_gae), ("ma_update", gen_ma_update)):
+                     ("dataloader", gen_dataloader), ("trust", gen_trust), ("main_runs", gen_main_runs), ("siblings", gen_siblings), ("ma_gae", gen_ma_gae), ("ma_update", gen_ma_update), ("ma_epoch", gen_ma_epoch)):
         if only and name not in only:
             continue
         out = {}

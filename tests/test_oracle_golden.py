@@ -242,3 +242,52 @@ def test_ma_networks_and_ppo_update_match_reference(golden):
             for key, want in step["state"][n].items():
                 assert torch.equal(nets[n].p[key].detach(), want), (n, key)
     torch.set_num_threads(threads)
+
+
+def test_ma_buffer_trainer_and_runner_iteration_match_reference(golden):
+    """SURVEY 8f rank 3, the callers of ppo_update: the oracle's SeparatedReplayBuffer / MAPPO_L_Trainer.train / Runner.collect,
+    insert, compute, train (buffer.py:209-465, mappolag.py:200-234,402-504,583-597) against two whole iterations of two agents
+    run through the reference's own methods (tests/golden/ma_epoch.pt): sampled actions and log-probs of every step (same draws
+    from the global generator), masks, returns and cost returns after compute(), and after train() the cross-agent factor,
+    lamda_lagr, the PopArt statistics and all weights of both agents -- bit for bit."""
+    from oracle import ma_oracle as MA
+    c = golden("ma_epoch")["ma_epoch"]
+    T, N, D, DS, A, H, NA = c["dims"]
+    cfg = c["cfg"]
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        nets = [tuple(MA.OracleMANet(st[n], layer_N=cfg["layer_N"]) for n in ("actor", "critic", "cost_critic")) for st in c["init"]]
+        run = MA.OracleMARunner(nets, cfg, T, N, D, DS, A)
+        run.warmup(c["obs0"], c["share_obs0"])
+        torch.manual_seed(c["seed"])
+        for it in range(2):
+            for step in range(T):
+                s = c["stream"][it][step]
+                values, actions, logps, cost_preds = run.collect(step)
+                assert torch.equal(values, s["values"]) and torch.equal(cost_preds, s["cost_preds"]), (it, step)
+                for a in range(NA):
+                    assert torch.equal(actions[a], s["actions"][a]) and torch.equal(logps[a], s["action_log_probs"][a]), (it, step, a)
+                run.insert(s["obs"], s["share_obs"], s["rewards"], s["costs"], s["dones"], values, actions, logps, cost_preds)
+            run.compute()
+            for a in range(NA):
+                want, b = c["iters"][it]["after_compute"][a], run.buffer[a]
+                for k in ("returns", "cost_returns", "value_preds", "cost_preds", "masks", "active_masks"):
+                    assert torch.equal(getattr(b, k), want[k]), (it, a, k)
+            run.train()
+            for a in range(NA):
+                want = c["iters"][it]["agents"][a]
+                assert torch.equal(run.buffer[a].factor, want["factor"]), (it, a)
+                assert float(run.trainer[a].lamda_lagr) == float(want["lamda_lagr"]), (it, a)
+                pop = run.trainer[a].popart
+                for got, w in zip((pop.running_mean, pop.running_mean_sq, pop.debiasing_term), want["popart"]):
+                    assert torch.equal(got.reshape(-1), w.reshape(-1)), (it, a)
+                for n, net in zip(("actor", "critic", "cost_critic"), run.nets[a]):
+                    for k, v in want["state"][n].items():
+                        assert torch.equal(net.p[k].detach(), v), (it, a, n, k)
+            if it == 0:                       # Runner.return_aver_cost after an iteration with finished episodes
+                for b in run.buffer:
+                    b.aver_episode_costs = torch.tensor(c["aver_cost_after_first"])
+        assert any(bool((c["iters"][1]["agents"][a]["factor"] != 1).any()) for a in range(NA))     # the factor did move
+    finally:
+        torch.set_num_threads(threads)
