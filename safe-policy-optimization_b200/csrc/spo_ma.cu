@@ -3,14 +3,17 @@
 // safepo/utils/mlp.py:9-61 (LayerNorm -> [Linear -> ELU -> LayerNorm] x (1 + layer_N)) and the DiagGaussian head of
 // safepo/utils/distributions.py:21-42 / act.py:24-43 (std = sigmoid(log_std / x_coef) * y_coef, per-dimension log-probs).
 //
-// First slice of SURVEY section 8f rank 3: forward only, fp32 FFMA tiles (the update of these nets is not built).  One
+// First slice of SURVEY section 8f rank 3: the forward, fp32 FFMA tiles; with `pre` / `xn` outputs the same kernel is the training
+// forward of the update (second slice, spo_ma_update.cu).  One
 // launch per hidden layer: a CTA owns 32 rows x ALL H outputs, so the LayerNorm over the H outputs of a row is a warp-level
 // reduction in the epilogue (warp w holds rows 4w..4w+3 completely: lane l owns columns 4l..4l+3 of every 128-column block).
 // The K loop stages 16-wide chunks of W (transposed to [k][h]: conflict-free float4 reads) and of the input rows (with the
 // optional input LayerNorm applied on the fly) in shared memory: 256 FMA per 20 shared-memory float4 loads per thread.
 // Algorithmic cost per row and layer: 2 K H FLOP, 4 (K + H) bytes; at config 5 (N = 8192, K = 398 / 512, H = 512) a layer is
-// 3.3 / 4.3 GFLOP and FFMA-bound.  The tensor-core version of these layers (K-major operand tiles do not fit one SM's shared
-// memory at H = 512: a cluster would split H and exchange the LayerNorm statistics) is the next step, DESIGN.md section 8.
+// 3.3 / 4.3 GFLOP and FFMA-bound.  A tensor-pipe variant (mma.sync 3xTF32 with the truncating register split, LayerNorm statistics
+// exchanged between eight column groups) measured 15 % faster but 3x less accurate through three layers and was not kept
+// (DESIGN.md section 4.6); the tcgen05 version (K-major operand tiles do not fit one SM's shared memory: a cluster would split H
+// and exchange the LayerNorm statistics) is the next step, DESIGN.md section 8.
 #include "spo_common.cuh"
 
 namespace {
