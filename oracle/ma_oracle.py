@@ -237,10 +237,10 @@ class OracleMABuffer:
         self.cost_preds[-1] = next_cost
         self.cost_returns[:-1] = masked_gae(self.costs, self.cost_preds, self.masks, popart, self.gamma, self.gae_lambda)
 
-    def whole_batch_sample(self, advantages, cost_adv):
+    def whole_batch_sample(self, advantages, cost_adv, perm=None):
         """feed_forward_generator with num_mini_batch = 1: ONE sample holding every row in a random order (randperm from the
-        global generator)."""
-        idx = torch.randperm(self.T * self.N)
+        global generator; ``perm`` replaces the draw when a test needs the same order on both sides)."""
+        idx = torch.randperm(self.T * self.N) if perm is None else perm
         flat = lambda t: t.reshape(-1, t.shape[-1])[idx]        # noqa: E731
         return dict(share_obs=flat(self.share_obs[:-1]), obs=flat(self.obs[:-1]), actions=flat(self.actions),
                     value_preds=flat(self.value_preds[:-1]), returns=flat(self.returns[:-1]),
@@ -249,7 +249,7 @@ class OracleMABuffer:
                     aver_episode_costs=self.aver_episode_costs)
 
 
-def ma_trainer_train(trainer, buf, learning_iters):
+def ma_trainer_train(trainer, buf, learning_iters, perms=None):
     """MAPPO_L_Trainer.train (mappolag.py:200-234): advantages = returns - denormalised predictions, standardised with the
     (NaN-propagating, see the header) mean / unbiased std over the active entries; learning_iters whole-batch updates."""
     def standardise(ret, pred):
@@ -260,8 +260,8 @@ def ma_trainer_train(trainer, buf, learning_iters):
     advantages = standardise(buf.returns, buf.value_preds)
     cost_adv = standardise(buf.cost_returns, buf.cost_preds)
     out = None
-    for _ in range(learning_iters):
-        out = trainer.ppo_update(buf.whole_batch_sample(advantages, cost_adv))
+    for it in range(learning_iters):
+        out = trainer.ppo_update(buf.whole_batch_sample(advantages, cost_adv, None if perms is None else perms[it]))
     return out
 
 
@@ -280,11 +280,18 @@ class OracleMARunner:
             b.share_obs[0].copy_(share_obs[:, a])
             b.obs[0].copy_(obs[:, a])
 
-    def collect(self, step):
+    def collect(self, step, eps=None):
+        """eps: per-agent standard-normal draws replacing Normal.sample() (tests that need the same draws on both sides)."""
         values, actions, logps, cost_preds = [], [], [], []
         for a, (actor, critic, cost_critic) in enumerate(self.nets):
             b = self.buffer[a]
-            v, act, lp, cp = ma_get_actions(actor, critic, cost_critic, b.share_obs[step], b.obs[step])
+            if eps is None:
+                v, act, lp, cp = ma_get_actions(actor, critic, cost_critic, b.share_obs[step], b.obs[step])
+            else:
+                with torch.no_grad():
+                    dist = ma_actor_dist(actor, b.obs[step])
+                    act = dist.mean + dist.stddev * eps[a]
+                    v, lp, cp = ma_critic_value(critic, b.share_obs[step]), dist.log_prob(act), ma_critic_value(cost_critic, b.share_obs[step])
             values.append(v), actions.append(act), logps.append(lp), cost_preds.append(cp)
         return torch.transpose(torch.stack(values), 1, 0), actions, logps, torch.transpose(torch.stack(cost_preds), 1, 0)
 
@@ -305,9 +312,9 @@ class OracleMARunner:
                 b.compute_returns(ma_critic_value(critic, b.share_obs[-1]), tr.popart)
                 b.compute_cost_returns(ma_critic_value(cost_critic, b.share_obs[-1]), tr.popart)
 
-    def train(self):
+    def train(self, agent_order=None, perms=None):
         factor = torch.ones(self.T, self.N, 1)
-        for agent_id in torch.randperm(self.num_agents):
+        for agent_id in (torch.randperm(self.num_agents) if agent_order is None else agent_order):
             a = int(agent_id)
             b, tr, actor = self.buffer[a], self.trainer[a], self.nets[a][0]
             A = b.actions.shape[-1]
@@ -315,7 +322,7 @@ class OracleMARunner:
             flat_obs, flat_act = b.obs[:-1].reshape(-1, b.obs.shape[-1]), b.actions.reshape(-1, A)
             with torch.no_grad():
                 old_lp = ma_actor_dist(actor, flat_obs).log_prob(flat_act)
-            ma_trainer_train(tr, b, self.cfg["learning_iters"])
+            ma_trainer_train(tr, b, self.cfg["learning_iters"], None if perms is None else perms[a])
             with torch.no_grad():
                 new_lp = ma_actor_dist(actor, flat_obs).log_prob(flat_act)
             factor = factor * torch.prod(torch.exp(new_lp - old_lp).reshape(self.T, self.N, A), dim=-1, keepdim=True)

@@ -148,3 +148,78 @@ def masked_gae_returns(rewards, value_preds, masks, popart_mean, popart_sqrt_var
     L.check(L.lib().spo_gae_masked(L.ptr(rewards), L.ptr(value_preds), L.ptr(masks), float(popart_mean), float(popart_sqrt_var),
                                    float(gamma), float(gamma) * float(gae_lambda), L.ptr(out), N, T, L.stream()), "spo_gae_masked")
     return out
+
+
+class SeparatedReplayBuffer:
+    """The multi-agent buffer of one agent on the device (reference safepo/common/buffer.py:209-465; MLP policies: no
+    recurrent states, continuous actions: no available_actions).  Time-major tensors [T+1, N, ...] / [T, N, ...] like the
+    reference; ``compute_returns`` / ``compute_cost_returns`` run ``spo_gae_masked``; ``whole_batch_sample`` is
+    ``feed_forward_generator`` with ``num_mini_batch = 1`` (the yaml's value): one sample holding every row in a random order."""
+
+    def __init__(self, config, obs_dim, share_obs_dim, act_dim, device):
+        self.episode_length, self.n_rollout_threads = int(config["episode_length"]), int(config["n_rollout_threads"])
+        self.gamma, self.gae_lambda = float(config["gamma"]), float(config["gae_lambda"])
+        self.device = torch.device(device)
+        T, N = self.episode_length, self.n_rollout_threads
+
+        def z(*shape):
+            return torch.zeros(*shape, dtype=torch.float32, device=self.device)
+        self.aver_episode_costs = z(T + 1, N, obs_dim)      # buffer.py:240 (observation-shaped until the first return_aver_insert)
+        self.share_obs, self.obs = z(T + 1, N, share_obs_dim), z(T + 1, N, obs_dim)
+        self.value_preds, self.returns = z(T + 1, N, 1), z(T + 1, N, 1)
+        self.cost_preds, self.cost_returns = z(T + 1, N, 1), z(T + 1, N, 1)
+        self.actions, self.action_log_probs = z(T, N, act_dim), z(T, N, act_dim)
+        self.rewards, self.costs = z(T, N, 1), z(T, N, 1)
+        self.masks, self.active_masks = z(T + 1, N, 1) + 1, z(T + 1, N, 1) + 1
+        self.factor = z(T, N, 1) + 1
+        self.step = 0
+
+    def update_factor(self, factor):
+        self.factor.copy_(factor)
+
+    def return_aver_insert(self, aver_episode_costs):
+        self.aver_episode_costs = torch.as_tensor(aver_episode_costs, dtype=torch.float32).to(self.device).clone()
+
+    def insert(self, share_obs, obs, actions, action_log_probs, value_preds, rewards, masks, active_masks=None, costs=None, cost_preds=None):
+        s = self.step
+        self.share_obs[s + 1].copy_(share_obs)
+        self.obs[s + 1].copy_(obs)
+        self.actions[s].copy_(actions)
+        self.action_log_probs[s].copy_(action_log_probs)
+        self.value_preds[s].copy_(value_preds)
+        self.rewards[s].copy_(rewards)
+        self.masks[s + 1].copy_(masks)
+        if active_masks is not None:
+            self.active_masks[s + 1].copy_(active_masks)
+        if costs is not None:
+            self.costs[s].copy_(costs)
+        if cost_preds is not None:
+            self.cost_preds[s].copy_(cost_preds)
+        self.step = (s + 1) % self.episode_length
+
+    def after_update(self):
+        for t in (self.share_obs, self.obs, self.masks, self.active_masks):
+            t[0].copy_(t[-1])
+
+    def compute_returns(self, next_value, popart_mean, popart_sqrt_var):
+        """buffer.py:356-376 with the PopArt statistics as two floats (MultiAgentTrainer.popart_mean_sqrt_var)."""
+        self.value_preds[-1].copy_(next_value)
+        masked_gae_returns(self.rewards, self.value_preds, self.masks, popart_mean, popart_sqrt_var, self.gamma, self.gae_lambda,
+                           out=self.returns[:-1])
+
+    def compute_cost_returns(self, next_cost, popart_mean, popart_sqrt_var):
+        self.cost_preds[-1].copy_(next_cost)
+        masked_gae_returns(self.costs, self.cost_preds, self.masks, popart_mean, popart_sqrt_var, self.gamma, self.gae_lambda,
+                           out=self.cost_returns[:-1])
+
+    def whole_batch_sample(self, advantages, cost_adv, perm=None):
+        T, N = self.episode_length, self.n_rollout_threads
+        idx = torch.randperm(T * N, device=self.device) if perm is None else torch.as_tensor(perm).to(self.device)
+
+        def flat(t):
+            return t.reshape(-1, t.shape[-1])[idx].contiguous()
+        return dict(share_obs=flat(self.share_obs[:-1]), obs=flat(self.obs[:-1]), actions=flat(self.actions),
+                    value_preds=flat(self.value_preds[:-1]), returns=flat(self.returns[:-1]),
+                    old_action_log_probs=flat(self.action_log_probs), adv_targ=flat(advantages), factor=flat(self.factor),
+                    cost_preds=flat(self.cost_preds[:-1]), cost_returns=flat(self.cost_returns[:-1]), cost_adv_targ=flat(cost_adv),
+                    aver_episode_costs=self.aver_episode_costs)

@@ -68,8 +68,7 @@ class _Net:
 class MultiAgentNets:
     def __init__(self, actor_state, critic_state, cost_critic_state, device, layer_N=2, std_x_coef=1.0, std_y_coef=0.5):
         device = torch.device(device)
-        if device.type != "cuda":
-            raise L.SpoError("MultiAgentNets runs on a CUDA device only (no CPU fallback)")
+        self._require_cuda(device)
         self.device = device
         self.actor = _Net(actor_state, device, layer_N)
         self.critic = _Net(critic_state, device, layer_N)
@@ -77,6 +76,11 @@ class MultiAgentNets:
         self.act_dim = self.actor.p["act.action_out.fc_mean.weight"].shape[0]
         self.std_x_coef, self.std_y_coef = float(std_x_coef), float(std_y_coef)
         self._work = {}
+
+    @staticmethod
+    def _require_cuda(device):
+        if device.type != "cuda":
+            raise L.SpoError("MultiAgentNets runs on a CUDA device only (no CPU fallback)")
 
     def _buffers(self, n, H):
         key = (n, H)
@@ -96,7 +100,7 @@ class MultiAgentNets:
         """(values [N,1], actions [N,A], action_log_probs [N,A], cost_preds [N,1]) like MAPPO_L_Policy.get_actions.
         ``eps`` [N,A]: the standard-normal draws to use (torch.randn on the device when omitted and not deterministic)."""
         for t in (cent_obs, obs):
-            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            if not (t.device.type == self.device.type and t.dtype == torch.float32 and t.is_contiguous()):   # self.device is CUDA (constructor)
                 raise L.SpoError("MultiAgentNets needs contiguous fp32 CUDA tensors")
         n, A, net = obs.shape[0], self.act_dim, self.actor
         feat = net.features(obs, self._buffers(n, net.H))
@@ -111,6 +115,21 @@ class MultiAgentNets:
                 L.ptr(logp), L.stream())
         return self._value(self.critic, cent_obs), actions, logp, self._value(self.cost_critic, cent_obs)
 
+
+    def evaluate_actions(self, obs, actions):
+        """Per-dimension log-probabilities of given actions under the current actor (MultiAgentActor.evaluate_actions,
+        model.py:270-296 -> act.py:62-77), as the runner needs them for the cross-agent factor (mappolag.py:474-497): the mean
+        from the forward kernels, then Normal.log_prob's own formula element-wise on the device."""
+        n, A, net = obs.shape[0], self.act_dim, self.actor
+        feat = net.features(obs, self._buffers(n, net.H))
+        mean = torch.empty(n, A, dtype=torch.float32, device=self.device)
+        _launch("spo_ma_head", L.ptr(feat), n, net.H, L.ptr(net.p["act.action_out.fc_mean.weight"]), L.ptr(net.p["act.action_out.fc_mean.bias"]),
+                A, L.ptr(net.p["act.action_out.log_std"]), self.std_x_coef, self.std_y_coef, None, L.ptr(mean), None, L.stream())
+        std = torch.sigmoid(net.p["act.action_out.log_std"] / self.std_x_coef) * self.std_y_coef
+        return -((actions - mean) ** 2) / (2 * std ** 2) - std.log() - _LOG_SQRT_2PI
+
+
+_LOG_SQRT_2PI = 0.9189385332046727      # math.log(math.sqrt(2 * math.pi)), torch.distributions.Normal.log_prob
 
 # the 18 positions of the sample tuple MAPPO_L_Trainer.ppo_update unpacks (mappolag.py:137-141)
 _SAMPLE_KEYS = ("share_obs", "obs", "rnn_states", "rnn_states_critic", "actions", "value_preds", "returns", "masks", "active_masks",
@@ -233,8 +252,8 @@ class MultiAgentTrainer:
         cost_preds, cost_returns, cost_adv = dv_(sample["cost_preds"], 1), dv_(sample["cost_returns"], 1), dv_(sample["cost_adv_targ"], 1)
         aver_costs = dv_(sample["aver_episode_costs"], 1)
         n, A = obs.shape[0], nets.act_dim
-        if aver_costs.numel() != n:
-            raise L.SpoError("aver_episode_costs must hold one value per row")
+        if aver_costs.numel() != n:      # the reference only uses aver_episode_costs.mean() (mappolag.py:170); its buffer field is not [n]
+            aver_costs = aver_costs.mean().expand(n).contiguous()
 
         # ---- actor: surrogate on the product of the per-dimension ratios, Lagrangian-mixed advantage ----
         net = nets.actor
@@ -260,3 +279,34 @@ class MultiAgentTrainer:
         value_loss, critic_grad_norm = self._critic_update(nets.critic, share_obs, value_preds, returns, self._ws(n, nets.critic))
         cost_loss, cost_grad_norm = self._critic_update(nets.cost_critic, share_obs, cost_preds, cost_returns, self._ws(n, nets.cost_critic))
         return value_loss, critic_grad_norm, scal[0], scal[1], actor_grad_norm, imp, cost_loss, cost_grad_norm
+
+
+    # ---- MAPPO_L_Trainer.train (mappolag.py:200-234) ----
+    def popart_mean_sqrt_var(self):
+        """(mean, sqrt(var)) of the PopArt normaliser as host floats (popart.py:64-74): one device -> host copy of 3 floats."""
+        st = self.popart_state.cpu()
+        den = st[2].clamp(min=self.popart_eps)
+        mean, mean_sq = st[0] / den, st[1] / den
+        var = (mean_sq - mean ** 2).clamp(min=1e-2)
+        return float(mean), float(torch.sqrt(var))
+
+    def train(self, buf, perms=None):
+        """learning_iters whole-batch updates on a SeparatedReplayBuffer: advantages = returns - denormalised predictions,
+        standardised by the mean / unbiased std over the entries (the reference writes NaN into inactive entries and then
+        takes torch.mean, so a buffer with any inactive entry yields NaN advantages there too -- reproduced).  ``perms``: the row
+        orders to use (one per iteration; torch.randperm on the device when omitted)."""
+        mean, sd = self.popart_mean_sqrt_var()
+
+        def standardise(ret, pred):
+            adv = ret[:-1] - (pred[:-1] * sd + mean)
+            copy = adv.clone()
+            copy[buf.active_masks[:-1] == 0.0] = float("nan")
+            return (adv - torch.mean(copy)) / (torch.std(copy) + 1e-8)
+        advantages = standardise(buf.returns, buf.value_preds)
+        cost_adv = standardise(buf.cost_returns, buf.cost_preds)
+        out = None
+        for it in range(int(self.cfg["learning_iters"])):
+            perm = None if perms is None else perms[it]
+            out = self.ppo_update(buf.whole_batch_sample(advantages, cost_adv, perm))
+        return out
+

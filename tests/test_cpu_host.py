@@ -352,3 +352,129 @@ def test_multi_agent_net_packing_and_no_cpu_path():
     with pytest.raises(L.SpoError, match="CUDA"):
         MultiAgentNets(st, st, st, "cpu")
 
+
+
+# ---- host orchestration of the multi-agent path, with the C-ABI emulated on the CPU (tests/ma_emulator.py: test infrastructure) ----
+def _ma_small_state(g, din, H, A, head):
+    st = {"base.feature_norm.weight": 1 + 0.1 * torch.randn(din, generator=g), "base.feature_norm.bias": 0.1 * torch.randn(din, generator=g)}
+    dims = [din, H, H, H]
+    for li, name in enumerate(("fc1", "fc2.0", "fc2.1")):
+        st[f"base.mlp.{name}.0.weight"] = torch.randn(H, dims[li], generator=g) * (1.4 / dims[li] ** 0.5)
+        st[f"base.mlp.{name}.0.bias"] = 0.1 * torch.randn(H, generator=g)
+        st[f"base.mlp.{name}.2.weight"] = 1 + 0.1 * torch.randn(H, generator=g)
+        st[f"base.mlp.{name}.2.bias"] = 0.1 * torch.randn(H, generator=g)
+    if head == "actor":
+        st["act.action_out.log_std"] = torch.ones(A) + 0.3 * torch.randn(A, generator=g)
+        st["act.action_out.fc_mean.weight"] = torch.randn(A, H, generator=g) * 0.05
+        st["act.action_out.fc_mean.bias"] = 0.1 * torch.randn(A, generator=g)
+    else:
+        st["v_out.weight"] = torch.randn(1, H, generator=g) * 0.1
+        st["v_out.bias"] = 0.1 * torch.randn(1, generator=g)
+    return st
+
+
+def test_multi_agent_trainer_call_sequence_vs_oracle(golden, monkeypatch):
+    """MultiAgentTrainer.ppo_update driven through the emulated C-ABI: the sequence of entry points, the buffers handed to each
+    and the partial-sum layouts the host relies on reproduce the oracle's update (gradients, returned quantities, lamda, PopArt,
+    weights after two updates).  The kernels behind the real entry points are checked on the GPU by test_ma_ppo_update_vs_oracle."""
+    import ma_emulator
+    from oracle import ma_oracle as MA
+    from safepo.common.ma_model import MultiAgentNets, MultiAgentTrainer
+    ma_emulator.install(monkeypatch)
+    cfg = dict(golden("ma_update")["ma_update"]["cfg"])
+    cfg["entropy_coef"] = 0.01
+    N, D, DS, A, H = 300, 10, 14, 3, 32
+    g = torch.Generator().manual_seed(4)
+    sa, sc, sk = _ma_small_state(g, D, H, A, "actor"), _ma_small_state(g, DS, H, A, "critic"), _ma_small_state(g, DS, H, A, "critic")
+    oa, oc, ok_ = MA.OracleMANet(sa), MA.OracleMANet(sc), MA.OracleMANet(sk)
+    obs, share = torch.randn(N, D, generator=g) * 2 + 0.5, torch.randn(N, DS, generator=g) * 3
+    with torch.no_grad():
+        dist = MA.ma_actor_dist(oa, obs)
+        actions = dist.mean + dist.stddev * torch.randn(N, A, generator=g)
+        logp = dist.log_prob(actions)
+        v0, k0 = MA.ma_critic_value(oc, share), MA.ma_critic_value(ok_, share)
+    sample = dict(share_obs=share, obs=obs, actions=actions, value_preds=v0 + 0.1 * torch.randn(N, 1, generator=g),
+                  returns=torch.randn(N, 1, generator=g) * 4 + 1, old_action_log_probs=logp + 0.05 * torch.randn(N, A, generator=g),
+                  adv_targ=torch.randn(N, 1, generator=g), factor=torch.rand(N, 1, generator=g) + 0.5,
+                  cost_preds=k0 + 0.1 * torch.randn(N, 1, generator=g), cost_returns=torch.randn(N, 1, generator=g).abs() * 30,
+                  cost_adv_targ=torch.randn(N, 1, generator=g), aver_episode_costs=torch.rand(7, 5, generator=g) * 60)   # only its mean is used
+    otr = MA.OracleMATrainer(oa, oc, ok_, cfg)
+    nets = MultiAgentNets(sa, sc, sk, "cpu", layer_N=cfg["layer_N"], std_x_coef=cfg["std_x_coef"], std_y_coef=cfg["std_y_coef"])
+    tr = MultiAgentTrainer(nets, cfg)
+    got_v, got_a, got_lp, got_k = nets.get_actions(share, obs, deterministic=True)
+    assert torch.allclose(got_v, v0, atol=2e-6) and torch.allclose(got_a, dist.mean, atol=2e-6) and torch.allclose(got_k, k0, atol=2e-6)
+    assert torch.allclose(nets.evaluate_actions(obs, actions), logp, atol=1e-5)
+    names = ("value_loss", "critic_grad_norm", "policy_loss", "dist_entropy", "actor_grad_norm", "imp_weights", "cost_loss", "cost_grad_norm")
+    for it in range(2):
+        want = otr.ppo_update(sample)
+        got = dict(zip(names, tr.ppo_update(sample)))
+        for k in names:
+            assert torch.allclose(got[k].reshape(-1), torch.as_tensor(want[k]).reshape(-1), rtol=2e-4, atol=2e-6), (it, k, got[k], want[k])
+        for net, onet, nk in ((nets.actor, oa, "actor_grad_norm"), (nets.critic, oc, "critic_grad_norm"), (nets.cost_critic, ok_, "cost_grad_norm")):
+            coef = min(1.0, float(cfg["max_grad_norm"]) / (float(want[nk]) + 1e-6))
+            for k, pt in onet.p.items():
+                wg = pt.grad / coef
+                assert float((net.g[k] - wg).abs().max()) <= 1e-4 * float(wg.abs().max()) + 1e-7, (it, k)
+                assert float((net.p[k] - pt.detach()).abs().max()) < 2e-5, (it, k)
+        assert abs(float(tr.lamda_lagr) - float(otr.lamda_lagr)) < 1e-6
+        for got_s, want_s in zip(tr.popart_state, (otr.popart.running_mean, otr.popart.running_mean_sq, otr.popart.debiasing_term)):
+            assert abs(float(got_s) - float(want_s)) <= 1e-5 * abs(float(want_s)) + 1e-12
+
+
+def test_multi_agent_runner_iteration_vs_oracle(golden, monkeypatch):
+    """safepo/multi_agent/mappolag.py Runner (collect / insert / compute / train) with SeparatedReplayBuffer and
+    MultiAgentTrainer.train through the emulated C-ABI, against the oracle's runner (itself pinned bit for bit to the reference's
+    Runner by tests/golden/ma_epoch.pt) on the fixture's environment stream with the same injected draws: two iterations of two
+    agents -- buffers after compute(), the cross-agent factor, lamda, PopArt and all weights after train()."""
+    import ma_emulator
+    from oracle import ma_oracle as MA
+    from safepo.common.ma_model import MultiAgentNets
+    from safepo.multi_agent.mappolag import Runner
+    ma_emulator.install(monkeypatch)
+    c = golden("ma_epoch")["ma_epoch"]
+    T, N, D, DS, A, H, NA = c["dims"]
+    cfg = dict(c["cfg"])
+    onets = [tuple(MA.OracleMANet(st[n], layer_N=cfg["layer_N"]) for n in ("actor", "critic", "cost_critic")) for st in c["init"]]
+    orun = MA.OracleMARunner(onets, cfg, T, N, D, DS, A)
+    nets = [MultiAgentNets(st["actor"], st["critic"], st["cost_critic"], "cpu", layer_N=cfg["layer_N"], std_x_coef=cfg["std_x_coef"],
+                           std_y_coef=cfg["std_y_coef"]) for st in c["init"]]
+    run = Runner(nets, cfg, D, DS, A)
+    orun.warmup(c["obs0"], c["share_obs0"])
+    run.warmup(c["obs0"], c["share_obs0"])
+    g = torch.Generator().manual_seed(9)
+
+    def near(a, b, tol=2e-5):
+        return float((a - b).abs().max()) <= tol * (1.0 + float(b.abs().max()))
+    for it in range(2):
+        for step in range(T):
+            s = c["stream"][it][step]
+            eps = [torch.randn(N, A, generator=g) for _ in range(NA)]
+            ov, oact, olp, ocp = orun.collect(step, eps=eps)
+            v, act, lp, cp = run.collect(step, eps=eps)
+            assert near(v, ov) and near(cp, ocp) and all(near(act[a], oact[a]) and near(lp[a], olp[a]) for a in range(NA)), (it, step)
+            orun.insert(s["obs"], s["share_obs"], s["rewards"], s["costs"], s["dones"], ov, oact, olp, ocp)
+            run.insert(s["obs"], s["share_obs"], s["rewards"], s["costs"], s["dones"], v, act, lp, cp)
+        orun.compute()
+        run.compute()
+        for a in range(NA):
+            for k in ("returns", "cost_returns", "value_preds", "cost_preds", "masks", "active_masks", "rewards", "costs", "actions", "obs", "share_obs"):
+                assert near(getattr(run.buffer[a], k), getattr(orun.buffer[a], k), 5e-5), (it, a, k)
+        order = torch.randperm(NA, generator=g)
+        perms = [[torch.randperm(T * N, generator=g) for _ in range(cfg["learning_iters"])] for _ in range(NA)]
+        orun.train(agent_order=order, perms=perms)
+        assert run.train(agent_order=order, perms=perms) == [int(a) for a in order]
+        for a in range(NA):
+            assert near(run.buffer[a].factor, orun.buffer[a].factor, 1e-4), (it, a)
+            assert abs(float(run.trainer[a].lamda_lagr) - float(orun.trainer[a].lamda_lagr)) < 1e-6
+            pop = orun.trainer[a].popart
+            for got_s, want_s in zip(run.trainer[a].popart_state, (pop.running_mean, pop.running_mean_sq, pop.debiasing_term)):
+                assert abs(float(got_s) - float(want_s)) <= 1e-5 * abs(float(want_s)) + 1e-12
+            for net, onet in zip((nets[a].actor, nets[a].critic, nets[a].cost_critic), onets[a]):
+                for k, pt in onet.p.items():
+                    assert float((net.p[k] - pt.detach()).abs().max()) < 5e-5, (it, a, k)
+            assert near(run.buffer[a].obs[0], orun.buffer[a].obs[0]) and near(run.buffer[a].masks[0], orun.buffer[a].masks[0])    # after_update
+        if it == 0:
+            run.return_aver_cost(torch.tensor(c["aver_cost_after_first"]))
+            for b in orun.buffer:
+                b.aver_episode_costs = torch.tensor(c["aver_cost_after_first"])
+    assert any(bool((run.buffer[a].factor != 1).any()) for a in range(NA))

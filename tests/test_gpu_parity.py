@@ -985,3 +985,67 @@ def test_ma_ppo_update_vs_oracle(golden, N, D, DS, A, H):
                 assert err < 0.05 * lr + 1e-6, (it, k, err, lr)
     print(f"\nMA ppo_update N={N} D={D} H={H}: worst relative gradient error per tensor {max(worst.values()):.2e}")
 
+
+
+@pytest.mark.gpu
+def test_ma_runner_iteration_vs_oracle(golden):
+    """safepo/multi_agent/mappolag.py Runner on the device -- collect / insert / compute / train of two agents with
+    SeparatedReplayBuffer, spo_gae_masked, MultiAgentTrainer.train and the cross-agent factor -- against the oracle's runner
+    (pinned bit for bit to the reference's Runner by tests/golden/ma_epoch.pt) on a synthetic environment stream with the same
+    injected draws: two iterations.  (The same host code runs against an emulated C-ABI in the CPU suite:
+    tests/test_cpu_host.py::test_multi_agent_runner_iteration_vs_oracle.)"""
+    from oracle import ma_oracle as MA
+    from safepo.common.ma_model import MultiAgentNets
+    from safepo.multi_agent.mappolag import Runner
+    dev = _cuda()
+    cfg = dict(golden("ma_epoch")["ma_epoch"]["cfg"])
+    T, N, D, DS, A, H, NA = 4, 24, 10, 14, 3, 128, 2
+    cfg.update(episode_length=T, n_rollout_threads=N)
+    g = torch.Generator().manual_seed(31)
+    states = [dict(actor=_ma_state(g, D, H, A, "actor"), critic=_ma_state(g, DS, H, A, "critic"), cost_critic=_ma_state(g, DS, H, A, "critic"))
+              for _ in range(NA)]
+    onets = [tuple(MA.OracleMANet(st[n], layer_N=cfg["layer_N"]) for n in ("actor", "critic", "cost_critic")) for st in states]
+    orun = MA.OracleMARunner(onets, cfg, T, N, D, DS, A)
+    nets = [MultiAgentNets(st["actor"], st["critic"], st["cost_critic"], dev, layer_N=cfg["layer_N"], std_x_coef=cfg["std_x_coef"],
+                           std_y_coef=cfg["std_y_coef"]) for st in states]
+    run = Runner(nets, cfg, D, DS, A)
+    obs0, share0 = torch.randn(N, NA, D, generator=g) * 2 + 0.5, torch.randn(N, NA, DS, generator=g) * 3
+    orun.warmup(obs0, share0)
+    run.warmup(obs0, share0)
+
+    def near(a, b, tol):
+        a, b = a.detach().cpu(), b.detach().cpu()
+        return float((a - b).abs().max()) <= tol * (1.0 + float(b.abs().max()))
+    for it in range(2):
+        for step in range(T):
+            eps = [torch.randn(N, A, generator=g) for _ in range(NA)]
+            ov, oact, olp, ocp = orun.collect(step, eps=eps)
+            v, act, lp, cp = run.collect(step, eps=eps)
+            assert near(v, ov, 5e-5) and near(cp, ocp, 5e-5) and all(near(act[a], oact[a], 5e-5) and near(lp[a], olp[a], 5e-5) for a in range(NA)), (it, step)
+            obs, share = torch.randn(N, NA, D, generator=g) * 2 + 0.5, torch.randn(N, NA, DS, generator=g) * 3
+            rewards, costs = torch.randn(N, NA, 1, generator=g), (torch.rand(N, NA, 1, generator=g) < 0.3).float()
+            dones = (torch.rand(N, generator=g) < 0.2)[:, None].expand(N, NA).clone()
+            # both sides store the ORACLE's actions / predictions, so that the buffers only differ by what is under test
+            orun.insert(obs, share, rewards, costs, dones, ov, oact, olp, ocp)
+            run.insert(obs, share, rewards, costs, dones, ov.to(dev), [x.to(dev) for x in oact], [x.to(dev) for x in olp], ocp.to(dev))
+        orun.compute()
+        run.compute()
+        for a in range(NA):
+            for k in ("returns", "cost_returns", "value_preds", "cost_preds", "masks", "active_masks"):
+                assert near(getattr(run.buffer[a], k), getattr(orun.buffer[a], k), 1e-4), (it, a, k)
+        order = torch.randperm(NA, generator=g)
+        perms = [[torch.randperm(T * N, generator=g) for _ in range(cfg["learning_iters"])] for _ in range(NA)]
+        orun.train(agent_order=order, perms=perms)
+        assert run.train(agent_order=order, perms=perms) == [int(a) for a in order]
+        torch.cuda.synchronize()
+        for a in range(NA):
+            assert near(run.buffer[a].factor, orun.buffer[a].factor, 5e-4), (it, a)
+            assert abs(float(run.trainer[a].lamda_lagr) - float(orun.trainer[a].lamda_lagr)) < 1e-5
+            pop = orun.trainer[a].popart
+            for got_s, want_s in zip(run.trainer[a].popart_state.cpu(), (pop.running_mean, pop.running_mean_sq, pop.debiasing_term)):
+                assert abs(float(got_s) - float(want_s)) <= 1e-4 * abs(float(want_s)) + 1e-12
+            for net, onet, lr in zip((nets[a].actor, nets[a].critic, nets[a].cost_critic), onets[a], (cfg["actor_lr"], cfg["critic_lr"], cfg["critic_lr"])):
+                for k, pt in onet.p.items():
+                    err = float((net.p[k].cpu() - pt.detach()).abs().max())
+                    assert err < 0.2 * lr + 2e-6, (it, a, k, err)       # a wrong gradient sign would be 2 lr per update
+    assert any(bool((run.buffer[a].factor != 1).any()) for a in range(NA))
