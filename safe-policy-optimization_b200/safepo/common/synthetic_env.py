@@ -15,6 +15,7 @@ staggered per env), optional Bernoulli termination.
 from __future__ import annotations
 
 import numpy as np
+import torch
 
 TASK_DIMS = {
     # obs_dim, act_dim of the tasks BASELINE.json names (upstream Safety-Gymnasium values)
@@ -91,3 +92,40 @@ def make_synthetic_env(num_envs, env_id="SafetyPointGoal1-v0", seed=0, episode_l
     env = SyntheticVecEnv(num_envs, obs_dim, act_dim, episode_len=episode_len,
                           seed=0 if seed is None else seed, **kw)
     return env, env.observation_space, env.action_space
+
+
+class SyntheticMultiAgentEnv:
+    """A synthetic multi-agent vector environment with the interface the reference's multi-agent Runner uses
+    (safepo/multi_agent/mappolag.py:300-345: ``reset() -> obs, share_obs, _`` and ``step(actions) -> obs, share_obs, rewards,
+    costs, dones, infos, _``), on the device: observations ~ N(0, 1), rewards ~ 0.01 N(0, 1), costs ~ Bernoulli(0.05) like the
+    single-agent synthetic stream, all agents of an environment finish together every ``episode_len`` steps."""
+
+    def __init__(self, num_envs, num_agents, obs_dim, share_obs_dim, act_dim, episode_len, seed, device):
+        self.num_envs, self.num_agents = int(num_envs), int(num_agents)
+        self.obs_dim, self.share_obs_dim, self.act_dim = int(obs_dim), int(share_obs_dim), int(act_dim)
+        self.episode_len, self.device = int(episode_len), torch.device(device)
+        self._g = torch.Generator(device=self.device).manual_seed(int(seed))
+        self._t = 0
+
+    def _obs(self):
+        n, a = self.num_envs, self.num_agents
+        return (torch.randn(n, a, self.obs_dim, generator=self._g, device=self.device),
+                torch.randn(n, a, self.share_obs_dim, generator=self._g, device=self.device))
+
+    def reset(self):
+        self._t = 0
+        obs, share_obs = self._obs()
+        return obs, share_obs, None
+
+    def step(self, actions):
+        if len(actions) != self.num_agents or any(a.shape != (self.num_envs, self.act_dim) for a in actions):
+            raise ValueError("one [num_envs, act_dim] action tensor per agent expected")
+        n, a = self.num_envs, self.num_agents
+        self._t += 1
+        obs, share_obs = self._obs()
+        rewards = 0.01 * torch.randn(n, a, 1, generator=self._g, device=self.device)
+        costs = (torch.rand(n, a, 1, generator=self._g, device=self.device) < 0.05).float()
+        done = self._t % self.episode_len == 0
+        dones = torch.full((n, a), bool(done), dtype=torch.bool, device=self.device)
+        return obs, share_obs, rewards, costs, dones, None, None
+

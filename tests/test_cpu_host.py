@@ -478,3 +478,52 @@ def test_multi_agent_runner_iteration_vs_oracle(golden, monkeypatch):
             for b in orun.buffer:
                 b.aver_episode_costs = torch.tensor(c["aver_cost_after_first"])
     assert any(bool((run.buffer[a].factor != 1).any()) for a in range(NA))
+
+
+def test_multi_agent_run_loop_and_cli_through_emulated_abi(monkeypatch, tmp_path):
+    """Runner.run (the loop of mappolag.py:300-373) on the synthetic multi-agent environment and the module's CLI, host logic only
+    (emulated C-ABI): episode sums and finished-episode means, the average episode cost handed to the buffers, per-agent log
+    columns, weights that move, a progress.csv; the reference's initialisation (orthogonal weights, zero biases, log_std = x_coef)."""
+    import ma_emulator
+    from safepo.common.ma_model import MultiAgentNets
+    from safepo.common.synthetic_env import SyntheticMultiAgentEnv
+    from safepo.multi_agent import mappolag as M
+    ma_emulator.install(monkeypatch)
+    g = torch.Generator().manual_seed(0)
+    st = M.init_state(10, 32, 2, "actor", act_dim=3, generator=g)
+    w = st["base.mlp.fc2.0.0.weight"]
+    gain2 = float(torch.nn.init.calculate_gain("relu")) ** 2
+    assert torch.allclose(w @ w.t(), gain2 * torch.eye(32), atol=1e-4)                   # orthogonal with the ReLU gain
+    assert float(st["base.mlp.fc1.0.bias"].abs().max()) == 0.0 and torch.equal(st["act.action_out.log_std"], torch.ones(3))
+    assert float((st["act.action_out.fc_mean.weight"] @ st["act.action_out.fc_mean.weight"].t() - 1e-4 * torch.eye(3)).abs().max()) < 1e-6
+    cfg = dict(M.DEFAULT_CONFIG, episode_length=4, n_rollout_threads=6, hidden_size=32, learning_iters=2, entropy_coef=0.01)
+    T, N, D, DS, A, NA = 4, 6, 10, 14, 3, 2
+
+    def build(seed):
+        gg = torch.Generator().manual_seed(seed)
+        nets = [MultiAgentNets(M.init_state(D, 32, 2, "actor", A, generator=gg), M.init_state(DS, 32, 2, "critic", generator=gg),
+                               M.init_state(DS, 32, 2, "critic", generator=gg), "cpu") for _ in range(NA)]
+        return M.Runner(nets, cfg, D, DS, A), SyntheticMultiAgentEnv(N, NA, D, DS, A, episode_len=3, seed=seed, device="cpu")
+    run, envs = build(1)
+    w0 = run.nets[0].actor.flat.clone()
+    torch.manual_seed(5)
+    rows = run.run(envs, 3)
+    assert [r["Train/TotalSteps"] for r in rows] == [24, 48, 72]
+    assert all("Metrics/EpCost" in r and "Loss/Loss_actor/agent1" in r and "Misc/Lagrange/agent0" in r for r in rows)
+    assert run.buffer[0].aver_episode_costs.numel() == 1                                  # replaced by the finished episodes' mean cost
+    assert abs(float(run.buffer[0].aver_episode_costs) - rows[-1]["Metrics/EpCost"]) < 1e-6
+    assert 0.0 <= rows[0]["Metrics/EpCost"] <= 3.0                                        # episodes of 3 steps, cost in {0, 1} per step
+    assert float((run.nets[0].actor.flat - w0).abs().max()) > 0
+    assert torch.equal(run.buffer[1].obs[0], run.buffer[1].obs[-1])                       # after_update rolled the last observation over
+    run2, envs2 = build(1)
+    torch.manual_seed(5)
+    rows2 = run2.run(envs2, 3)
+    drop = ("Time/Total", "Time/FPS")
+    assert [{k: v for k, v in r.items() if k not in drop} for r in rows] == [{k: v for k, v in r.items() if k not in drop} for r in rows2]
+    out = M.main(["--num-envs", "6", "--obs-dim", "10", "--share-obs-dim", "14", "--act-dim", "3", "--hidden-size", "32", "--iterations", "2",
+                  "--episode-len", "5", "--device", "cpu", "--log-dir", str(tmp_path / "exp" / "synthetic" / "mappolag" / "seed0")])
+    assert len(out) == 2
+    csv_text = (tmp_path / "exp" / "synthetic" / "mappolag" / "seed0" / "progress.csv").read_text()
+    assert "Loss/Loss_reward_critic/agent0" in csv_text and len(csv_text.strip().splitlines()) == 3
+    with pytest.raises(ValueError):
+        envs.step([torch.zeros(N, A)])                                                     # one action tensor per agent

@@ -1049,3 +1049,41 @@ def test_ma_runner_iteration_vs_oracle(golden):
                     err = float((net.p[k].cpu() - pt.detach()).abs().max())
                     assert err < 0.2 * lr + 2e-6, (it, a, k, err)       # a wrong gradient sign would be 2 lr per update
     assert any(bool((run.buffer[a].factor != 1).any()) for a in range(NA))
+
+
+@pytest.mark.gpu
+def test_ma_run_loop_on_device(tmp_path):
+    """Runner.run on the synthetic multi-agent environment on the device (the loop's logic is checked against expectations in the
+    CPU suite through the emulated C-ABI): three iterations with episodes finishing inside them -- finite losses, weights that
+    move, the finished episodes' mean cost handed to the buffers, identical log rows for identical seeds."""
+    from safepo.common.ma_model import MultiAgentNets
+    from safepo.common.synthetic_env import SyntheticMultiAgentEnv
+    from safepo.multi_agent import mappolag as M
+    dev = _cuda()
+    cfg = dict(M.DEFAULT_CONFIG, episode_length=4, n_rollout_threads=48, hidden_size=128, learning_iters=2, entropy_coef=0.01)
+    T, N, D, DS, A, NA = 4, 48, 22, 30, 5, 2
+
+    def build(seed):
+        gg = torch.Generator().manual_seed(seed)
+        nets = [MultiAgentNets(M.init_state(D, 128, 2, "actor", A, generator=gg), M.init_state(DS, 128, 2, "critic", generator=gg),
+                               M.init_state(DS, 128, 2, "critic", generator=gg), dev) for _ in range(NA)]
+        return M.Runner(nets, cfg, D, DS, A), SyntheticMultiAgentEnv(N, NA, D, DS, A, episode_len=3, seed=seed, device=dev)
+    run, envs = build(2)
+    w0 = run.nets[1].critic.flat.clone()
+    torch.manual_seed(7)
+    torch.cuda.manual_seed(7)
+    rows = run.run(envs, 3)
+    assert [r["Train/TotalSteps"] for r in rows] == [T * N, 2 * T * N, 3 * T * N]
+    for r in rows:
+        assert all(np.isfinite(v) for v in r.values()), r
+        assert "Metrics/EpCost" in r and 0.0 <= r["Metrics/EpCost"] <= 3.0
+    assert float((run.nets[1].critic.flat - w0).abs().max()) > 0
+    assert run.buffer[0].aver_episode_costs.numel() == 1 and abs(float(run.buffer[0].aver_episode_costs) - rows[-1]["Metrics/EpCost"]) < 1e-6
+    run2, envs2 = build(2)
+    torch.manual_seed(7)
+    torch.cuda.manual_seed(7)
+    rows2 = run2.run(envs2, 3)
+    for r, r2 in zip(rows, rows2):       # every kernel sums in a fixed order: the same seeds give the same numbers
+        for k, v in r.items():
+            if k not in ("Time/Total", "Time/FPS"):
+                assert abs(v - r2[k]) <= 1e-6 * (1.0 + abs(v)), (k, v, r2[k])
